@@ -1,0 +1,184 @@
+/*
+ * rebert_b200.h — C ABI of the B200-native recommendation scoring path.
+ *
+ * This is the drop-in boundary for robot-ebert's scoring code.  The reference has no FFI of its
+ * own (it is pure Python); the entry points below replace, one for one, the pandas / scikit-learn
+ * expressions on its hot path.  Citations are into the reference tree (src/backend/app/...):
+ *
+ *   catalog load          constants.py:55-56   -> rebert_catalog_store_rows, rebert_catalog_norms
+ *   E.loc[liked] + mean   lib.py:51-52         -> rebert_profile_accumulate, rebert_profile_finalize
+ *   cosine_similarity     lib.py:51, :105      -> rebert_query_normalize + rebert_gemv_topk (one query),
+ *                                                 rebert_gemm_* (batched), rebert_score_subset (:105 subset form)
+ *   .loc[unrated]         lib.py:48,55         -> rebert_filter_t (applied inside the scoring kernels)
+ *   sort_values()[:k]     lib.py:55            -> fused in rebert_gemv_topk / rebert_gemm_filter,
+ *                                                 finished by rebert_finalize_topk / rebert_merge_topk
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, POD structs.  No torch types, no exceptions across the boundary.
+ *   - Every function returns REBERT_OK (0) or a negative rebert_status; rebert_last_error() gives a
+ *     thread-local message for the last failure on the calling thread.
+ *   - Unless a parameter says "host", pointers are DEVICE pointers owned by the caller.  The
+ *     library allocates no device memory: scratch space is a caller-provided workspace whose size
+ *     comes from the matching *_workspace_bytes function.
+ *   - All work is enqueued on the caller's stream; functions return without synchronising, except
+ *     the *_host convenience entry points, which say so.
+ *   - Re-entrant: no global mutable state; concurrent calls on one immutable catalog are safe as
+ *     long as each call has its own stream + workspace + outputs.
+ *   - Row ids: "local" = index into this shard's arrays; "global" = local + row_base.
+ *   - Result order everywhere: (score descending, global row ascending).  With catalog rows stored
+ *     in tmdb_id-string order this is the order lib.py:55,63 guarantees.
+ */
+#ifndef REBERT_B200_H
+#define REBERT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REBERT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define REBERT_API __attribute__((visibility("default")))
+#else
+#define REBERT_API
+#endif
+
+typedef enum {
+    REBERT_OK = 0,
+    REBERT_ERR_INVALID = -1,      /* bad argument (null pointer, size, alignment, k out of range) */
+    REBERT_ERR_UNSUPPORTED = -2,  /* shape / dtype combination this build has no kernel for */
+    REBERT_ERR_WORKSPACE = -3,    /* workspace too small */
+    REBERT_ERR_CUDA = -4,         /* a CUDA runtime call failed; message holds cudaGetErrorString */
+    REBERT_ERR_DEVICE = -5        /* not an sm_100 device */
+} rebert_status;
+
+typedef enum { REBERT_F32 = 0, REBERT_BF16 = 1 } rebert_dtype;
+
+typedef void* rebert_stream;      /* a cudaStream_t */
+
+/* One HBM-resident catalog shard (replaces the DataFrame at constants.py:55-56).
+ * rows is row-major [n, ld]; ld >= d is the padded row stride from rebert_catalog_layout, padding
+ * columns are zero.  inv_norm / norm64 follow sklearn's normalize(): zero-norm rows use 1. */
+typedef struct {
+    const void*   rows;       /* [n, ld] of dtype */
+    const float*  inv_norm;   /* [n] fp32 1 / ||row||2 */
+    const double* norm64;     /* [n] fp64 ||row||2 (1 where the row is all zero) */
+    int64_t       n;          /* rows in this shard */
+    int64_t       row_base;   /* global row index of local row 0 */
+    int32_t       d;          /* logical columns */
+    int32_t       ld;         /* padded columns (elements) */
+    int32_t       dtype;      /* rebert_dtype */
+    int32_t       reserved;
+} rebert_catalog_t;
+
+/* Rows that may NOT be returned (lib.py:48,55 `unrated`), plus the optional C5 genre/year predicate.
+ * Any member may be NULL / 0.  A row is allowed iff it passes every non-null test. */
+typedef struct {
+    const uint32_t* exclude_bitmap;  /* [ceil(n/32)], local row r excluded iff bit (r & 31) of word r >> 5 is set */
+    const int32_t*  exclude_rows;    /* GLOBAL row ids, sorted ascending, unique */
+    int32_t         n_exclude;
+    uint32_t        genre_any;       /* keep rows with (genre_bits & genre_any) != 0 */
+    const uint32_t* genre_bits;      /* [n] local, or NULL */
+    const uint16_t* year;            /* [n] local, or NULL */
+    uint16_t        year_lo, year_hi;/* keep year_lo <= year <= year_hi */
+    uint32_t        reserved;
+} rebert_filter_t;
+
+/* ---- library ------------------------------------------------------------------------------ */
+REBERT_API int         rebert_abi_version(void);
+REBERT_API const char* rebert_last_error(void);
+/* REBERT_OK iff the current device is compute capability 10.x. */
+REBERT_API int         rebert_check_device(void);
+
+/* ---- catalog store (constants.py:55-56) --------------------------------------------------- */
+/* Padded row stride (elements) and bytes for an [n, d] catalog of `dtype`. */
+REBERT_API int rebert_catalog_layout(int64_t n, int32_t d, int32_t dtype, int32_t* ld, size_t* rows_bytes);
+/* Convert src fp32 [n, d] (dense, device) into stored rows [n, ld] of `dtype` (bf16: round-to-nearest-even),
+ * zero-filling the padding.  May be called per chunk with offset pointers. */
+REBERT_API int rebert_catalog_store_rows(const float* src, int64_t n, int32_t d, int32_t dtype, void* rows, int32_t ld,
+                              rebert_stream stream);
+/* Row norms of the STORED values: norm64[r] = sqrt(sum x^2) in fp64 (0 -> 1), inv_norm[r] = (float)(1/norm64[r]). */
+REBERT_API int rebert_catalog_norms(const void* rows, int64_t n, int32_t ld, int32_t dtype, float* inv_norm, double* norm64,
+                         rebert_stream stream);
+
+/* ---- query / profile (lib.py:51-52) ------------------------------------------------------- */
+/* b queries q[b, d] fp32 -> unit vectors: qn64 = q / ||q|| (fp64, zero norm -> 1), qn32 = (float) qn64; both [b, ld]. */
+REBERT_API int rebert_query_normalize(const float* q, int32_t b, int32_t d, int32_t ld, float* qn32, double* qn64,
+                           rebert_stream stream);
+/* Ragged CSR gather-sum over THIS shard's rows: for user u, sum64[u, :] += w * row / norm64[row] for every
+ * entry whose global row `col` lies in [row_base, row_base + n); wsum[u] += w for EVERY entry (so it is the
+ * same on all shards).  w == NULL means weight 1 (the reference's 1[rating >= 3.5]).  Outputs are overwritten. */
+REBERT_API int rebert_profile_accumulate(const rebert_catalog_t* cat, const int64_t* row_ptr, const int32_t* col, const float* w,
+                              int32_t b, double* sum64 /* [b, ld] */, double* wsum /* [b] */, rebert_stream stream);
+/* p64 = sum64 / wsum (the mean of unit rows, NOT re-normalised: lib.py:52), p32 = (float) p64, pbf16 optional. */
+REBERT_API int rebert_profile_finalize(const double* sum64, const double* wsum, int32_t b, int32_t ld, float* p32, double* p64,
+                            void* pbf16 /* [b, ld] bf16 or NULL */, rebert_stream stream);
+
+/* ---- single query: fused score + mask + top-k (lib.py:51-55, L = 1 or a prebuilt profile) -- */
+/* Candidate count the fast pass keeps for a request of k: a multiple of 32 >= k + margin; 0 if k is unsupported. */
+REBERT_API int32_t rebert_candidates_for_k(int32_t k);
+REBERT_API size_t  rebert_gemv_workspace_bytes(int64_t n, int32_t kc);
+/* Fast pass.  score(r) = <qn32, row r> * inv_norm[r] in fp32; keeps the kc best allowed rows of the shard.
+ * Output: cand_keys[kc] sorted best-first (packed (score, local row) keys; unused slots are 0). */
+REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, int32_t kc,
+                     void* workspace, size_t workspace_bytes, uint64_t* cand_keys, rebert_stream stream);
+/* Exact pass over the kc candidates: fp64 re-score with the oracle's formula (x/||x||, y/||y||, dot), order by
+ * (score desc, global row asc), write the best k.  out_count[0] = results written (<= k).
+ * out_margin[0] = (exact k-th score) - (fast score of the worst kept candidate) when the candidate list was
+ * full, else +inf: a caller proves the set exact by margin > eps and retries with more candidates otherwise. */
+REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* qn64, const uint64_t* cand_keys, int32_t kc,
+                         int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin,
+                         rebert_stream stream);
+
+/* ---- merge of per-shard results (lib.py:55 across shards) --------------------------------- */
+/* For each of b queries merge `lists` sorted result lists [lists, b, k] (rows, scores, counts[lists, b]) into the best k. */
+REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, const int32_t* counts, int32_t lists, int32_t b,
+                      int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_stream stream);
+
+/* ---- subset scoring for the search re-rank (lib.py:105-106) ------------------------------- */
+/* out[u, j] = <p64[u], row sub_rows[j]> / norm64 in fp64 for m candidate GLOBAL rows (all must be in this shard). */
+REBERT_API int rebert_score_subset(const rebert_catalog_t* cat, const double* p64, int32_t b, const int32_t* sub_rows, int32_t m,
+                        double* out /* [b, m] */, rebert_stream stream);
+
+/* ---- dense scores (test / diagnostics: the materialised matrix of lib.py:51) --------------- */
+/* out[u, r] = <q32[u], row r> * inv_norm[r], fp32, plain CUDA-core kernel independent of the fused paths. */
+REBERT_API int rebert_scores_dense(const rebert_catalog_t* cat, const float* q32, int32_t b, float* out /* [b, n] */,
+                        rebert_stream stream);
+
+/* ---- batched queries: tcgen05 bf16 GEMM with fused threshold filter (lib.py:51-55, many users) ---- */
+typedef struct {
+    int32_t b;            /* queries */
+    int32_t k;            /* results per query */
+    int32_t kc;           /* exact-pass candidates per query (from rebert_candidates_for_k) */
+    int32_t sample_rows;  /* catalog rows in the threshold sample (multiple of 256) */
+    int32_t sample_rank;  /* order statistic of the sample used as the threshold */
+    int32_t cand_cap;     /* per-query capacity of the filtered candidate buffer */
+} rebert_gemm_plan_t;
+REBERT_API int    rebert_gemm_plan(int64_t n, int32_t b, int32_t k, rebert_gemm_plan_t* plan);
+REBERT_API size_t rebert_gemm_workspace_bytes(const rebert_catalog_t* cat, const rebert_gemm_plan_t* plan);
+/* Whole batched path: sample -> per-query threshold -> full GEMM with fused scale + threshold filter -> per-query
+ * select -> fp64 re-score -> ordered top-k.  qbf16 [b, ld] bf16 (fast pass), q64 [b, ld] (exact pass).
+ * excl_row_ptr / excl_col: per-query CSR of excluded GLOBAL rows, sorted within a query (may be NULL).
+ * out_rows / out_scores are [b, k]; out_count[b]; out_status[b] is 0 when the query's result is proven exact and
+ * non-zero when the caller must re-run that query through the single-query path (threshold sample too optimistic,
+ * candidate buffer overflow, or margin below eps). */
+REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, const double* q64, const int64_t* excl_row_ptr,
+                     const int32_t* excl_col, const rebert_gemm_plan_t* plan, void* workspace, size_t workspace_bytes,
+                     int64_t* out_rows, double* out_scores, int32_t* out_count, int32_t* out_status,
+                     rebert_stream stream);
+/* Building block, also used by tests: out[u, j] = <q[u], row j> * inv_norm[j] for rows [row0, row0 + nrows) on the
+ * tensor cores (bf16 catalog only), fp32 [b, nrows]. */
+REBERT_API int rebert_gemm_scores(const rebert_catalog_t* cat, const void* qbf16, int32_t b, int64_t row0, int64_t nrows,
+                       float* out, rebert_stream stream);
+
+/* ---- synthetic inputs (bench / tests; bit-identical twin of robot_ebert_b200/synth.py) ----- */
+REBERT_API int rebert_synth_rows(uint64_t seed, int64_t row0, int64_t n, int32_t d, int32_t scale_rows, int32_t dtype, void* rows,
+                      int32_t ld, rebert_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REBERT_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of include/rebert_b200.h.  No fallback: if the library is missing this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "librebert_b200.so")
+
+F32, BF16 = 0, 1
+DTYPES = {"fp32": F32, "bf16": BF16}
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_DEVICE = 0, -1, -2, -3, -4, -5
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rebert_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Catalog(C.Structure):
+    _fields_ = [("rows", C.c_void_p), ("inv_norm", C.c_void_p), ("norm64", C.c_void_p), ("n", C.c_int64),
+                ("row_base", C.c_int64), ("d", C.c_int32), ("ld", C.c_int32), ("dtype", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Filter(C.Structure):
+    _fields_ = [("exclude_bitmap", C.c_void_p), ("exclude_rows", C.c_void_p), ("n_exclude", C.c_int32),
+                ("genre_any", C.c_uint32), ("genre_bits", C.c_void_p), ("year", C.c_void_p),
+                ("year_lo", C.c_uint16), ("year_hi", C.c_uint16), ("reserved", C.c_uint32)]
+
+
+class GemmPlan(C.Structure):
+    _fields_ = [("b", C.c_int32), ("k", C.c_int32), ("kc", C.c_int32), ("sample_rows", C.c_int32),
+                ("sample_rank", C.c_int32), ("cand_cap", C.c_int32)]
+
+
+_P = C.c_void_p
+_SIGS = {
+    "rebert_abi_version": (C.c_int, []),
+    "rebert_last_error": (C.c_char_p, []),
+    "rebert_check_device": (C.c_int, []),
+    "rebert_catalog_layout": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
+    "rebert_catalog_store_rows": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
+    "rebert_catalog_norms": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
+    "rebert_query_normalize": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "rebert_profile_accumulate": (C.c_int, [C.POINTER(Catalog), _P, _P, _P, C.c_int32, _P, _P, _P]),
+    "rebert_profile_finalize": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "rebert_candidates_for_k": (C.c_int32, [C.c_int32]),
+    "rebert_gemv_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "rebert_gemv_topk": (C.c_int, [C.POINTER(Catalog), _P, C.POINTER(Filter), C.c_int32, _P, C.c_size_t, _P, _P]),
+    "rebert_finalize_topk": (C.c_int, [C.POINTER(Catalog), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "rebert_merge_topk": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "rebert_score_subset": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "rebert_scores_dense": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, _P]),
+    "rebert_gemm_plan": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(GemmPlan)]),
+    "rebert_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(Catalog), C.POINTER(GemmPlan)]),
+    "rebert_gemm_topk": (C.c_int, [C.POINTER(Catalog), _P, _P, _P, _P, C.POINTER(GemmPlan), _P, C.c_size_t, _P, _P, _P, _P, _P]),
+    "rebert_gemm_scores": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
+    "rebert_synth_rows": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load librebert_b200.so (built in-tree by robot_ebert_b200/build.py).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU or PyTorch fallback for the scoring path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rebert_abi_version() != 1:
+        raise ImportError("rebert_b200 ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(_SIGS)
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        msg = load().rebert_last_error().decode("utf-8", "replace")
+        if rc == ERR_INVALID:
+            raise ValueError(f"rebert_b200: {msg}")
+        raise NativeError(rc, msg)

@@ -1,0 +1,355 @@
+"""HBM-resident catalog store and the single-request scoring call.
+
+Replaces the process-global DataFrame `movies_collab_embeddings` (reference
+src/backend/app/constants.py:55-56) and the pandas/sklearn expressions at src/backend/app/lib.py:44-55.
+torch is used for device memory, pinned staging and streams only; all arithmetic happens in
+librebert_b200.so (hand-written sm_100a kernels) through the C ABI in include/rebert_b200.h.
+There is no CPU path: without a CUDA device and the built library every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import warnings
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _align(x: int, a: int = 16) -> int:
+    return (x + a - 1) // a * a
+
+
+class RowFilter:
+    """Optional row predicate beside the seen-movie exclusion (BASELINE config 5: genre / year)."""
+
+    def __init__(self, genre_any: int = 0, year_lo: int = 0, year_hi: int = 65535,
+                 exclude_bitmap: Optional[torch.Tensor] = None):
+        self.genre_any, self.year_lo, self.year_hi = int(genre_any), int(year_lo), int(year_hi)
+        self.exclude_bitmap = exclude_bitmap
+
+
+class _Scratch:
+    """Per-thread staging + device scratch so concurrent requests (FastAPI's threadpool) never share buffers."""
+
+    def __init__(self, store: "CatalogStore"):
+        self.store = store
+        self.in_cap = 0
+        self.kc = 0
+        self.k_cap = 0
+        dev = store.device
+        ld = store.ld
+        self.qn32 = torch.zeros(ld, dtype=torch.float32, device=dev)
+        self.qn64 = torch.zeros(ld, dtype=torch.float64, device=dev)
+        self.sum64 = torch.zeros(ld, dtype=torch.float64, device=dev)
+        self.wsum = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def ensure_in(self, nbytes: int):
+        if nbytes > self.in_cap:
+            cap = max(4096, 1 << (nbytes - 1).bit_length())
+            self.h_in = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            self.d_in = torch.empty(cap, dtype=torch.uint8, device=self.store.device)
+            self.h_in_np = self.h_in.numpy()
+            self.in_cap = cap
+
+    def ensure_out(self, k: int, kc: int):
+        if kc != self.kc:
+            lib = nat.load()
+            wsb = lib.rebert_gemv_workspace_bytes(self.store.n, kc)
+            self.ws = torch.empty(wsb, dtype=torch.uint8, device=self.store.device)
+            self.cand = torch.empty(kc, dtype=torch.int64, device=self.store.device)   # u64 keys
+            self.kc = kc
+        if k > self.k_cap:
+            cap = max(16, 1 << (k - 1).bit_length())
+            nbytes = cap * 16 + 16
+            self.d_out = torch.empty(nbytes, dtype=torch.uint8, device=self.store.device)
+            self.h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            self.h_out_np = self.h_out.numpy()
+            self.k_cap = cap
+
+
+class CatalogStore:
+    """One catalog shard in HBM: rows [n, ld] (fp32 or bf16), fp32 inv_norm[n], fp64 norm64[n].
+
+    Rows are kept in ascending tmdb_id *string* order, so "row ascending" is the tie-break of lib.py:55,63.
+    """
+
+    def __init__(self, rows: torch.Tensor, inv_norm: torch.Tensor, norm64: torch.Tensor, n: int, d: int, ld: int,
+                 dtype: str, row_base: int = 0, ids: Optional[Sequence[str]] = None):
+        self.rows, self.inv_norm, self.norm64 = rows, inv_norm, norm64
+        self.n, self.d, self.ld, self.dtype, self.row_base = int(n), int(d), int(ld), dtype, int(row_base)
+        self.device = rows.device
+        self.ids = list(ids) if ids is not None else None
+        self._row_of = None
+        self.genre_bits: Optional[torch.Tensor] = None
+        self.year: Optional[torch.Tensor] = None
+        self._tls = threading.local()
+        self._c = nat.Catalog(rows=rows.data_ptr(), inv_norm=inv_norm.data_ptr(), norm64=norm64.data_ptr(), n=self.n,
+                              row_base=self.row_base, d=self.d, ld=self.ld, dtype=nat.DTYPES[dtype], reserved=0)
+        esize = 2 if dtype == "bf16" else 4
+        chunks, epc = self.ld * esize // 16, 16 // esize
+        self.elements_per_lane = epc if chunks <= 16 else (chunks // 32) * epc   # mirrors csrc row_layout()
+        # fp32 error bound of the fast pass on a unit-vector dot
+        self.fast_eps = float((self.elements_per_lane + 12) * 2.0 ** -24)
+
+    # ------------------------------------------------------------------ construction -----------
+    @staticmethod
+    def _require_cuda(device) -> torch.device:
+        if not torch.cuda.is_available():
+            raise RuntimeError("robot_ebert_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device(device if device is not None else "cuda:0")
+        lib = nat.load()
+        with torch.cuda.device(dev):
+            nat.check(lib.rebert_check_device())
+        return dev
+
+    @staticmethod
+    def layout(n: int, d: int, dtype: str) -> Tuple[int, int]:
+        lib = nat.load()
+        ld, nbytes = C.c_int32(0), C.c_size_t(0)
+        nat.check(lib.rebert_catalog_layout(n, d, nat.DTYPES[dtype], C.byref(ld), C.byref(nbytes)))
+        return ld.value, nbytes.value
+
+    @classmethod
+    def _alloc(cls, n: int, d: int, dtype: str, dev: torch.device):
+        ld, _ = cls.layout(n, d, dtype)
+        tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+        rows = torch.empty((max(n, 1), ld), dtype=tdt, device=dev)
+        inv_norm = torch.empty(_align(max(n, 1), 4), dtype=torch.float32, device=dev)
+        norm64 = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+        return ld, rows, inv_norm, norm64
+
+    @classmethod
+    def from_host(cls, ids: Optional[Sequence[str]], matrix: np.ndarray, dtype: str = "fp32", device=None,
+                  row_base: int = 0, chunk_rows: int = 1 << 18, sort_ids: bool = True) -> "CatalogStore":
+        """Upload an [N, D] host matrix (what Chroma's collection.get returns, constants.py:55) and build the store."""
+        dev = cls._require_cuda(device)
+        lib = nat.load()
+        matrix = np.asarray(matrix, dtype=np.float32)
+        if matrix.ndim != 2:
+            raise ValueError("matrix must be [N, D]")
+        n, d = matrix.shape
+        if ids is not None:
+            if len(ids) != n:
+                raise ValueError("len(ids) != rows")
+            ids = [str(i) for i in ids]
+            if sort_ids:
+                order = sorted(range(n), key=ids.__getitem__)
+                if order != list(range(n)):
+                    matrix = matrix[np.asarray(order)]
+                    ids = [ids[i] for i in order]
+            if len(set(ids)) != n:
+                raise ValueError("duplicate ids")
+        ld, rows, inv_norm, norm64 = cls._alloc(n, d, dtype, dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            esize = rows.element_size()
+            for s in range(0, n, chunk_rows):
+                e = min(n, s + chunk_rows)
+                src = torch.from_numpy(np.ascontiguousarray(matrix[s:e])).to(dev)
+                nat.check(lib.rebert_catalog_store_rows(src.data_ptr(), e - s, d, nat.DTYPES[dtype],
+                                                        rows.data_ptr() + s * ld * esize, ld, st))
+                torch.cuda.current_stream().synchronize()
+            if n:
+                nat.check(lib.rebert_catalog_norms(rows.data_ptr(), n, ld, nat.DTYPES[dtype], inv_norm.data_ptr(),
+                                                   norm64.data_ptr(), st))
+            torch.cuda.current_stream().synchronize()
+        return cls(rows, inv_norm, norm64, n, d, ld, dtype, row_base, ids)
+
+    @classmethod
+    def synthetic(cls, seed: int, n: int, d: int, dtype: str = "bf16", scale_rows: bool = False, device=None,
+                  row0: int = 0, row_base: Optional[int] = None) -> "CatalogStore":
+        """Rows [row0, row0+n) of the counter-based synthetic catalog (robot_ebert_b200/synth.py), generated in HBM."""
+        dev = cls._require_cuda(device)
+        lib = nat.load()
+        ld, rows, inv_norm, norm64 = cls._alloc(n, d, dtype, dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            nat.check(lib.rebert_synth_rows(seed, row0, n, d, int(scale_rows), nat.DTYPES[dtype], rows.data_ptr(), ld, st))
+            nat.check(lib.rebert_catalog_norms(rows.data_ptr(), n, ld, nat.DTYPES[dtype], inv_norm.data_ptr(),
+                                               norm64.data_ptr(), st))
+            torch.cuda.current_stream().synchronize()
+        return cls(rows, inv_norm, norm64, n, d, ld, dtype, row0 if row_base is None else row_base, None)
+
+    def set_metadata(self, genre_bits: np.ndarray, year: np.ndarray) -> None:
+        """Per-row side columns for the genre/year predicate (local row order)."""
+        self.genre_bits = torch.from_numpy(np.ascontiguousarray(genre_bits, dtype=np.uint32).view(np.int32)).to(self.device)
+        self.year = torch.from_numpy(np.ascontiguousarray(year, dtype=np.uint16).view(np.int16)).to(self.device)
+
+    # ------------------------------------------------------------------ id map ------------------
+    def row_of(self, tmdb_id: str) -> Optional[int]:
+        if self._row_of is None:
+            if self.ids is None:
+                raise ValueError("catalog has no id table")
+            self._row_of = {i: r + self.row_base for r, i in enumerate(self.ids)}
+        return self._row_of.get(tmdb_id)
+
+    def id_of(self, row: int) -> str:
+        return self.ids[row - self.row_base] if self.ids is not None else str(row)
+
+    # ------------------------------------------------------------------ scoring -----------------
+    def _scratch(self) -> _Scratch:
+        s = getattr(self._tls, "s", None)
+        if s is None:
+            s = self._tls.s = _Scratch(self)
+        return s
+
+    def recommend(self, *, query: Optional[np.ndarray] = None, liked_rows: Optional[np.ndarray] = None,
+                  weights: Optional[np.ndarray] = None, exclude_rows: Optional[np.ndarray] = None, k: int = 10,
+                  row_filter: Optional[RowFilter] = None, return_info: bool = False):
+        """Top-k rows by cosine to `query`, or by mean cosine to `liked_rows` (lib.py:51-55).
+
+        query        fp32 [D] host vector (not normalised), OR
+        liked_rows   global row ids of the liked movies (+ optional weights; default 1 = the reference)
+        exclude_rows global row ids that must not be returned (the user's rated movies, lib.py:48)
+        Returns (rows int64[k'], scores float64[k']), k' = min(k, #allowed rows), ordered (score desc, row asc).
+        Host buffers in, host buffers out: the H2D/D2H copies are part of the call.
+        """
+        if (query is None) == (liked_rows is None):
+            raise ValueError("pass exactly one of query / liked_rows")
+        if k <= 0:
+            raise ValueError("k must be positive")
+        lib = nat.load()
+        kc = lib.rebert_candidates_for_k(k)
+        if kc == 0:
+            raise ValueError(f"k={k} is outside the supported range (1..240)")
+        while True:
+            rows, scores, margin = self._recommend_once(lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter)
+            if margin > self.fast_eps or kc >= 256:
+                break
+            kc = min(256, kc * 4)                       # candidate set not provably exact: widen and redo
+        proven = margin > self.fast_eps
+        if not proven:
+            warnings.warn(f"top-{k}: fp32 candidate margin {margin:.3e} <= {self.fast_eps:.3e}; ids may differ from fp64 order")
+        if return_info:
+            return rows, scores, {"kc": kc, "margin": margin, "proven_exact": proven}
+        return rows, scores
+
+    def _recommend_once(self, lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter):
+        s = self._scratch()
+        d, ld = self.d, self.ld
+        excl = None
+        if exclude_rows is not None and len(exclude_rows):
+            excl = np.unique(np.asarray(exclude_rows, dtype=np.int32))
+        ne = 0 if excl is None else int(excl.shape[0])
+        nl = 0
+        if liked_rows is not None:
+            liked = np.asarray(liked_rows, dtype=np.int32)
+            nl = int(liked.shape[0])
+            if nl == 0:
+                # same failure the reference hits: sklearn's check_array on an empty frame
+                raise ValueError("Found array with 0 sample(s): user has no liked movies in the catalog")
+        # ---- pack every input into one pinned buffer -> one H2D copy
+        off_q = 0
+        off_rp = _align(4 * d)
+        off_e = off_rp + 16
+        off_c = off_e + _align(4 * ne)
+        off_w = off_c + _align(4 * nl)
+        total = off_w + _align(4 * nl)
+        s.ensure_in(total)
+        s.ensure_out(k, kc)
+        h = s.h_in_np
+        if query is not None:
+            q = np.asarray(query, dtype=np.float32)
+            if q.shape != (d,):
+                raise ValueError(f"query must have shape ({d},)")
+            h[off_q:off_q + 4 * d].view(np.float32)[:] = q
+        else:
+            h[off_rp:off_rp + 16].view(np.int64)[:] = (0, nl)
+            h[off_c:off_c + 4 * nl].view(np.int32)[:] = liked
+            if weights is not None:
+                h[off_w:off_w + 4 * nl].view(np.float32)[:] = np.asarray(weights, dtype=np.float32)
+        if ne:
+            h[off_e:off_e + 4 * ne].view(np.int32)[:] = excl
+
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream()
+            st = stream.cuda_stream
+            s.d_in[:total].copy_(s.h_in[:total], non_blocking=True)
+            base = s.d_in.data_ptr()
+            if query is not None:
+                nat.check(lib.rebert_query_normalize(base + off_q, 1, d, ld, s.qn32.data_ptr(), s.qn64.data_ptr(), st))
+            else:
+                nat.check(lib.rebert_profile_accumulate(C.byref(self._c), base + off_rp, base + off_c,
+                                                        (base + off_w) if weights is not None else None, 1,
+                                                        s.sum64.data_ptr(), s.wsum.data_ptr(), st))
+                nat.check(lib.rebert_profile_finalize(s.sum64.data_ptr(), s.wsum.data_ptr(), 1, ld, s.qn32.data_ptr(),
+                                                      s.qn64.data_ptr(), None, st))
+            f = nat.Filter()
+            if ne:
+                f.exclude_rows, f.n_exclude = base + off_e, ne
+            if row_filter is not None:
+                if row_filter.exclude_bitmap is not None:
+                    f.exclude_bitmap = row_filter.exclude_bitmap.data_ptr()
+                if row_filter.genre_any:
+                    if self.genre_bits is None:
+                        raise ValueError("row_filter.genre_any needs set_metadata()")
+                    f.genre_bits, f.genre_any = self.genre_bits.data_ptr(), row_filter.genre_any
+                if (row_filter.year_lo, row_filter.year_hi) != (0, 65535):
+                    if self.year is None:
+                        raise ValueError("row_filter year range needs set_metadata()")
+                    f.year, f.year_lo, f.year_hi = self.year.data_ptr(), row_filter.year_lo, row_filter.year_hi
+            nat.check(lib.rebert_gemv_topk(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
+                                           s.ws.numel(), s.cand.data_ptr(), st))
+            kcap = s.k_cap
+            ob = s.d_out.data_ptr()
+            nat.check(lib.rebert_finalize_topk(C.byref(self._c), s.qn64.data_ptr(), s.cand.data_ptr(), kc, k, ob,
+                                               ob + 8 * kcap, ob + 16 * kcap, ob + 16 * kcap + 8, st))
+            s.h_out.copy_(s.d_out, non_blocking=True)
+            stream.synchronize()
+        o = s.h_out_np
+        cnt = int(o[16 * kcap:16 * kcap + 4].view(np.int32)[0])
+        margin = float(o[16 * kcap + 8:16 * kcap + 16].view(np.float64)[0])
+        rows = o[:8 * kcap].view(np.int64)[:cnt].copy()
+        scores = o[8 * kcap:16 * kcap].view(np.float64)[:cnt].copy()
+        return rows, scores, margin
+
+    # ------------------------------------------------------------------ diagnostics -------------
+    def scores_dense(self, q32: torch.Tensor) -> torch.Tensor:
+        """Materialised fp32 score rows for b pre-normalised queries [b, ld] (test / diagnostics only)."""
+        lib = nat.load()
+        b = q32.shape[0]
+        out = torch.empty((b, self.n), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(lib.rebert_scores_dense(C.byref(self._c), q32.data_ptr(), b, out.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def score_subset(self, p64: torch.Tensor, sub_rows: np.ndarray) -> np.ndarray:
+        """fp64 scores of `sub_rows` (global ids) against b prepared profiles [b, ld] (lib.py:105-106)."""
+        lib = nat.load()
+        sub = torch.from_numpy(np.asarray(sub_rows, dtype=np.int32)).to(self.device)
+        b, m = p64.shape[0], sub.shape[0]
+        out = torch.empty((b, m), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(lib.rebert_score_subset(C.byref(self._c), p64.data_ptr(), b, sub.data_ptr(), m, out.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+        return out.cpu().numpy()
+
+    def build_profiles(self, row_ptr: np.ndarray, col: np.ndarray, w: Optional[np.ndarray] = None):
+        """Batched profile build from a ragged CSR of liked rows: returns (p32, p64, pbf16) device tensors [b, ld]."""
+        lib = nat.load()
+        dev = self.device
+        rp = torch.from_numpy(np.asarray(row_ptr, dtype=np.int64)).to(dev)
+        cl = torch.from_numpy(np.asarray(col, dtype=np.int32)).to(dev)
+        wt = None if w is None else torch.from_numpy(np.asarray(w, dtype=np.float32)).to(dev)
+        b = rp.shape[0] - 1
+        sum64 = torch.empty((b, self.ld), dtype=torch.float64, device=dev)
+        wsum = torch.empty(b, dtype=torch.float64, device=dev)
+        p32 = torch.empty((b, self.ld), dtype=torch.float32, device=dev)
+        p64 = torch.empty((b, self.ld), dtype=torch.float64, device=dev)
+        pbf = torch.empty((b, self.ld), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            nat.check(lib.rebert_profile_accumulate(C.byref(self._c), rp.data_ptr(), cl.data_ptr(), _ptr(wt), b,
+                                                    sum64.data_ptr(), wsum.data_ptr(), st))
+            nat.check(lib.rebert_profile_finalize(sum64.data_ptr(), wsum.data_ptr(), b, self.ld, p32.data_ptr(),
+                                                  p64.data_ptr(), pbf.data_ptr(), st))
+        return p32, p64, pbf

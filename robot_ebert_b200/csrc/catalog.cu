@@ -1,0 +1,394 @@
+// Catalog store, query / profile preparation, subset + dense scoring, synthetic generator.
+// Reference sites: src/backend/app/constants.py:55-56 (catalog), lib.py:51-52 (profile = mean of unit rows),
+// lib.py:105-106 (subset scoring).  All of these are one-pass HBM-bound or tiny kernels.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace rebert {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return REBERT_ERR_CUDA;
+}
+int num_sms() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+RowLayout row_layout(int d, int dtype) {
+    RowLayout L;
+    L.esize = dtype == REBERT_BF16 ? 2 : 4;
+    L.epc = 16 / L.esize;
+    int chunks = (d * L.esize + 15) / 16;
+    if (chunks <= 16) {
+        int lanes = 2;
+        while (lanes < chunks) lanes <<= 1;
+        L.lanes = lanes;
+        L.cpl = 1;
+    } else {
+        L.lanes = 32;
+        L.cpl = (chunks + 31) / 32;
+    }
+    L.ld = L.lanes * L.cpl * L.epc;
+    return L;
+}
+
+DevFilter make_filter(const rebert_filter_t* f, int64_t row_base) {
+    DevFilter d;
+    memset(&d, 0, sizeof(d));
+    d.row_base = row_base;
+    if (f) {
+        d.exclude_bitmap = f->exclude_bitmap;
+        d.exclude_rows = f->n_exclude > 0 ? f->exclude_rows : nullptr;
+        d.n_exclude = f->exclude_rows ? f->n_exclude : 0;
+        d.genre_bits = f->genre_bits;
+        d.genre_any = f->genre_any;
+        d.year = f->year;
+        d.year_lo = f->year_lo;
+        d.year_hi = f->year_hi;
+    }
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device side of the synthetic generator: must stay bit-identical to robot_ebert_b200/synth.py
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float synth_value(uint64_t seed, uint64_t row, uint32_t d, uint32_t c, int scale_rows) {
+    uint64_t h = splitmix64(seed * 0xD6E8FEB86659FD93ull + row * (uint64_t)d + c);
+    int s = (int)(h & 0xFFFF) + (int)((h >> 16) & 0xFFFF) + (int)((h >> 32) & 0xFFFF) + (int)(h >> 48);
+    float v = __fmul_rn((float)(s - 131070), (float)(1.0 / 37837.2273));
+    if (scale_rows) {
+        int e = (int)(splitmix64((seed ^ 0xA0761D6478BD642Full) + row) % 9ull) - 4;
+        v = __fmul_rn(v, __int_as_float((127 + e) << 23));
+    }
+    return v;
+}
+__device__ __forceinline__ uint16_t f32_to_bf16_rne(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (uint16_t)((b + 0x7FFFu + ((b >> 16) & 1u)) >> 16);
+}
+
+template <typename T> __device__ __forceinline__ T store_cvt(float v);
+template <> __device__ __forceinline__ float store_cvt<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 store_cvt<__nv_bfloat16>(float v) {
+    return __ushort_as_bfloat16(f32_to_bf16_rne(v));
+}
+
+template <typename T>
+__global__ void synth_rows_kernel(uint64_t seed, int64_t row0, int64_t n, int d, int ld, int scale_rows, T* __restrict__ rows) {
+    int64_t total = n * (int64_t)ld;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ld;
+        int c = (int)(i - r * ld);
+        float v = c < d ? synth_value(seed, (uint64_t)(row0 + r), (uint32_t)d, (uint32_t)c, scale_rows) : 0.0f;
+        rows[i] = store_cvt<T>(v);
+    }
+}
+
+template <typename T>
+__global__ void store_rows_kernel(const float* __restrict__ src, int64_t n, int d, int ld, T* __restrict__ rows) {
+    int64_t total = n * (int64_t)ld;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ld;
+        int c = (int)(i - r * ld);
+        rows[i] = store_cvt<T>(c < d ? src[r * d + c] : 0.0f);
+    }
+}
+
+// One warp per row: fp64 sum of squares of the stored values (sklearn row_norms, zero -> 1).
+template <typename T>
+__global__ void norms_kernel(const T* __restrict__ rows, int64_t n, int ld, float* __restrict__ inv_norm,
+                             double* __restrict__ norm64) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const T* row = rows + r * ld;
+        double acc = 0.0;
+        for (int c = lane; c < ld; c += 32) {
+            double x = elem_f64<T>(row, c);
+            acc = fma(x, x, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            double nrm = sqrt(acc);
+            if (nrm == 0.0) nrm = 1.0;
+            norm64[r] = nrm;
+            inv_norm[r] = (float)(1.0 / nrm);
+        }
+    }
+}
+
+// One CTA per query.
+__global__ void query_normalize_kernel(const float* __restrict__ q, int d, int ld, float* __restrict__ qn32,
+                                       double* __restrict__ qn64) {
+    __shared__ double red[32];
+    const float* src = q + (int64_t)blockIdx.x * d;
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        double x = (double)src[c];
+        acc = fma(x, x, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    double nrm = sqrt(red[0]);
+    if (nrm == 0.0) nrm = 1.0;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        double v = c < d ? (double)src[c] / nrm : 0.0;
+        if (qn64) qn64[(int64_t)blockIdx.x * ld + c] = v;
+        if (qn32) qn32[(int64_t)blockIdx.x * ld + c] = (float)v;
+    }
+}
+
+// One CTA per user; thread c owns column c and walks the user's CSR entries in order, so the fp64 sum has a
+// fixed order (deterministic).  Entries outside this shard are skipped.
+template <typename T>
+__global__ void profile_accumulate_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n,
+                                          int64_t row_base, int ld, const int64_t* __restrict__ row_ptr,
+                                          const int32_t* __restrict__ col, const float* __restrict__ w,
+                                          double* __restrict__ sum64, double* __restrict__ wsum) {
+    int u = blockIdx.x;
+    int64_t e0 = row_ptr[u], e1 = row_ptr[u + 1];
+    for (int c0 = 0; c0 < ld; c0 += blockDim.x) {
+        int c = c0 + threadIdx.x;
+        double acc = 0.0;
+        for (int64_t e = e0; e < e1; ++e) {
+            int64_t r = (int64_t)col[e] - row_base;
+            if (r < 0 || r >= n) continue;
+            double wt = w ? (double)w[e] : 1.0;
+            double rn = wt / norm64[r];
+            if (c < ld) acc = fma(elem_f64<T>(rows + r * ld, c), rn, acc);
+        }
+        if (c < ld) sum64[(int64_t)u * ld + c] = acc;
+    }
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int64_t e = e0; e < e1; ++e) s += w ? (double)w[e] : 1.0;
+        wsum[u] = s;
+    }
+}
+
+__global__ void profile_finalize_kernel(const double* __restrict__ sum64, const double* __restrict__ wsum, int ld,
+                                        float* __restrict__ p32, double* __restrict__ p64,
+                                        __nv_bfloat16* __restrict__ pbf16) {
+    int u = blockIdx.x;
+    double ws = wsum[u];
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        int64_t i = (int64_t)u * ld + c;
+        double v = ws != 0.0 ? sum64[i] / ws : 0.0;
+        if (p64) p64[i] = v;
+        if (p32) p32[i] = (float)v;
+        if (pbf16) pbf16[i] = __ushort_as_bfloat16(f32_to_bf16_rne((float)v));
+    }
+}
+
+// One warp per (user, candidate): fp64 dot / norm64.
+template <typename T>
+__global__ void score_subset_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n,
+                                    int64_t row_base, int ld, const double* __restrict__ p64, int b,
+                                    const int32_t* __restrict__ sub_rows, int m, double* __restrict__ out) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (int64_t)b * m) return;
+    int u = (int)(warp / m), j = (int)(warp % m);
+    int64_t r = (int64_t)sub_rows[j] - row_base;
+    double acc = 0.0;
+    if (r >= 0 && r < n) {
+        const T* row = rows + r * ld;
+        const double* p = p64 + (int64_t)u * ld;
+        for (int c = lane; c < ld; c += 32) acc = fma(p[c], elem_f64<T>(row, c), acc);
+        acc = warp_sum(acc) / norm64[r];
+    } else {
+        acc = nan("");
+    }
+    if (lane == 0) out[(int64_t)u * m + j] = acc;
+}
+
+// One warp per catalog row, looping over the (few) queries: the materialised score matrix of lib.py:51 in fp32.
+template <typename T>
+__global__ void scores_dense_kernel(const T* __restrict__ rows, const float* __restrict__ inv_norm, int64_t n, int ld,
+                                    const float* __restrict__ q32, int b, float* __restrict__ out) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const T* row = rows + r * ld;
+        float inv = inv_norm[r];
+        for (int u = 0; u < b; ++u) {
+            const float* q = q32 + (int64_t)u * ld;
+            float acc = 0.0f;
+            for (int c = lane; c < ld; c += 32) acc = fmaf(q[c], (float)elem_f64<T>(row, c), acc);
+            acc = warp_sum(acc);
+            if (lane == 0) out[(int64_t)u * n + r] = acc * inv;
+        }
+    }
+}
+
+static int grid_for(int64_t work_items, int block) {
+    int64_t g = (work_items + block - 1) / block;
+    int64_t cap = (int64_t)num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace rebert
+
+using namespace rebert;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+REBERT_API int rebert_abi_version(void) { return REBERT_ABI_VERSION; }
+REBERT_API const char* rebert_last_error(void) { return g_err; }
+
+REBERT_API int rebert_check_device(void) {
+    int dev = 0, major = 0;
+    REBERT_CUDA(cudaGetDevice(&dev));
+    REBERT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        set_error("device %d has compute capability %d.x; this library carries sm_100a code only", dev, major);
+        return REBERT_ERR_DEVICE;
+    }
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_catalog_layout(int64_t n, int32_t d, int32_t dtype, int32_t* ld, size_t* rows_bytes) {
+    REBERT_REQUIRE(n >= 0 && d > 0, "catalog_layout: n=%lld d=%d", (long long)n, d);
+    REBERT_REQUIRE(dtype == REBERT_F32 || dtype == REBERT_BF16, "catalog_layout: dtype %d", dtype);
+    RowLayout L = row_layout(d, dtype);
+    if (ld) *ld = L.ld;
+    if (rows_bytes) *rows_bytes = (size_t)n * L.ld * L.esize;
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_catalog_store_rows(const float* src, int64_t n, int32_t d, int32_t dtype, void* rows, int32_t ld,
+                              rebert_stream stream) {
+    REBERT_REQUIRE(src && rows && n >= 0 && d > 0 && ld >= d, "catalog_store_rows: bad arguments");
+    if (n == 0) return REBERT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(n * ld, 256);
+    if (dtype == REBERT_F32) store_rows_kernel<float><<<g, 256, 0, st>>>(src, n, d, ld, (float*)rows);
+    else if (dtype == REBERT_BF16) store_rows_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(src, n, d, ld, (__nv_bfloat16*)rows);
+    else REBERT_REQUIRE(false, "catalog_store_rows: dtype %d", dtype);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_catalog_norms(const void* rows, int64_t n, int32_t ld, int32_t dtype, float* inv_norm, double* norm64,
+                         rebert_stream stream) {
+    REBERT_REQUIRE(rows && inv_norm && norm64 && n >= 0 && ld > 0, "catalog_norms: bad arguments");
+    if (n == 0) return REBERT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(n * 32, 256);
+    if (dtype == REBERT_F32) norms_kernel<float><<<g, 256, 0, st>>>((const float*)rows, n, ld, inv_norm, norm64);
+    else if (dtype == REBERT_BF16) norms_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)rows, n, ld, inv_norm, norm64);
+    else REBERT_REQUIRE(false, "catalog_norms: dtype %d", dtype);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_query_normalize(const float* q, int32_t b, int32_t d, int32_t ld, float* qn32, double* qn64,
+                           rebert_stream stream) {
+    REBERT_REQUIRE(q && b > 0 && d > 0 && ld >= d && (qn32 || qn64), "query_normalize: bad arguments");
+    query_normalize_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(q, d, ld, qn32, qn64);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_profile_accumulate(const rebert_catalog_t* cat, const int64_t* row_ptr, const int32_t* col, const float* w,
+                              int32_t b, double* sum64, double* wsum, rebert_stream stream) {
+    REBERT_REQUIRE(cat && cat->rows && cat->norm64 && row_ptr && col && sum64 && wsum && b > 0,
+                   "profile_accumulate: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cat->dtype == REBERT_F32)
+        profile_accumulate_kernel<float><<<b, 256, 0, st>>>((const float*)cat->rows, cat->norm64, cat->n, cat->row_base,
+                                                            cat->ld, row_ptr, col, w, sum64, wsum);
+    else
+        profile_accumulate_kernel<__nv_bfloat16><<<b, 256, 0, st>>>((const __nv_bfloat16*)cat->rows, cat->norm64, cat->n,
+                                                                    cat->row_base, cat->ld, row_ptr, col, w, sum64, wsum);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_profile_finalize(const double* sum64, const double* wsum, int32_t b, int32_t ld, float* p32, double* p64,
+                            void* pbf16, rebert_stream stream) {
+    REBERT_REQUIRE(sum64 && wsum && b > 0 && ld > 0, "profile_finalize: bad arguments");
+    profile_finalize_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(sum64, wsum, ld, p32, p64, (__nv_bfloat16*)pbf16);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_score_subset(const rebert_catalog_t* cat, const double* p64, int32_t b, const int32_t* sub_rows, int32_t m,
+                        double* out, rebert_stream stream) {
+    REBERT_REQUIRE(cat && cat->rows && cat->norm64 && p64 && sub_rows && out && b > 0 && m > 0, "score_subset: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t warps = (int64_t)b * m;
+    int g = (int)((warps * 32 + 255) / 256);
+    if (cat->dtype == REBERT_F32)
+        score_subset_kernel<float><<<g, 256, 0, st>>>((const float*)cat->rows, cat->norm64, cat->n, cat->row_base, cat->ld,
+                                                      p64, b, sub_rows, m, out);
+    else
+        score_subset_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)cat->rows, cat->norm64, cat->n,
+                                                              cat->row_base, cat->ld, p64, b, sub_rows, m, out);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_scores_dense(const rebert_catalog_t* cat, const float* q32, int32_t b, float* out, rebert_stream stream) {
+    REBERT_REQUIRE(cat && cat->rows && cat->inv_norm && q32 && out && b > 0, "scores_dense: bad arguments");
+    if (cat->n == 0) return REBERT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(cat->n * 32, 256);
+    if (cat->dtype == REBERT_F32)
+        scores_dense_kernel<float><<<g, 256, 0, st>>>((const float*)cat->rows, cat->inv_norm, cat->n, cat->ld, q32, b, out);
+    else
+        scores_dense_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)cat->rows, cat->inv_norm, cat->n, cat->ld,
+                                                              q32, b, out);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_synth_rows(uint64_t seed, int64_t row0, int64_t n, int32_t d, int32_t scale_rows, int32_t dtype, void* rows,
+                      int32_t ld, rebert_stream stream) {
+    REBERT_REQUIRE(rows && n >= 0 && d > 0 && ld >= d, "synth_rows: bad arguments");
+    if (n == 0) return REBERT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(n * ld, 256);
+    if (dtype == REBERT_F32) synth_rows_kernel<float><<<g, 256, 0, st>>>(seed, row0, n, d, ld, scale_rows, (float*)rows);
+    else if (dtype == REBERT_BF16)
+        synth_rows_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(seed, row0, n, d, ld, scale_rows, (__nv_bfloat16*)rows);
+    else REBERT_REQUIRE(false, "synth_rows: dtype %d", dtype);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+}  // extern "C"

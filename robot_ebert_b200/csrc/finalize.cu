@@ -1,0 +1,164 @@
+// Exact pass and merges.
+//   rebert_finalize_topk : fp64 re-score of the fast pass's candidates with the oracle's formula
+//                          (sklearn cosine_similarity: x/||x||, y/||y||, dot — lib.py:51), then the
+//                          (score desc, row asc) order of lib.py:55,63, best k out.
+//   rebert_merge_topk    : the same order across per-shard result lists (row-sharded catalogs).
+#include "common.cuh"
+
+namespace rebert {
+
+constexpr int kFinalThreads = 1024;
+constexpr int kMaxKc = 1024;
+
+__device__ __forceinline__ bool better(double sa, int64_t ra, double sb, int64_t rb) {
+    return sa > sb || (sa == sb && ra < rb);
+}
+
+// grid = (b); one CTA per query.  cand_keys [b, kc], q64 [b, ld], outputs [b, k].
+template <typename T>
+__global__ void __launch_bounds__(kFinalThreads, 1)
+finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t row_base, int ld,
+                     const double* __restrict__ q64, const uint64_t* __restrict__ cand_keys, int kc, int k,
+                     int64_t* __restrict__ out_rows, double* __restrict__ out_scores, int32_t* __restrict__ out_count,
+                     double* __restrict__ out_margin) {
+    __shared__ double s_score[kMaxKc];
+    __shared__ int64_t s_row[kMaxKc];
+    __shared__ int s_valid;
+    __shared__ double s_kth;
+    const int u = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const uint64_t* keys = cand_keys + (size_t)u * kc;
+    const double* q = q64 + (size_t)u * ld;
+    if (threadIdx.x == 0) { s_valid = 0; s_kth = 0.0; }
+    __syncthreads();
+
+    for (int c = warp; c < kc; c += nwarps) {
+        const uint64_t key = keys[c];
+        double sc = -INFINITY;
+        int64_t gr = -1;
+        if (key != 0) {
+            const uint32_t lr = key_row(key);
+            const T* row = rows + (size_t)lr * ld;
+            double acc = 0.0;
+            for (int i = lane; i < ld; i += 32) acc = fma(q[i], elem_f64<T>(row, i), acc);
+            acc = warp_sum(acc);
+            sc = acc / norm64[lr];
+            gr = row_base + lr;
+        }
+        if (lane == 0) {
+            s_score[c] = sc;
+            s_row[c] = gr;
+            if (key != 0) atomicAdd(&s_valid, 1);
+        }
+    }
+    __syncthreads();
+    const int valid = s_valid;
+    const int nout = valid < k ? valid : k;
+    for (int c = threadIdx.x; c < kc; c += blockDim.x) {
+        const int64_t r = s_row[c];
+        if (r < 0) continue;
+        const double sc = s_score[c];
+        int rank = 0;
+        for (int j = 0; j < kc; ++j) {
+            const int64_t rj = s_row[j];
+            if (rj >= 0 && better(s_score[j], rj, sc, r)) ++rank;
+        }
+        if (rank < k) {
+            out_rows[(size_t)u * k + rank] = r;
+            out_scores[(size_t)u * k + rank] = sc;
+            if (rank == k - 1) s_kth = sc;
+        }
+    }
+    for (int i = nout + threadIdx.x; i < k; i += blockDim.x) {
+        out_rows[(size_t)u * k + i] = -1;
+        out_scores[(size_t)u * k + i] = -INFINITY;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out_count[u] = nout;
+        if (out_margin) {
+            const uint64_t last = keys[kc - 1];
+            // list full => rows outside it have fast score <= key_score(last); compare against the exact k-th
+            out_margin[u] = (last != 0 && valid >= k) ? s_kth - (double)key_score(last) : INFINITY;
+        }
+    }
+}
+
+// One CTA per query: rank-merge `lists` sorted lists of up to k entries each.
+__global__ void merge_topk_kernel(const int64_t* __restrict__ rows, const double* __restrict__ scores,
+                                  const int32_t* __restrict__ counts, int lists, int b, int k,
+                                  int64_t* __restrict__ out_rows, double* __restrict__ out_scores,
+                                  int32_t* __restrict__ out_count) {
+    const int u = blockIdx.x;
+    int total = 0;
+    for (int l = 0; l < lists; ++l) total += counts[(size_t)l * b + u];
+    const int nout = total < k ? total : k;
+    for (int i = threadIdx.x; i < lists * k; i += blockDim.x) {
+        const int l = i / k, e = i - l * k;
+        if (e >= counts[(size_t)l * b + u]) continue;
+        const size_t off = ((size_t)l * b + u) * k;
+        const double sc = scores[off + e];
+        const int64_t r = rows[off + e];
+        int rank = e;
+        for (int o = 0; o < lists; ++o) {
+            if (o == l) continue;
+            const size_t oo = ((size_t)o * b + u) * k;
+            int lo = 0, hi = counts[(size_t)o * b + u];      // entries of list o better than (sc, r)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (better(scores[oo + mid], rows[oo + mid], sc, r)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            out_rows[(size_t)u * k + rank] = r;
+            out_scores[(size_t)u * k + rank] = sc;
+        }
+    }
+    for (int i = nout + threadIdx.x; i < k; i += blockDim.x) {
+        out_rows[(size_t)u * k + i] = -1;
+        out_scores[(size_t)u * k + i] = -INFINITY;
+    }
+    if (threadIdx.x == 0) out_count[u] = nout;
+}
+
+int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
+                    int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st) {
+    if (cat->dtype == REBERT_F32)
+        finalize_topk_kernel<float><<<b, kFinalThreads, 0, st>>>((const float*)cat->rows, cat->norm64, cat->row_base, cat->ld,
+                                                                  q64, cand_keys, kc, k, out_rows, out_scores, out_count,
+                                                                  out_margin);
+    else
+        finalize_topk_kernel<__nv_bfloat16><<<b, kFinalThreads, 0, st>>>((const __nv_bfloat16*)cat->rows, cat->norm64,
+                                                                          cat->row_base, cat->ld, q64, cand_keys, kc, k,
+                                                                          out_rows, out_scores, out_count, out_margin);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+}  // namespace rebert
+
+using namespace rebert;
+
+extern "C" {
+
+REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* qn64, const uint64_t* cand_keys, int32_t kc,
+                         int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin,
+                         rebert_stream stream) {
+    REBERT_REQUIRE(cat && cat->rows && cat->norm64 && qn64 && cand_keys && out_rows && out_scores && out_count,
+                   "finalize_topk: null argument");
+    REBERT_REQUIRE(kc > 0 && kc <= kMaxKc && k > 0 && k <= kc, "finalize_topk: k=%d kc=%d", k, kc);
+    return finalize_launch(cat, qn64, cand_keys, 1, kc, k, out_rows, out_scores, out_count, out_margin,
+                           (cudaStream_t)stream);
+}
+
+REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, const int32_t* counts, int32_t lists, int32_t b,
+                      int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_stream stream) {
+    REBERT_REQUIRE(rows && scores && counts && out_rows && out_scores && out_count, "merge_topk: null argument");
+    REBERT_REQUIRE(lists > 0 && b > 0 && k > 0, "merge_topk: lists=%d b=%d k=%d", lists, b, k);
+    merge_topk_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(rows, scores, counts, lists, b, k, out_rows, out_scores, out_count);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,457 @@
+// Single-query fused score + mask + top-k  (reference: lib.py:51-55 with one query / one profile).
+//
+// HBM-bound: every catalog byte is read exactly once.  Design:
+//   * persistent grid, one CTA per SM, 8 consumer warps + 1 producer warp;
+//   * the producer streams contiguous row tiles (and the matching inv_norm slice) into a ring of shared-memory
+//     stages with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers, L2 evict-first;
+//   * a row is LANES*CPL 16-byte chunks; the LANES lanes that share a row each keep their CPL chunks of the query in
+//     registers, so the inner loop is conflict-free LDS.128 + FFMA and never touches global memory;
+//   * every warp keeps its running top-kc as packed 64-bit keys in registers (kc/32 per lane); a row is looked at
+//     again only if it beats the warp's threshold (one FSETP per row), and only then is the filter evaluated;
+//   * at the end the 8 warp lists are rank-merged through shared memory into one sorted list per CTA; a second,
+//     single-CTA kernel merges the per-CTA lists.  The N-long score vector never exists.
+#include "common.cuh"
+
+namespace rebert {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kStageBytes = 48 * 1024;
+constexpr int kMaxStages = 4;
+
+struct GemvParams {
+    const void*  rows;
+    const float* inv_norm;
+    const float* q;        // [ld] fp32
+    int64_t      n;
+    int64_t      num_tiles;
+    int          ld;
+    int          cpl;       // runtime chunks per lane (generic kernel)
+    int          tile_rows;
+    int          stages;
+    int          kc;
+    DevFilter    filter;
+    uint64_t*    cta_lists; // [grid, kc]
+};
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int EPC = 4;
+    __device__ static __forceinline__ void dot(const uint4& v, const float* q, float& acc) {
+        acc = fmaf(__uint_as_float(v.x), q[0], acc);
+        acc = fmaf(__uint_as_float(v.y), q[1], acc);
+        acc = fmaf(__uint_as_float(v.z), q[2], acc);
+        acc = fmaf(__uint_as_float(v.w), q[3], acc);
+    }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int EPC = 8;
+    __device__ static __forceinline__ void dot(const uint4& v, const float* q, float& acc) {
+        acc = fmaf(bf16lo(v.x), q[0], acc);
+        acc = fmaf(bf16hi(v.x), q[1], acc);
+        acc = fmaf(bf16lo(v.y), q[2], acc);
+        acc = fmaf(bf16hi(v.y), q[3], acc);
+        acc = fmaf(bf16lo(v.z), q[4], acc);
+        acc = fmaf(bf16hi(v.z), q[5], acc);
+        acc = fmaf(bf16lo(v.w), q[6], acc);
+        acc = fmaf(bf16hi(v.w), q[7], acc);
+    }
+};
+
+// Warp-distributed sorted list of M*32 keys: entry e = m*32 + lane, best first.
+template <int M>
+struct WarpTopK {
+    uint64_t keys[M];
+    float    thr;   // score of the worst kept entry once the list is full, else -inf
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int m = 0; m < M; ++m) keys[m] = 0;
+        thr = -INFINITY;
+    }
+    // All lanes call with the same (warp-uniform) key.  Rows arrive in ascending order per warp, so a new key
+    // never ties-and-wins against a kept one: strict "greater" decides the slot.
+    __device__ __forceinline__ void insert(uint64_t key, int lane) {
+        int pos = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) pos += __popc(__ballot_sync(0xffffffffu, keys[m] > key));
+#pragma unroll
+        for (int m = M - 1; m >= 0; --m) {
+            uint64_t up = __shfl_up_sync(0xffffffffu, keys[m], 1);
+            if (m > 0) {
+                uint64_t prev_last = __shfl_sync(0xffffffffu, keys[m - 1], 31);
+                if (lane == 0) up = prev_last;
+            }
+            int e = m * 32 + lane;
+            keys[m] = e < pos ? keys[m] : (e == pos ? key : up);
+        }
+        uint64_t last = __shfl_sync(0xffffffffu, keys[M - 1], 31);
+        thr = last ? key_score(last) : -INFINITY;
+    }
+};
+
+template <typename T, int CPL, int LANES, int M>
+__global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams p) {
+    constexpr int EPC = Elem<T>::EPC;
+    constexpr int RPW = 32 / LANES;              // rows a warp scores at once
+    constexpr bool kRegQ = CPL > 0;              // query chunks live in registers
+    constexpr int QREGS = kRegQ ? CPL * EPC : 1;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int row_bytes = p.ld * (int)sizeof(T);
+    const int tile_bytes = p.tile_rows * row_bytes;
+    const int inv_bytes = p.tile_rows * 4;                       // tile_rows is a multiple of 4
+    const int stage_stride = tile_bytes + ((inv_bytes + 127) & ~127);
+    unsigned char* stage_base = smem;
+    uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_stride);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    float* q_smem = (float*)(empty_bar + kMaxStages);            // generic kernel only: [ld]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    if (!kRegQ) {
+        for (int c = threadIdx.x; c < p.ld; c += blockDim.x) q_smem[c] = p.q[c];
+    }
+    __syncthreads();
+
+    WarpTopK<M> top;
+    top.init();
+
+    if (warp == kConsumerWarps) {
+        // ===================== producer warp: one elected lane issues the bulk copies =====================
+        if (lane == 0) {
+            const uint64_t policy = l2_policy_evict_first();
+            int it = 0;
+            for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                const int s = it % p.stages;
+                const uint32_t round = (uint32_t)(it / p.stages);
+                mbar_wait(&empty_bar[s], (round & 1u) ^ 1u);
+                const int64_t row0 = t * p.tile_rows;
+                const int64_t left = p.n - row0;
+                const int nrows = left < p.tile_rows ? (int)left : p.tile_rows;
+                const uint32_t bytes = (uint32_t)nrows * (uint32_t)row_bytes;
+                const uint32_t ibytes = (uint32_t)(nrows & ~3) * 4u;   // tail (<4 rows) is read through __ldg
+                unsigned char* dst = stage_base + (size_t)s * stage_stride;
+                mbar_arrive_expect_tx(&full_bar[s], bytes + ibytes);
+                bulk_g2s(dst, (const unsigned char*)p.rows + row0 * row_bytes, bytes, &full_bar[s], policy);
+                if (ibytes) bulk_g2s(dst + tile_bytes, p.inv_norm + row0, ibytes, &full_bar[s], policy);
+            }
+        }
+    } else {
+        // ===================== consumer warps =====================
+        const int sub = lane / LANES;            // which of the warp's RPW rows this lane works on
+        const int cl = lane % LANES;             // chunk lane within the row
+        float q[QREGS];
+        if (kRegQ) {
+#pragma unroll
+            for (int j = 0; j < (kRegQ ? CPL : 0); ++j)
+#pragma unroll
+                for (int e = 0; e < EPC; ++e) q[j * EPC + e] = __ldg(p.q + (j * LANES + cl) * EPC + e);
+        }
+        const int cpl = kRegQ ? CPL : p.cpl;
+        const int row_chunks = cpl * LANES;
+
+        int it = 0;
+        for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int s = it % p.stages;
+            const uint32_t round = (uint32_t)(it / p.stages);
+            const int64_t row0 = t * p.tile_rows;
+            const int64_t left = p.n - row0;
+            const int nrows = left < p.tile_rows ? (int)left : p.tile_rows;
+            const int nrows4 = nrows & ~3;
+            const unsigned char* st = stage_base + (size_t)s * stage_stride;
+            const uint4* tile = (const uint4*)st;
+            const float* inv_s = (const float*)(st + tile_bytes);
+
+            mbar_wait(&full_bar[s], round & 1u);
+
+            // two row groups per step for ILP: rows rA and rB = rA + kConsumerWarps*RPW
+            for (int base = warp * RPW; base < nrows; base += 2 * kConsumerWarps * RPW) {
+                const int rA = base + sub;
+                const int rB = rA + kConsumerWarps * RPW;
+                const bool vA = rA < nrows, vB = rB < nrows;
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                const uint4* pa = tile + (size_t)(vA ? rA : 0) * row_chunks + cl;
+                const uint4* pb = tile + (size_t)(vB ? rB : 0) * row_chunks + cl;
+                if (kRegQ) {
+#pragma unroll
+                    for (int j = 0; j < (kRegQ ? CPL : 0); ++j) {
+                        const uint4 va = pa[j * LANES];
+                        const uint4 vb = pb[j * LANES];
+                        if (j & 1) { Elem<T>::dot(va, q + j * EPC, a1); Elem<T>::dot(vb, q + j * EPC, b1); }
+                        else       { Elem<T>::dot(va, q + j * EPC, a0); Elem<T>::dot(vb, q + j * EPC, b0); }
+                    }
+                } else {
+                    for (int j = 0; j < cpl; ++j) {
+                        const uint4 va = pa[j * LANES];
+                        const uint4 vb = pb[j * LANES];
+                        float qq[EPC];
+                        const float4* qs = (const float4*)(q_smem + (j * LANES + cl) * EPC);
+#pragma unroll
+                        for (int e = 0; e < EPC / 4; ++e) {
+                            float4 f = qs[e];
+                            qq[e * 4 + 0] = f.x; qq[e * 4 + 1] = f.y; qq[e * 4 + 2] = f.z; qq[e * 4 + 3] = f.w;
+                        }
+                        if (j & 1) { Elem<T>::dot(va, qq, a1); Elem<T>::dot(vb, qq, b1); }
+                        else       { Elem<T>::dot(va, qq, a0); Elem<T>::dot(vb, qq, b0); }
+                    }
+                }
+                float sa = a0 + a1, sb = b0 + b1;
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                }
+                const float ia = vA ? (rA < nrows4 ? inv_s[rA] : __ldg(p.inv_norm + row0 + rA)) : 0.f;
+                const float ib = vB ? (rB < nrows4 ? inv_s[rB] : __ldg(p.inv_norm + row0 + rB)) : 0.f;
+                sa *= ia;
+                sb *= ib;
+
+                // rare path: some row of this step beats the warp threshold.  Row order A(sub 0..), then B(sub 0..)
+                // is ascending, which WarpTopK::insert relies on.
+                unsigned ma = __ballot_sync(0xffffffffu, vA && cl == 0 && sa > top.thr);
+                while (ma) {
+                    const int src = __ffs(ma) - 1;
+                    ma &= ma - 1;
+                    const float sc = __shfl_sync(0xffffffffu, sa, src);
+                    const uint32_t lr = (uint32_t)(row0 + base + src / LANES);
+                    if (sc > top.thr && row_allowed(p.filter, lr)) top.insert(make_key(sc, lr), lane);
+                }
+                unsigned mb = __ballot_sync(0xffffffffu, vB && cl == 0 && sb > top.thr);
+                while (mb) {
+                    const int src = __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    const float sc = __shfl_sync(0xffffffffu, sb, src);
+                    const uint32_t lr = (uint32_t)(row0 + base + kConsumerWarps * RPW + src / LANES);
+                    if (sc > top.thr && row_allowed(p.filter, lr)) top.insert(make_key(sc, lr), lane);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+    }
+
+    // ===================== CTA merge: 8 sorted warp lists -> one sorted list of kc keys =====================
+    __syncthreads();   // every stage has been consumed; the pipeline memory is free to reuse
+    uint64_t* lists = (uint64_t*)smem;           // [kConsumerWarps][kc]
+    const int kc = p.kc;
+    if (warp < kConsumerWarps) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) lists[warp * kc + m * 32 + lane] = top.keys[m];
+    }
+    __syncthreads();
+    uint64_t* out = p.cta_lists + (size_t)blockIdx.x * kc;
+    int total = 0;
+    for (int w = 0; w < kConsumerWarps; ++w) {   // non-empty entries per list (lists are sorted, zeros last)
+        const uint64_t* L = lists + w * kc;
+        int lo = 0, hi = kc;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (L[mid] != 0) lo = mid + 1; else hi = mid; }
+        total += lo;
+    }
+    for (int i = threadIdx.x; i < kConsumerWarps * kc; i += blockDim.x) {
+        const uint64_t key = lists[i];
+        if (key == 0) continue;
+        const int w = i / kc;
+        int rank = i - w * kc;
+        for (int o = 0; o < kConsumerWarps; ++o) {
+            if (o == w) continue;
+            const uint64_t* L = lists + o * kc;
+            int lo = 0, hi = kc;                 // count of keys in L greater than key
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (L[mid] > key) lo = mid + 1; else hi = mid; }
+            rank += lo;
+        }
+        if (rank < kc) out[rank] = key;
+    }
+    for (int i = total + threadIdx.x; i < kc; i += blockDim.x) out[i] = 0;
+}
+
+// Single CTA: merge `lists` sorted lists of kc keys each into the best kc (sorted).  Entries are processed in
+// chunks that fit shared memory; each round keeps the running best kc at the front.
+constexpr int kMergeThreads = 1024;
+constexpr int kMergeCap = 16384;   // keys per round (128 KB)
+
+__global__ void __launch_bounds__(kMergeThreads, 1)
+merge_lists_kernel(const uint64_t* __restrict__ in, int total, int kc, int cap, uint64_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint64_t buf[];
+    int done = 0;       // input entries consumed
+    int carried = 0;    // best-so-far entries at buf[0 .. carried)
+    while (true) {
+        int take = total - done;
+        if (take > cap - carried) take = cap - carried;
+        for (int i = threadIdx.x; i < take; i += blockDim.x) buf[carried + i] = in[done + i];
+        int filled = carried + take;
+        int p2 = 1;
+        while (p2 < filled) p2 <<= 1;
+        if (p2 < 2) p2 = 2;
+        for (int i = filled + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
+        __syncthreads();
+        block_bitonic_sort_desc(buf, p2);
+        done += take;
+        carried = kc;
+        if (done >= total) break;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
+}
+
+// ---------------------------------------------------------------- host side ----------------------------------
+struct GemvLaunch {
+    int grid, stages, tile_rows;
+    size_t smem;
+};
+
+static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic) {
+    GemvLaunch g;
+    const int row_bytes = L.ld * L.esize;
+    const int rpw = 32 / L.lanes;
+    int tr = kStageBytes / row_bytes;
+    const int unit = kConsumerWarps * rpw;           // rows one step of all warps covers
+    if (tr >= 2 * unit) tr = (tr / (2 * unit)) * (2 * unit);
+    else if (tr >= unit) tr = unit;
+    tr &= ~3;
+    if (tr < 4) tr = 4;
+    g.tile_rows = tr;
+    const int tile_bytes = tr * row_bytes;
+    const int stage_stride = tile_bytes + ((tr * 4 + 127) & ~127);
+    const size_t fixed = 2 * kMaxStages * sizeof(uint64_t) + (generic ? (size_t)L.ld * 4 : 0) + 128;
+    int stages = kMaxStages;
+    while (stages > 1 && (size_t)stages * stage_stride + fixed > 220 * 1024) --stages;
+    g.stages = stages;
+    g.smem = (size_t)stages * stage_stride + fixed;
+    const size_t merge_bytes = (size_t)kConsumerWarps * kc * sizeof(uint64_t);
+    if (g.smem < merge_bytes) g.smem = merge_bytes;
+    const int64_t tiles = (n + tr - 1) / tr;
+    int grid = num_sms();
+    if (tiles < grid) grid = (int)(tiles > 0 ? tiles : 1);
+    g.grid = grid;
+    return g;
+}
+
+template <typename T, int CPL, int LANES>
+static int launch_gemv_m(const GemvParams& p, const GemvLaunch& g, int kc, cudaStream_t st) {
+#define REBERT_LAUNCH_M(MM)                                                                                      \
+    {                                                                                                            \
+        auto kern = gemv_topk_kernel<T, CPL, LANES, MM>;                                                         \
+        REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));       \
+        kern<<<g.grid, kThreads, g.smem, st>>>(p);                                                               \
+    }
+    switch (kc) {
+        case 32: REBERT_LAUNCH_M(1); break;
+        case 64: REBERT_LAUNCH_M(2); break;
+        case 128: REBERT_LAUNCH_M(4); break;
+        case 256: REBERT_LAUNCH_M(8); break;
+        default: set_error("gemv_topk: kc=%d is not one of 32/64/128/256", kc); return REBERT_ERR_UNSUPPORTED;
+    }
+#undef REBERT_LAUNCH_M
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+template <typename T>
+static int launch_gemv(const RowLayout& L, const GemvParams& p, const GemvLaunch& g, int kc, cudaStream_t st) {
+    if (L.lanes < 32) {
+        switch (L.lanes) {
+            case 2: return launch_gemv_m<T, 1, 2>(p, g, kc, st);
+            case 4: return launch_gemv_m<T, 1, 4>(p, g, kc, st);
+            case 8: return launch_gemv_m<T, 1, 8>(p, g, kc, st);
+            case 16: return launch_gemv_m<T, 1, 16>(p, g, kc, st);
+        }
+    }
+    switch (L.cpl) {
+        case 1: return launch_gemv_m<T, 1, 32>(p, g, kc, st);
+        case 2: return launch_gemv_m<T, 2, 32>(p, g, kc, st);
+        case 3: return launch_gemv_m<T, 3, 32>(p, g, kc, st);
+        case 4: return launch_gemv_m<T, 4, 32>(p, g, kc, st);
+        case 6: return launch_gemv_m<T, 6, 32>(p, g, kc, st);
+        case 12: return launch_gemv_m<T, 12, 32>(p, g, kc, st);
+        default: return launch_gemv_m<T, 0, 32>(p, g, kc, st);
+    }
+}
+
+static bool use_generic(const RowLayout& L) {
+    if (L.lanes < 32) return false;
+    switch (L.cpl) { case 1: case 2: case 3: case 4: case 6: case 12: return false; }
+    return true;
+}
+
+}  // namespace rebert
+
+using namespace rebert;
+
+extern "C" {
+
+REBERT_API int32_t rebert_candidates_for_k(int32_t k) {
+    if (k <= 0) return 0;
+    int need = k + 16;                 // margin for the fp32 -> fp64 re-ranking
+    if (need <= 32) return 32;
+    if (need <= 64) return 64;
+    if (need <= 128) return 128;
+    if (need <= 256) return 256;
+    return 0;
+}
+
+REBERT_API size_t rebert_gemv_workspace_bytes(int64_t n, int32_t kc) {
+    (void)n;
+    return (size_t)(num_sms() + 1) * (size_t)kc * sizeof(uint64_t) + 256;
+}
+
+REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, int32_t kc,
+                     void* workspace, size_t workspace_bytes, uint64_t* cand_keys, rebert_stream stream) {
+    REBERT_REQUIRE(cat && cat->rows && cat->inv_norm && qn32 && workspace && cand_keys, "gemv_topk: null argument");
+    REBERT_REQUIRE(cat->n >= 0 && cat->n < (1ll << 31), "gemv_topk: shard rows %lld out of range", (long long)cat->n);
+    REBERT_REQUIRE(cat->dtype == REBERT_F32 || cat->dtype == REBERT_BF16, "gemv_topk: dtype %d", cat->dtype);
+    REBERT_REQUIRE(((uintptr_t)cat->rows & 127) == 0 && ((uintptr_t)cat->inv_norm & 15) == 0,
+                   "gemv_topk: catalog rows must be 128-byte and inv_norm 16-byte aligned");
+    RowLayout L = row_layout(cat->d, cat->dtype);
+    REBERT_REQUIRE(L.ld == cat->ld, "gemv_topk: ld=%d does not match rebert_catalog_layout (%d)", cat->ld, L.ld);
+    if (L.ld * L.esize > kStageBytes / 4) {
+        set_error("gemv_topk: rows of %d bytes exceed the %d-byte staging limit", L.ld * L.esize, kStageBytes / 4);
+        return REBERT_ERR_UNSUPPORTED;
+    }
+    if (workspace_bytes < rebert_gemv_workspace_bytes(cat->n, kc)) {
+        set_error("gemv_topk: workspace %zu < %zu", workspace_bytes, rebert_gemv_workspace_bytes(cat->n, kc));
+        return REBERT_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cat->n == 0) {
+        REBERT_CUDA(cudaMemsetAsync(cand_keys, 0, (size_t)kc * sizeof(uint64_t), st));
+        return REBERT_OK;
+    }
+    const bool generic = use_generic(L);
+    GemvLaunch g = plan_gemv(L, cat->n, kc, generic);
+    GemvParams p;
+    p.rows = cat->rows;
+    p.inv_norm = cat->inv_norm;
+    p.q = qn32;
+    p.n = cat->n;
+    p.ld = L.ld;
+    p.cpl = L.cpl;
+    p.tile_rows = g.tile_rows;
+    p.num_tiles = (cat->n + g.tile_rows - 1) / g.tile_rows;
+    p.stages = g.stages;
+    p.kc = kc;
+    p.filter = make_filter(filter, cat->row_base);
+    p.cta_lists = (uint64_t*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
+
+    int rc = cat->dtype == REBERT_F32 ? launch_gemv<float>(L, p, g, kc, st) : launch_gemv<__nv_bfloat16>(L, p, g, kc, st);
+    if (rc != REBERT_OK) return rc;
+
+    const int total = g.grid * kc;
+    int cap = 2;
+    while (cap < total && cap < kMergeCap) cap <<= 1;
+    if (cap < 2 * kc) cap = 2 * kc;
+    const size_t msmem = (size_t)cap * sizeof(uint64_t);
+    REBERT_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    merge_lists_kernel<<<1, kMergeThreads, msmem, st>>>(p.cta_lists, total, kc, cap, cand_keys);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/rebert_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from robot_ebert_b200 import _native as nat
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(REPO, "include", "rebert_b200.h")).read()
+    return sorted(set(re.findall(r"REBERT_API[^;(]*?\b(rebert_\w+)\s*\(", src)))
+
+
+def test_header_declares_functions():
+    names = _header_functions()
+    assert len(names) >= 20 and "rebert_gemv_topk" in names and "rebert_gemm_topk" in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    for name in _header_functions():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+
+
+def test_binding_matches_header():
+    assert sorted(nat.exported_symbols()) == _header_functions()
+    lib = nat.load()
+    assert lib.rebert_abi_version() == 1
+
+
+def test_layout_and_candidates_host_logic():
+    from robot_ebert_b200 import CatalogStore
+    assert CatalogStore.layout(10, 1536, "bf16") == (1536, 10 * 1536 * 2)
+    assert CatalogStore.layout(10, 1536, "fp32") == (1536, 10 * 1536 * 4)
+    assert CatalogStore.layout(4, 32, "fp32")[0] == 32          # production collab shape: 128-byte rows
+    assert CatalogStore.layout(4, 50, "bf16")[0] == 64          # padded to a power-of-two chunk count
+    assert CatalogStore.layout(4, 2200, "bf16")[0] == 2304      # 9 chunks per lane
+    lib = nat.load()
+    assert [lib.rebert_candidates_for_k(k) for k in (1, 10, 16, 17, 48, 100, 112, 113, 240, 241)] == \
+        [32, 32, 32, 64, 64, 128, 128, 256, 256, 0]
+    with pytest.raises(ValueError):
+        CatalogStore.layout(4, 0, "fp32")
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must raise, not compute on the CPU."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from robot_ebert_b200 import CatalogStore
+    with pytest.raises(RuntimeError):
+        CatalogStore.from_host(None, np.zeros((4, 8), np.float32))
+
+
+def test_product_never_imports_oracle():
+    """Product code must not import, call or execute anything under oracle/ (it is test infrastructure)."""
+    pkg = os.path.join(REPO, "robot_ebert_b200")
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)|oracle/|oracle\.", re.M)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                assert not pat.search(open(os.path.join(root, f)).read()), f

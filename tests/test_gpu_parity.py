@@ -1,0 +1,180 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_scoring as ora
+from robot_ebert_b200 import CatalogStore, RowFilter, synth
+from tests.helpers import build_catalog_f32, build_catalog_f64
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-9      # fp64 re-score vs the float64 oracle (north_star allows 1e-5 for fp32)
+
+
+def _stored_f64(store: CatalogStore) -> np.ndarray:
+    return store.rows[:store.n, :store.d].to(torch.float64).cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("d,scale", [(32, False), (50, True), (1536, True)])
+def test_synth_generator_bit_identical(dtype, d, scale):
+    n, row0 = 300, 12345
+    store = CatalogStore.synthetic(7, n, d, dtype, scale_rows=scale, row0=row0)
+    want = synth.quantise(synth.catalog_rows_f32(7, row0, n, d, scale), dtype)
+    np.testing.assert_array_equal(_stored_f64(store), want)
+    if store.ld > d:
+        assert float(store.rows[:, d:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_catalog_build_and_norms(dtype):
+    m = synth.catalog_rows_f32(3, 0, 500, 96, scale_rows=True)
+    m[17] = 0.0
+    store = CatalogStore.from_host(synth.row_ids(500), m, dtype)
+    want = synth.quantise(m, dtype)
+    np.testing.assert_array_equal(_stored_f64(store), want)
+    nrm = np.sqrt(np.einsum("ij,ij->i", want, want))
+    nrm[nrm == 0] = 1.0
+    np.testing.assert_allclose(store.norm64[:500].cpu().numpy(), nrm, rtol=1e-14)
+    np.testing.assert_allclose(store.inv_norm[:500].cpu().numpy(), (1.0 / nrm).astype(np.float32), rtol=1e-6)
+    assert store.norm64[17].item() == 1.0
+
+
+def test_golden_user_recs(golden):
+    """Every get_user_recs case the unmodified reference produced: ids exact, scores to 1e-9 relative."""
+    stores = {}
+    checked = 0
+    for case in golden["user_recs"]:
+        spec = golden["catalogs"][case["catalog"]]
+        if case["catalog"] not in stores:
+            m = build_catalog_f32(spec)
+            stores[case["catalog"]] = CatalogStore.from_host(synth.row_ids(m.shape[0]), m, spec["dtype"])
+        store = stores[case["catalog"]]
+        rated = [(store.row_of(i), r) for i, r in case["ratings"] if store.row_of(i) is not None]   # lib.py:44
+        if not case["ratings"]:
+            continue                                                                                # lib.py:39-40
+        liked = np.array([r for r, x in rated if x >= 3.5], dtype=np.int64)
+        excl = np.array([r for r, _ in rated], dtype=np.int64)
+        if case.get("raises"):
+            with pytest.raises(ValueError):
+                store.recommend(liked_rows=liked, exclude_rows=excl, k=case["k"])
+            continue
+        rows, scores, info = store.recommend(liked_rows=liked, exclude_rows=excl, k=case["k"], return_info=True)
+        assert [store.id_of(r) for r in rows] == [e[0] for e in case["expect"]], case["user_id"]
+        np.testing.assert_allclose(scores, [e[1] for e in case["expect"]], rtol=SCORE_RTOL, atol=1e-15)
+        checked += 1
+    assert checked >= 20
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("n,d,k", [(10_000, 1536, 10), (50_000, 1536, 100), (4099, 32, 10), (20_001, 50, 25),
+                                   (3000, 1000, 10), (2500, 2200, 10), (70_000, 256, 50), (1, 1536, 10), (33, 8, 10)])
+def test_single_query_vs_oracle(dtype, n, d, k):
+    store = CatalogStore.synthetic(0, n, d, dtype, scale_rows=True)
+    m = _stored_f64(store)
+    q = synth.query_f32(1, d)
+    rng = np.random.default_rng(5)
+    excl = rng.choice(n, size=min(n // 2, 133), replace=False) if n > 1 else np.array([], dtype=np.int64)
+    rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True)
+    want_rows, want_scores = ora.query_rows(m, q.astype(np.float64), excl, k)
+    assert info["proven_exact"]
+    np.testing.assert_array_equal(rows, want_rows)
+    np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=1e-15)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_user_profile_vs_oracle(dtype):
+    n, d = 30_000, 1536
+    store = CatalogStore.synthetic(0, n, d, dtype, scale_rows=True)
+    m = _stored_f64(store)
+    for rows_u, rts in synth.user_ratings(2, n, 3):
+        liked = rows_u[rts >= 3.5]
+        got_rows, got_scores = store.recommend(liked_rows=liked, exclude_rows=rows_u, k=10)
+        want_rows, want_scores = ora.recommend_rows(m, liked, rows_u, 10)
+        np.testing.assert_array_equal(got_rows, want_rows)
+        np.testing.assert_allclose(got_scores, want_scores, rtol=SCORE_RTOL, atol=1e-15)
+
+
+def test_ties_zero_rows_and_short_lists():
+    n, d = 5000, 64
+    m = synth.catalog_rows_f32(9, 0, n, d)
+    dups = [4000, 17, 2500, 900, 4999, 3]
+    for r in dups:
+        m[r] = m[100]                  # exact duplicates of row 100 -> exact score ties
+    m[7] = 0.0                         # zero-norm row must score exactly 0
+    store = CatalogStore.from_host(synth.row_ids(n), m, "fp32")
+    q = m[100].copy()
+    rows, scores = store.recommend(query=q, k=5)
+    assert rows.tolist() == sorted(dups + [100])[:5]          # ties resolved by ascending row
+    want_rows, want_scores = ora.query_rows(m.astype(np.float64), q.astype(np.float64), None, 5)
+    np.testing.assert_array_equal(rows, want_rows)
+    # all but 3 rows excluded -> fewer than k results, like lib.py:55 on a short `unrated`
+    keep = [7, 100, 4321]
+    excl = np.setdiff1d(np.arange(n), keep)
+    rows, scores = store.recommend(query=q, exclude_rows=excl, k=10)
+    want_rows, want_scores = ora.query_rows(m.astype(np.float64), q.astype(np.float64), excl, 10)
+    np.testing.assert_array_equal(rows, want_rows)
+    np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=1e-15)
+    assert scores[rows.tolist().index(7)] == 0.0
+    # everything excluded -> empty
+    rows, scores = store.recommend(query=q, exclude_rows=np.arange(n), k=10)
+    assert rows.shape == (0,) and scores.shape == (0,)
+
+
+def test_predicate_filter_and_bitmap():
+    n, d = 40_000, 128
+    store = CatalogStore.synthetic(4, n, d, "bf16")
+    g, y = synth.movie_metadata(3, 0, n)
+    store.set_metadata(g, y)
+    m = _stored_f64(store)
+    q = synth.query_f32(1, d)
+    keep = ((g & 0b1011) != 0) & (y >= 1960) & (y <= 2000)
+    rows, scores = store.recommend(query=q, k=50, row_filter=RowFilter(genre_any=0b1011, year_lo=1960, year_hi=2000))
+    want_rows, want_scores = ora.query_rows(m, q.astype(np.float64), None, 50, keep_mask=keep)
+    np.testing.assert_array_equal(rows, want_rows)
+    # same mask expressed as an exclusion bitmap
+    bits = np.packbits(~keep, bitorder="little")
+    bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, np.uint8)]).view(np.int32)
+    bm = torch.from_numpy(bits.copy()).to(store.device)
+    rows2, _ = store.recommend(query=q, k=50, row_filter=RowFilter(exclude_bitmap=bm))
+    np.testing.assert_array_equal(rows2, want_rows)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_million_rows_against_dense_scores(dtype):
+    """BASELINE config 2 size: the fused path against the independent dense-score kernel + torch.topk."""
+    n, d, k = 1_000_000, 1536, 10
+    store = CatalogStore.synthetic(0, n, d, dtype)
+    q = synth.query_f32(1, d)
+    excl = np.random.default_rng(1).choice(n, size=133, replace=False)
+    rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True)
+    assert info["proven_exact"]
+    qn = (q.astype(np.float64) / np.linalg.norm(q.astype(np.float64)))
+    q32 = torch.zeros((1, store.ld), dtype=torch.float32, device=store.device)
+    q32[0, :d] = torch.from_numpy(qn.astype(np.float32)).to(store.device)
+    dense = store.scores_dense(q32)[0]
+    dense[torch.from_numpy(excl).to(store.device)] = -float("inf")
+    top = torch.topk(dense, k + 8)
+    cand = top.indices.cpu().numpy()
+    # exact fp64 scores of the dense path's candidates, computed on the host from regenerated rows
+    exact = []
+    for r in cand:
+        row = synth.quantise(synth.catalog_rows_f32(0, int(r), 1, d), dtype)[0]
+        exact.append(float(row @ qn / np.linalg.norm(row)))
+    order = np.lexsort((cand, -np.array(exact)))[:k]
+    np.testing.assert_array_equal(rows, cand[order])
+    np.testing.assert_allclose(scores, np.array(exact)[order], rtol=SCORE_RTOL)
+
+
+def test_unsupported_and_invalid_arguments():
+    store = CatalogStore.synthetic(0, 100, 32, "fp32")
+    q = synth.query_f32(1, 32)
+    with pytest.raises(ValueError):
+        store.recommend(query=q, k=0)
+    with pytest.raises(ValueError):
+        store.recommend(query=q, k=1000)
+    with pytest.raises(ValueError):
+        store.recommend(query=q[:5], k=3)
+    with pytest.raises(ValueError):
+        store.recommend(query=q, liked_rows=np.array([1]), k=3)
