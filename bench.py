@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the recommendation scoring hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--rows R]
+
+Workload (BASELINE.json `metric`): single-query cosine top-10 with a 133-row seen-movie exclusion over a
+10M x 1536 bf16 synthetic catalog.  One step = one query through the whole hot path.
+  N = 1 : the whole catalog on one B200 (30.7 GB).
+  N > 1 : the same 10M catalog row-sharded over N ranks (strong scaling), local top-k + NCCL all-gather + merge.
+`value`  : queries/s with the query already resident in HBM (kernels only).
+`e2e`    : queries/s through CatalogStore.recommend / ShardedCatalog.recommend with HOST buffers in and out
+           (pinned H2D of the request, D2H of the result, stream sync) inside the timed region.
+`--impl reference` times the reference's own CPU path (oracle/, pandas + scikit-learn, float64, all host threads) on
+a bounded row sample of the same workload and scales to the full catalog.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+N_ROWS, DIM, DTYPE, K, N_EXCL = 10_000_000, 1536, "bf16", 10, 133
+METRIC = "queries/s top-k cosine retrieval (10M x 1536 bf16)"
+
+
+def workload_name(rows):
+    return f"single-query cosine top-{K} + {N_EXCL}-row exclusion over {rows} x {DIM} {DTYPE} synthetic catalog"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(key):
+    path = os.path.join(REPO, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(key)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_leg(rows_full: int, steps: int, warmup: int, sample_rows: int):
+    """The reference's own CPU path (restated lib.py:51-55, L=1) on `sample_rows` rows; returns (q/s scaled to
+    rows_full, description, seconds per sample query, cores)."""
+    from oracle import reference_scoring as ora
+    from robot_ebert_b200 import synth
+    sample_rows = min(sample_rows, rows_full)
+    m = np.empty((sample_rows, DIM), dtype=np.float64)
+    for s in range(0, sample_rows, 8192):
+        e = min(sample_rows, s + 8192)
+        m[s:e] = synth.quantise(synth.catalog_rows_f32(0, s, e - s, DIM), DTYPE)
+    emb = ora.catalog_frame(synth.row_ids(sample_rows), m)              # float64 frame, string index (constants.py:56)
+    q = synth.query_f32(1, DIM).astype(np.float64)
+    excl_rows = np.random.default_rng(1).choice(sample_rows, size=N_EXCL, replace=False)
+    excl_ids = [emb.index[r] for r in excl_rows]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ora.single_query(emb, q, excl_ids, K)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    qps = 1.0 / (t * rows_full / sample_rows)
+    desc = (f"{len(times)} queries over the first {sample_rows} of {rows_full} rows x {DIM} (float64 DataFrame, pandas + "
+            f"sklearn cosine_similarity + sort, as lib.py:51-55); per-query time scaled by {rows_full / sample_rows:.0f}x")
+    return qps, desc, t, os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = args.rows or N_ROWS
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    sample = args.cpu_sample_rows
+    qps, desc, t, cores = cpu_reference_leg(rows, steps, warmup, sample)
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 / qps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(rows), "rows": rows, "dim": DIM, "k": K},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from robot_ebert_b200 import CatalogStore, synth
+    from robot_ebert_b200 import _native as nat
+    from robot_ebert_b200.sharding import CudaShardBackend, ShardedCatalog
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the scoring path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rows = args.rows or N_ROWS
+    steps, warmup = args.steps, max(3, args.warmup)
+    lib = nat.load()
+    kc = lib.rebert_candidates_for_k(K)
+
+    if world > 1:
+        sharded = ShardedCatalog.synthetic(0, rows, DIM, DTYPE, device=dev)
+        store = sharded.backend.store
+    else:
+        sharded = None
+        store = CatalogStore.synthetic(0, rows, DIM, DTYPE, device=dev)
+    q = synth.query_f32(1, DIM)
+    excl = np.random.default_rng(1).choice(rows, size=N_EXCL, replace=False).astype(np.int64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness of this very configuration, once, before timing (cheap: regenerates only the winners on host)
+    api = sharded if sharded is not None else store
+    got_rows, got_scores, info = api.recommend(query=q, exclude_rows=excl, k=K, return_info=True)
+    qn = q.astype(np.float64) / np.linalg.norm(q.astype(np.float64))
+    for r, sc in zip(got_rows, got_scores):
+        row = synth.quantise(synth.catalog_rows_f32(0, int(r), 1, DIM), DTYPE)[0]
+        ref = float(row @ qn / np.linalg.norm(row))
+        assert abs(ref - sc) <= 1e-9 * max(1.0, abs(ref)), (r, sc, ref)
+    assert info["proven_exact"] and len(got_rows) == K and not set(got_rows.tolist()) & set(excl.tolist())
+
+    # ---- value: device-resident query, kernels only
+    excl_ptr, ne = store.stage_inputs(q, None, None, excl, K, kc)
+    torch.cuda.synchronize()
+    scratch = store._scratch()
+    filt = nat.Filter()
+    filt.exclude_rows, filt.n_exclude = excl_ptr, ne
+    import ctypes as C
+    ob = scratch.d_out.data_ptr()
+
+    def step(ev=None):
+        st = torch.cuda.current_stream().cuda_stream
+        if ev is not None:
+            ev[0].record()
+        nat.check(lib.rebert_gemv_topk(C.byref(store._c), scratch.qn32.data_ptr(), C.byref(filt), kc, scratch.ws.data_ptr(),
+                                       scratch.ws.numel(), scratch.cand.data_ptr(), st))
+        if ev is not None:
+            ev[1].record()
+        nat.check(lib.rebert_finalize_topk(C.byref(store._c), scratch.qn64.data_ptr(), scratch.cand.data_ptr(), kc, K, ob,
+                                           ob + 8 * K, ob + 16 * K, ob + 16 * K + 8, st))
+        if sharded is not None:
+            buf = sharded._gather_buf(K, scratch.d_out)
+            dist.all_gather_into_tensor(buf.view(-1), scratch.d_out)
+            sharded.backend.merge(buf, K)
+
+    for _ in range(warmup):
+        step()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        t0.record()
+        for i in range(steps):
+            step(kev[i])
+        t1.record()
+        barrier()
+    elapsed_ms = t0.elapsed_time(t1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / steps
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        t = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_ms = float(t.item())
+    value = steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, through the public API
+    for _ in range(warmup):
+        api.recommend(query=q, exclude_rows=excl, k=K)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        api.recommend(query=q, exclude_rows=excl, k=K)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = steps / e2e_s
+    h2d, d2h = int(store.last_h2d_bytes), (2 * K + 2) * 8
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        shard_rows = store.n
+        alg_bytes = shard_rows * DIM * 2                                  # catalog bytes one launch must read
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 storage, fp32 accumulate, fp64 re-score", "data": "synthetic",
+            "config": {"workload": workload_name(rows), "rows": rows, "dim": DIM, "k": K, "exclusions": N_EXCL,
+                       "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                       "l2": f"inputs larger than L2 ({alg_bytes / 1e9:.2f} GB read per step per GPU)"},
+            "roofline": {"bound": "hbm", "kernel": "gemv_topk_kernel<bf16> (+ its 1-CTA list merge)", "achieved": achieved,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
+                         "traffic": ncu_traffic(f"gemv_topk_bf16_{shard_rows}")},
+            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / steps},
+            "gpu_launches": steps * (3 + (1 if world > 1 else 0)),
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            qps, desc, _, cores = cpu_reference_leg(rows, 5, 1, args.cpu_sample_rows)
+            line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=0, help="override catalog rows (default 10M)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,9 +134,13 @@ REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* q
                          rebert_stream stream);
 
 /* ---- merge of per-shard results (lib.py:55 across shards) --------------------------------- */
-/* For each of b queries merge `lists` sorted result lists [lists, b, k] (rows, scores, counts[lists, b]) into the best k. */
-REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, const int32_t* counts, int32_t lists, int32_t b,
-                      int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_stream stream);
+/* For each of b queries merge `lists` sorted result lists into the best k.  List l of query u is at
+ * rows[l*rows_stride + u*k ..], scores[l*scores_stride + u*k ..], counts[l*counts_stride + u] (strides in elements):
+ * a dense [lists, b, k] layout has strides (b*k, b*k, b); the packed per-rank buffers of an all-gather have one
+ * common byte stride expressed in each array's element size. */
+REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, const int32_t* counts, int64_t rows_stride,
+                      int64_t scores_stride, int64_t counts_stride, int32_t lists, int32_t b, int32_t k,
+                      int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_stream stream);
 
 /* ---- subset scoring for the search re-rank (lib.py:105-106) ------------------------------- */
 /* out[u, j] = <p64[u], row sub_rows[j]> / norm64 in fp64 for m candidate GLOBAL rows (all must be in this shard). */

@@ -66,13 +66,19 @@ class _Scratch:
             self.ws = torch.empty(wsb, dtype=torch.uint8, device=self.store.device)
             self.cand = torch.empty(kc, dtype=torch.int64, device=self.store.device)   # u64 keys
             self.kc = kc
-        if k > self.k_cap:
-            cap = max(16, 1 << (k - 1).bit_length())
-            nbytes = cap * 16 + 16
-            self.d_out = torch.empty(nbytes, dtype=torch.uint8, device=self.store.device)
-            self.h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        if k != self.k_cap:
+            # packed result, int64 words: rows[k] | scores[k] (fp64 bits) | count (int32, low half) | margin (fp64 bits)
+            self.d_out = torch.empty(2 * k + 2, dtype=torch.int64, device=self.store.device)
+            self.h_out = torch.empty(2 * k + 2, dtype=torch.int64).pin_memory()
             self.h_out_np = self.h_out.numpy()
-            self.k_cap = cap
+            self.k_cap = k
+
+
+def unpack_result(words: np.ndarray, k: int):
+    """Split a packed result (see _Scratch.ensure_out) into (rows int64[k'], scores f64[k'], margin)."""
+    cnt = int(words[2 * k:2 * k + 1].view(np.int32)[0])
+    margin = float(words[2 * k + 1:2 * k + 2].view(np.float64)[0])
+    return words[:cnt].copy(), words[k:k + cnt].view(np.float64).copy(), margin
 
 
 class CatalogStore:
@@ -234,6 +240,19 @@ class CatalogStore:
 
     def _recommend_once(self, lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter):
         s = self._scratch()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream()
+            excl_ptr, ne = self.stage_inputs(query, liked_rows, weights, exclude_rows, k, kc)
+            self.enqueue_topk(k, kc, excl_ptr, ne, row_filter)
+            s.h_out.copy_(s.d_out, non_blocking=True)
+            stream.synchronize()
+        return unpack_result(s.h_out_np, k)
+
+    def stage_inputs(self, query, liked_rows, weights, exclude_rows, k, kc, profile_partial_only: bool = False):
+        """Pack the request into one pinned buffer, issue ONE H2D copy, and enqueue query normalisation or the
+        profile build on the current stream.  Returns (device pointer of the exclusion list, its length)."""
+        lib = nat.load()
+        s = self._scratch()
         d, ld = self.d, self.ld
         excl = None
         if exclude_rows is not None and len(exclude_rows):
@@ -246,8 +265,6 @@ class CatalogStore:
             if nl == 0:
                 # same failure the reference hits: sklearn's check_array on an empty frame
                 raise ValueError("Found array with 0 sample(s): user has no liked movies in the catalog")
-        # ---- pack every input into one pinned buffer -> one H2D copy
-        off_q = 0
         off_rp = _align(4 * d)
         off_e = off_rp + 16
         off_c = off_e + _align(4 * ne)
@@ -260,7 +277,7 @@ class CatalogStore:
             q = np.asarray(query, dtype=np.float32)
             if q.shape != (d,):
                 raise ValueError(f"query must have shape ({d},)")
-            h[off_q:off_q + 4 * d].view(np.float32)[:] = q
+            h[0:4 * d].view(np.float32)[:] = q
         else:
             h[off_rp:off_rp + 16].view(np.int64)[:] = (0, nl)
             h[off_c:off_c + 4 * nl].view(np.int32)[:] = liked
@@ -268,48 +285,55 @@ class CatalogStore:
                 h[off_w:off_w + 4 * nl].view(np.float32)[:] = np.asarray(weights, dtype=np.float32)
         if ne:
             h[off_e:off_e + 4 * ne].view(np.int32)[:] = excl
+        self.last_h2d_bytes = total
+        st = torch.cuda.current_stream().cuda_stream
+        s.d_in[:total].copy_(s.h_in[:total], non_blocking=True)
+        base = s.d_in.data_ptr()
+        if query is not None:
+            nat.check(lib.rebert_query_normalize(base, 1, d, ld, s.qn32.data_ptr(), s.qn64.data_ptr(), st))
+        else:
+            nat.check(lib.rebert_profile_accumulate(C.byref(self._c), base + off_rp, base + off_c,
+                                                    (base + off_w) if weights is not None else None, 1,
+                                                    s.sum64.data_ptr(), s.wsum.data_ptr(), st))
+            if not profile_partial_only:
+                self.finalize_profile()
+        return (base + off_e) if ne else None, ne
 
-        with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream()
-            st = stream.cuda_stream
-            s.d_in[:total].copy_(s.h_in[:total], non_blocking=True)
-            base = s.d_in.data_ptr()
-            if query is not None:
-                nat.check(lib.rebert_query_normalize(base + off_q, 1, d, ld, s.qn32.data_ptr(), s.qn64.data_ptr(), st))
-            else:
-                nat.check(lib.rebert_profile_accumulate(C.byref(self._c), base + off_rp, base + off_c,
-                                                        (base + off_w) if weights is not None else None, 1,
-                                                        s.sum64.data_ptr(), s.wsum.data_ptr(), st))
-                nat.check(lib.rebert_profile_finalize(s.sum64.data_ptr(), s.wsum.data_ptr(), 1, ld, s.qn32.data_ptr(),
-                                                      s.qn64.data_ptr(), None, st))
-            f = nat.Filter()
-            if ne:
-                f.exclude_rows, f.n_exclude = base + off_e, ne
-            if row_filter is not None:
-                if row_filter.exclude_bitmap is not None:
-                    f.exclude_bitmap = row_filter.exclude_bitmap.data_ptr()
-                if row_filter.genre_any:
-                    if self.genre_bits is None:
-                        raise ValueError("row_filter.genre_any needs set_metadata()")
-                    f.genre_bits, f.genre_any = self.genre_bits.data_ptr(), row_filter.genre_any
-                if (row_filter.year_lo, row_filter.year_hi) != (0, 65535):
-                    if self.year is None:
-                        raise ValueError("row_filter year range needs set_metadata()")
-                    f.year, f.year_lo, f.year_hi = self.year.data_ptr(), row_filter.year_lo, row_filter.year_hi
-            nat.check(lib.rebert_gemv_topk(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
-                                           s.ws.numel(), s.cand.data_ptr(), st))
-            kcap = s.k_cap
-            ob = s.d_out.data_ptr()
-            nat.check(lib.rebert_finalize_topk(C.byref(self._c), s.qn64.data_ptr(), s.cand.data_ptr(), kc, k, ob,
-                                               ob + 8 * kcap, ob + 16 * kcap, ob + 16 * kcap + 8, st))
-            s.h_out.copy_(s.d_out, non_blocking=True)
-            stream.synchronize()
-        o = s.h_out_np
-        cnt = int(o[16 * kcap:16 * kcap + 4].view(np.int32)[0])
-        margin = float(o[16 * kcap + 8:16 * kcap + 16].view(np.float64)[0])
-        rows = o[:8 * kcap].view(np.int64)[:cnt].copy()
-        scores = o[8 * kcap:16 * kcap].view(np.float64)[:cnt].copy()
-        return rows, scores, margin
+    def finalize_profile(self):
+        """scratch.sum64 / scratch.wsum -> scratch.qn32 / qn64 (the mean of unit rows, lib.py:52)."""
+        lib = nat.load()
+        s = self._scratch()
+        nat.check(lib.rebert_profile_finalize(s.sum64.data_ptr(), s.wsum.data_ptr(), 1, self.ld, s.qn32.data_ptr(),
+                                              s.qn64.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+
+    def enqueue_topk(self, k: int, kc: int, excl_ptr=None, n_excl: int = 0, row_filter: Optional[RowFilter] = None):
+        """Device-resident step: fused score+mask+top-k over the shard, then the exact fp64 pass, for the query /
+        profile already sitting in this thread's scratch (qn32, qn64).  Result lands packed in scratch.d_out.
+        Nothing is copied and nothing synchronises."""
+        lib = nat.load()
+        s = self._scratch()
+        s.ensure_out(k, kc)
+        st = torch.cuda.current_stream().cuda_stream
+        f = nat.Filter()
+        if n_excl:
+            f.exclude_rows, f.n_exclude = excl_ptr, n_excl
+        if row_filter is not None:
+            if row_filter.exclude_bitmap is not None:
+                f.exclude_bitmap = row_filter.exclude_bitmap.data_ptr()
+            if row_filter.genre_any:
+                if self.genre_bits is None:
+                    raise ValueError("row_filter.genre_any needs set_metadata()")
+                f.genre_bits, f.genre_any = self.genre_bits.data_ptr(), row_filter.genre_any
+            if (row_filter.year_lo, row_filter.year_hi) != (0, 65535):
+                if self.year is None:
+                    raise ValueError("row_filter year range needs set_metadata()")
+                f.year, f.year_lo, f.year_hi = self.year.data_ptr(), row_filter.year_lo, row_filter.year_hi
+        nat.check(lib.rebert_gemv_topk(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
+                                       s.ws.numel(), s.cand.data_ptr(), st))
+        ob = s.d_out.data_ptr()
+        nat.check(lib.rebert_finalize_topk(C.byref(self._c), s.qn64.data_ptr(), s.cand.data_ptr(), kc, k, ob,
+                                           ob + 8 * k, ob + 16 * k, ob + 16 * k + 8, st))
+        return s.d_out
 
     # ------------------------------------------------------------------ diagnostics -------------
     def scores_dense(self, q32: torch.Tensor) -> torch.Tensor:

@@ -84,29 +84,32 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
     }
 }
 
-// One CTA per query: rank-merge `lists` sorted lists of up to k entries each.
+// One CTA per query: rank-merge `lists` sorted lists of up to k entries each.  List l of query u lives at
+// rows[l * rows_stride + u * k + e], scores[l * scores_stride + u * k + e], counts[l * counts_stride + u]
+// (strides in elements), which covers both a dense [lists, b, k] layout and the packed per-rank buffers an
+// all-gather produces.
 __global__ void merge_topk_kernel(const int64_t* __restrict__ rows, const double* __restrict__ scores,
-                                  const int32_t* __restrict__ counts, int lists, int b, int k,
-                                  int64_t* __restrict__ out_rows, double* __restrict__ out_scores,
-                                  int32_t* __restrict__ out_count) {
+                                  const int32_t* __restrict__ counts, int64_t rows_stride, int64_t scores_stride,
+                                  int64_t counts_stride, int lists, int k, int64_t* __restrict__ out_rows,
+                                  double* __restrict__ out_scores, int32_t* __restrict__ out_count) {
     const int u = blockIdx.x;
     int total = 0;
-    for (int l = 0; l < lists; ++l) total += counts[(size_t)l * b + u];
+    for (int l = 0; l < lists; ++l) total += min(counts[l * counts_stride + u], k);
     const int nout = total < k ? total : k;
     for (int i = threadIdx.x; i < lists * k; i += blockDim.x) {
         const int l = i / k, e = i - l * k;
-        if (e >= counts[(size_t)l * b + u]) continue;
-        const size_t off = ((size_t)l * b + u) * k;
-        const double sc = scores[off + e];
-        const int64_t r = rows[off + e];
+        if (e >= counts[l * counts_stride + u]) continue;
+        const double sc = scores[l * scores_stride + (int64_t)u * k + e];
+        const int64_t r = rows[l * rows_stride + (int64_t)u * k + e];
         int rank = e;
         for (int o = 0; o < lists; ++o) {
             if (o == l) continue;
-            const size_t oo = ((size_t)o * b + u) * k;
-            int lo = 0, hi = counts[(size_t)o * b + u];      // entries of list o better than (sc, r)
+            const int64_t* orow = rows + o * rows_stride + (int64_t)u * k;
+            const double* osc = scores + o * scores_stride + (int64_t)u * k;
+            int lo = 0, hi = min(counts[o * counts_stride + u], k);      // entries of list o better than (sc, r)
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (better(scores[oo + mid], rows[oo + mid], sc, r)) lo = mid + 1; else hi = mid;
+                if (better(osc[mid], orow[mid], sc, r)) lo = mid + 1; else hi = mid;
             }
             rank += lo;
         }
@@ -152,11 +155,13 @@ REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* q
                            (cudaStream_t)stream);
 }
 
-REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, const int32_t* counts, int32_t lists, int32_t b,
-                      int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_stream stream) {
+REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, const int32_t* counts, int64_t rows_stride,
+                      int64_t scores_stride, int64_t counts_stride, int32_t lists, int32_t b, int32_t k,
+                      int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_stream stream) {
     REBERT_REQUIRE(rows && scores && counts && out_rows && out_scores && out_count, "merge_topk: null argument");
     REBERT_REQUIRE(lists > 0 && b > 0 && k > 0, "merge_topk: lists=%d b=%d k=%d", lists, b, k);
-    merge_topk_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(rows, scores, counts, lists, b, k, out_rows, out_scores, out_count);
+    merge_topk_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(rows, scores, counts, rows_stride, scores_stride, counts_stride,
+                                                           lists, k, out_rows, out_scores, out_count);
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }

@@ -1,0 +1,151 @@
+"""Row-sharding layer: one process per GPU, catalog split row-wise, local top-k + all-gather + merge.
+
+SURVEY.md §8(e): score(j) depends only on catalog row j and the replicated query, so rank g owns the contiguous
+rows [g*N/G, (g+1)*N/G) and the only exchange step is an all-gather of each rank's k best (row, score) pairs
+(k*16+16 bytes per rank), followed by the same (score desc, row asc) merge on every rank — so every rank returns
+the result a single GPU would.  Building a user profile from liked rows scattered over the shards adds one
+all-reduce(sum) of the fp64 partial profile [ld+1].
+
+The collective plumbing is torch.distributed (NCCL on GPUs).  The arithmetic is behind a small backend object so
+the host logic can be exercised with gloo on CPU in tests; the product backend (`CudaShardBackend`) is CUDA-only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as nat
+from .catalog import CatalogStore, RowFilter, unpack_result
+
+
+class ShardPlan:
+    """Contiguous, balanced row ranges; rank g owns [start(g), start(g+1))."""
+
+    def __init__(self, n_total: int, world: int):
+        if n_total < 0 or world <= 0:
+            raise ValueError("bad shard plan")
+        self.n_total, self.world = int(n_total), int(world)
+
+    def start(self, g: int) -> int:
+        return (self.n_total * g) // self.world
+
+    def range(self, g: int) -> Tuple[int, int]:
+        """(row0, nrows) of rank g."""
+        return self.start(g), self.start(g + 1) - self.start(g)
+
+    def owner(self, row: int) -> int:
+        if not 0 <= row < self.n_total:
+            raise ValueError("row out of range")
+        g = min(self.world - 1, (row * self.world) // max(self.n_total, 1))
+        while row < self.start(g):
+            g -= 1
+        while row >= self.start(g + 1):
+            g += 1
+        return g
+
+
+class CudaShardBackend:
+    """Product backend: the local shard is a CatalogStore; every step is a kernel enqueued on the current stream."""
+
+    def __init__(self, store: CatalogStore):
+        self.store = store
+        self.device = store.device
+        self._merged = {}
+
+    def stage(self, query, liked_rows, weights, exclude_rows, k, kc):
+        st = self.store
+        self._excl = st.stage_inputs(query, liked_rows, weights, exclude_rows, k, kc, profile_partial_only=True)
+        if liked_rows is None:
+            return None
+        s = st._scratch()
+        return torch.cat([s.sum64, s.wsum])                      # fp64 [ld + 1] partial profile
+
+    def set_profile(self, summed: torch.Tensor):
+        st = self.store
+        s = st._scratch()
+        s.sum64.copy_(summed[:st.ld])
+        # wsum is summed over ranks too, but every rank added the full weight sum: divide it back
+        s.wsum.copy_(summed[st.ld:] / self._world)
+        st.finalize_profile()
+
+    def local_topk(self, k: int, kc: int, row_filter: Optional[RowFilter]) -> torch.Tensor:
+        ptr, ne = self._excl
+        return self.store.enqueue_topk(k, kc, ptr, ne, row_filter)
+
+    def merge(self, gathered: torch.Tensor, k: int) -> torch.Tensor:
+        """gathered int64 [G, 2k+2] packed per-rank results -> packed merged result int64 [2k+2] (margin = min)."""
+        lib = nat.load()
+        g = gathered.shape[0]
+        out = self._merged.get(k)
+        if out is None:
+            out = self._merged[k] = torch.empty(2 * k + 2, dtype=torch.int64, device=self.device)
+        base, w = gathered.data_ptr(), 2 * k + 2
+        ob = out.data_ptr()
+        nat.check(lib.rebert_merge_topk(base, base + 8 * k, base + 16 * k, w, w, 2 * w, g, 1, k, ob, ob + 8 * k, ob + 16 * k,
+                                        torch.cuda.current_stream().cuda_stream))
+        out[2 * k + 1:2 * k + 2].view(torch.float64).copy_(gathered[:, 2 * k + 1].view(torch.float64).min().reshape(1))
+        return out
+
+    def fetch(self, packed: torch.Tensor, k: int):
+        return unpack_result(packed.cpu().numpy(), k)
+
+
+class ShardedCatalog:
+    """The sharding layer.  Every rank calls recommend() with the same arguments and gets the same answer."""
+
+    def __init__(self, backend, n_total: int, group=None):
+        self.backend = backend
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.plan = ShardPlan(n_total, self.world)
+        backend._world = self.world
+        self._gather = {}
+
+    @classmethod
+    def synthetic(cls, seed: int, n_total: int, d: int, dtype: str = "bf16", scale_rows: bool = False, device=None,
+                  group=None) -> "ShardedCatalog":
+        plan = ShardPlan(n_total, dist.get_world_size(group))
+        row0, n = plan.range(dist.get_rank(group))
+        store = CatalogStore.synthetic(seed, n, d, dtype, scale_rows=scale_rows, device=device, row0=row0)
+        return cls(CudaShardBackend(store), n_total, group)
+
+    def _gather_buf(self, k: int, like: torch.Tensor) -> torch.Tensor:
+        buf = self._gather.get(k)
+        if buf is None:
+            buf = self._gather[k] = torch.empty((self.world, 2 * k + 2), dtype=torch.int64, device=like.device)
+        return buf
+
+    def enqueue(self, k: int, kc: int, row_filter=None) -> torch.Tensor:
+        """Device-resident step for an already staged query: local top-k -> all-gather -> merge (packed result)."""
+        local = self.backend.local_topk(k, kc, row_filter)
+        buf = self._gather_buf(k, local)
+        dist.all_gather_into_tensor(buf.view(-1), local, group=self.group)
+        return self.backend.merge(buf, k)
+
+    def recommend(self, *, query=None, liked_rows=None, weights=None, exclude_rows=None, k: int = 10, row_filter=None,
+                  return_info: bool = False):
+        if (query is None) == (liked_rows is None):
+            raise ValueError("pass exactly one of query / liked_rows")
+        lib = nat.load()
+        kc = lib.rebert_candidates_for_k(k)
+        if kc == 0:
+            raise ValueError(f"k={k} is outside the supported range (1..240)")
+        eps = getattr(getattr(self.backend, "store", None), "fast_eps", 0.0)
+        while True:
+            partial = self.backend.stage(query, liked_rows, weights, exclude_rows, k, kc)
+            if partial is not None:
+                dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
+                self.backend.set_profile(partial)
+            packed = self.enqueue(k, kc, row_filter)
+            rows, scores, margin = self.backend.fetch(packed, k)
+            if margin > eps or kc >= 256:
+                break
+            kc = min(256, kc * 4)
+        if return_info:
+            return rows, scores, {"kc": kc, "margin": margin, "proven_exact": margin > eps}
+        return rows, scores
