@@ -278,13 +278,13 @@ def run_b200(args):
             "config": {"workload": workload_name(rows), "rows": rows, "dim": DIM, "k": K, "exclusions": N_EXCL,
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e9:.2f} GB read per step per GPU)"},
-            "roofline": {"bound": "hbm", "kernel": "gemv_topk_kernel<bf16> (+ its 1-CTA list merge)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "gemv_topk_kernel<bf16,6,32,1> (scores + mask + top-k + cross-CTA merge, one launch)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
                          "traffic": ncu_traffic(f"gemv_topk_bf16_{shard_rows}")},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / steps},
-            "gpu_launches": steps * (3 + (1 if world > 1 else 0)),
+            "gpu_launches": steps * (2 + (1 if world > 1 else 0)),
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -8,8 +8,9 @@
 //     registers, so the inner loop is conflict-free LDS.128 + FFMA and never touches global memory;
 //   * every warp keeps its running top-kc as packed 64-bit keys in registers (kc/32 per lane); a row is looked at
 //     again only if it beats the warp's threshold (one FSETP per row), and only then is the filter evaluated;
-//   * at the end the 8 warp lists are rank-merged through shared memory into one sorted list per CTA; a second,
-//     single-CTA kernel merges the per-CTA lists.  The N-long score vector never exists.
+//   * at the end the 8 warp lists are rank-merged through shared memory into one sorted list per CTA, and the last
+//     CTA to finish (atomic ticket) merges the per-CTA lists behind two pruning thresholds — one launch per query.
+//     The N-long score vector never exists.
 #include "common.cuh"
 
 namespace rebert {
@@ -32,6 +33,9 @@ struct GemvParams {
     int          kc;
     DevFilter    filter;
     uint64_t*    cta_lists; // [grid, kc]
+    uint64_t*    cand_keys; // [kc] final output
+    unsigned*    counter;   // CTAs finished (zero before launch; the last CTA resets it)
+    int          merge_cap; // keys the final merge may hold in shared memory (power of two)
 };
 
 template <typename T> struct Elem;
@@ -89,6 +93,92 @@ struct WarpTopK {
         thr = last ? key_score(last) : -INFINITY;
     }
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// Final merge, run by the LAST CTA to finish (no second launch): `lists` sorted lists of kc keys -> best kc.
+// Two cheap lower bounds on the kc-th best key prune almost everything before any sorting:
+//   T0 = max over lists of their kc-th key            (that one list alone holds kc keys >= T0)
+//   T1 = kc-th largest key among the first P = ceil(kc / lists) keys of every list
+// Keys >= max(T0, T1) (typically kc + a few) are gathered into shared memory and bitonic-sorted.  If a pathological
+// input (mass ties) overflows the buffer, a chunked full sort over all keys is used instead.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t ldcg_u64(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
+
+__device__ void chunked_merge(const uint64_t* __restrict__ in, int total, int kc, int cap, uint64_t* buf,
+                              uint64_t* __restrict__ out) {
+    int done = 0, carried = 0;
+    while (true) {
+        int take = total - done;
+        if (take > cap - carried) take = cap - carried;
+        for (int i = threadIdx.x; i < take; i += blockDim.x) buf[carried + i] = ldcg_u64(in + done + i);
+        const int filled = carried + take;
+        int p2 = 2;
+        while (p2 < filled) p2 <<= 1;
+        for (int i = filled + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
+        __syncthreads();
+        block_bitonic_sort_desc(buf, p2);
+        done += take;
+        carried = kc;
+        if (done >= total) break;
+    }
+    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
+}
+
+__device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int kc, int cap, uint64_t* buf,
+                            uint64_t* __restrict__ out) {
+    __shared__ unsigned long long s_t0, s_t1;
+    __shared__ int s_cnt;
+    const int total = lists * kc;
+    if (threadIdx.x == 0) { s_t0 = 0; s_t1 = 0; s_cnt = 0; }
+    __syncthreads();
+    // T0
+    unsigned long long t0 = 0;
+    for (int l = threadIdx.x; l < lists; l += blockDim.x) {
+        const unsigned long long v = ldcg_u64(lists_g + (size_t)l * kc + kc - 1);
+        t0 = v > t0 ? v : t0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, t0, o);
+        t0 = v > t0 ? v : t0;
+    }
+    if ((threadIdx.x & 31) == 0 && t0) atomicMax(&s_t0, t0);
+    // T1: prefix set of P keys per list, rank-count for the kc-th largest
+    const int P = (kc + lists - 1) / lists;
+    const int S = P * lists;                       // kc <= S < kc + lists <= cap
+    for (int e = threadIdx.x; e < S; e += blockDim.x) buf[e] = ldcg_u64(lists_g + (size_t)(e / P) * kc + (e % P));
+    __syncthreads();
+    for (int e = threadIdx.x; e < S; e += blockDim.x) {
+        const uint64_t key = buf[e];
+        if (key == 0) continue;
+        int rank = 0;
+        for (int j = 0; j < S; ++j) rank += buf[j] > key;
+        if (rank == kc - 1) s_t1 = key;            // keys are distinct, so exactly one thread can hit this
+    }
+    __syncthreads();
+    const uint64_t T = s_t0 > s_t1 ? s_t0 : s_t1;
+    // gather survivors
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint64_t key = ldcg_u64(lists_g + i);
+        if (key != 0 && key >= T) {
+            const int idx = atomicAdd(&s_cnt, 1);
+            if (idx < cap) buf[idx] = key;
+        }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt > cap) {                               // mass ties: correct but slow path
+        __syncthreads();
+        chunked_merge(lists_g, total, kc, cap, buf, out);
+        return;
+    }
+    int p2 = 2;
+    while (p2 < cnt || p2 < kc) p2 <<= 1;
+    for (int i = cnt + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
+    __syncthreads();
+    block_bitonic_sort_desc(buf, p2);
+    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
+}
 
 template <typename T, int CPL, int LANES, int M>
 __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams p) {
@@ -270,40 +360,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
         if (rank < kc) out[rank] = key;
     }
     for (int i = total + threadIdx.x; i < kc; i += blockDim.x) out[i] = 0;
-}
 
-// Single CTA: merge `lists` sorted lists of kc keys each into the best kc (sorted).  Entries are processed in
-// chunks that fit shared memory; each round keeps the running best kc at the front.
-constexpr int kMergeThreads = 1024;
-constexpr int kMergeCap = 16384;   // keys per round (128 KB)
-
-__global__ void __launch_bounds__(kMergeThreads, 1)
-merge_lists_kernel(const uint64_t* __restrict__ in, int total, int kc, int cap, uint64_t* __restrict__ out) {
-    extern __shared__ __align__(16) uint64_t buf[];
-    int done = 0;       // input entries consumed
-    int carried = 0;    // best-so-far entries at buf[0 .. carried)
-    while (true) {
-        int take = total - done;
-        if (take > cap - carried) take = cap - carried;
-        for (int i = threadIdx.x; i < take; i += blockDim.x) buf[carried + i] = in[done + i];
-        int filled = carried + take;
-        int p2 = 1;
-        while (p2 < filled) p2 <<= 1;
-        if (p2 < 2) p2 = 2;
-        for (int i = filled + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
-        __syncthreads();
-        block_bitonic_sort_desc(buf, p2);
-        done += take;
-        carried = kc;
-        if (done >= total) break;
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
+    // ===================== last CTA to finish merges all per-CTA lists (no second launch) =====================
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    final_merge(p.cta_lists, (int)gridDim.x, kc, p.merge_cap, (uint64_t*)smem, p.cand_keys);
+    if (threadIdx.x == 0) *p.counter = 0;
 }
 
 // ---------------------------------------------------------------- host side ----------------------------------
 struct GemvLaunch {
-    int grid, stages, tile_rows;
+    int grid, stages, tile_rows, merge_cap;
     size_t smem;
 };
 
@@ -325,8 +397,15 @@ static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic)
     while (stages > 1 && (size_t)stages * stage_stride + fixed > 220 * 1024) --stages;
     g.stages = stages;
     g.smem = (size_t)stages * stage_stride + fixed;
-    const size_t merge_bytes = (size_t)kConsumerWarps * kc * sizeof(uint64_t);
+    size_t merge_bytes = (size_t)kConsumerWarps * kc * sizeof(uint64_t);
     if (g.smem < merge_bytes) g.smem = merge_bytes;
+    // final merge buffer: a power of two >= max(2 kc, kc + grid), as large as the pipeline memory allows (<= 16384 keys)
+    int need = 2 * kc > kc + num_sms() ? 2 * kc : kc + num_sms();
+    int cap = 2;
+    while (cap < need) cap <<= 1;
+    while (cap < 16384 && (size_t)cap * 2 * sizeof(uint64_t) <= g.smem) cap <<= 1;
+    if (g.smem < (size_t)cap * sizeof(uint64_t)) g.smem = (size_t)cap * sizeof(uint64_t);
+    g.merge_cap = cap;
     const int64_t tiles = (n + tr - 1) / tr;
     int grid = num_sms();
     if (tiles < grid) grid = (int)(tiles > 0 ? tiles : 1);
@@ -439,19 +518,12 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.kc = kc;
     p.filter = make_filter(filter, cat->row_base);
     p.cta_lists = (uint64_t*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
+    p.counter = (unsigned*)(p.cta_lists + (size_t)num_sms() * kc);
+    p.cand_keys = cand_keys;
+    p.merge_cap = g.merge_cap;
+    REBERT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned), st));
 
-    int rc = cat->dtype == REBERT_F32 ? launch_gemv<float>(L, p, g, kc, st) : launch_gemv<__nv_bfloat16>(L, p, g, kc, st);
-    if (rc != REBERT_OK) return rc;
-
-    const int total = g.grid * kc;
-    int cap = 2;
-    while (cap < total && cap < kMergeCap) cap <<= 1;
-    if (cap < 2 * kc) cap = 2 * kc;
-    const size_t msmem = (size_t)cap * sizeof(uint64_t);
-    REBERT_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    merge_lists_kernel<<<1, kMergeThreads, msmem, st>>>(p.cta_lists, total, kc, cap, cand_keys);
-    REBERT_CUDA(cudaGetLastError());
-    return REBERT_OK;
+    return cat->dtype == REBERT_F32 ? launch_gemv<float>(L, p, g, kc, st) : launch_gemv<__nv_bfloat16>(L, p, g, kc, st);
 }
 
 }  // extern "C"
