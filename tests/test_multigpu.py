@@ -1,0 +1,61 @@
+"""Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2`): row-sharded result == single-GPU result, ids bit-exact."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n, d, dtype, out_q):
+    import torch.distributed as dist
+    from robot_ebert_b200 import synth
+    from robot_ebert_b200.sharding import ShardedCatalog
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        sc = ShardedCatalog.synthetic(0, n, d, dtype, scale_rows=True, device=torch.device("cuda", rank))
+        q = synth.query_f32(1, d)
+        excl = np.random.default_rng(3).choice(n, size=133, replace=False)
+        r1 = sc.recommend(query=q, exclude_rows=excl, k=10)
+        (rated, rts), = synth.user_ratings(2, n, 1)
+        r2 = sc.recommend(liked_rows=rated[rts >= 3.5], exclude_rows=rated, k=50)
+        out_q.put((rank, r1[0].tolist(), r1[1].tolist(), r2[0].tolist(), r2[1].tolist()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_sharded_equals_single_gpu(dtype):
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    from robot_ebert_b200 import CatalogStore, synth
+    n, d = 200_003, 1536
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, d, dtype, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out_q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    store = CatalogStore.synthetic(0, n, d, dtype, scale_rows=True, device="cuda:0")
+    q = synth.query_f32(1, d)
+    excl = np.random.default_rng(3).choice(n, size=133, replace=False)
+    w1 = store.recommend(query=q, exclude_rows=excl, k=10)
+    (rated, rts), = synth.user_ratings(2, n, 1)
+    w2 = store.recommend(liked_rows=rated[rts >= 3.5], exclude_rows=rated, k=50)
+    for rank, r1r, r1s, r2r, r2s in results:
+        assert r1r == w1[0].tolist() and r2r == w2[0].tolist(), rank
+        np.testing.assert_allclose(r1s, w1[1], rtol=1e-12)
+        np.testing.assert_allclose(r2s, w2[1], rtol=1e-12)
