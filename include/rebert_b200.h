@@ -105,9 +105,10 @@ REBERT_API int rebert_catalog_norms(const void* rows, int64_t n, int32_t ld, int
                          rebert_stream stream);
 
 /* ---- query / profile (lib.py:51-52) ------------------------------------------------------- */
-/* b queries q[b, d] fp32 -> unit vectors: qn64 = q / ||q|| (fp64, zero norm -> 1), qn32 = (float) qn64; both [b, ld]. */
+/* b queries q[b, d] fp32 -> unit vectors: qn64 = q / ||q|| (fp64, zero norm -> 1), qn32 = (float) qn64,
+ * qnbf16 = bf16(qn32) for the tensor-core path; all [b, ld], any output may be NULL. */
 REBERT_API int rebert_query_normalize(const float* q, int32_t b, int32_t d, int32_t ld, float* qn32, double* qn64,
-                           rebert_stream stream);
+                           void* qnbf16, rebert_stream stream);
 /* Ragged CSR gather-sum over THIS shard's rows: for user u, sum64[u, :] += w * row / norm64[row] for every
  * entry whose global row `col` lies in [row_base, row_base + n); wsum[u] += w for EVERY entry (so it is the
  * same on all shards).  w == NULL means weight 1 (the reference's 1[rating >= 3.5]).  Outputs are overwritten. */
@@ -127,7 +128,7 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
                      void* workspace, size_t workspace_bytes, uint64_t* cand_keys, rebert_stream stream);
 /* Exact pass over the kc candidates: fp64 re-score with the oracle's formula (x/||x||, y/||y||, dot), order by
  * (score desc, global row asc), write the best k.  out_count[0] = results written (<= k).
- * out_margin[0] = (exact k-th score) - (fast score of the worst kept candidate) when the candidate list was
+ * out_margin[0] = (exact k-th score) - (fast score of the worst kept candidate) - 4 max|fast - exact| when the list was
  * full, else +inf: a caller proves the set exact by margin > eps and retries with more candidates otherwise. */
 REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* qn64, const uint64_t* cand_keys, int32_t kc,
                          int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin,

@@ -44,7 +44,7 @@ _SIGS = {
     "rebert_catalog_layout": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
     "rebert_catalog_store_rows": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "rebert_catalog_norms": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
-    "rebert_query_normalize": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "rebert_query_normalize": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "rebert_profile_accumulate": (C.c_int, [C.POINTER(Catalog), _P, _P, _P, C.c_int32, _P, _P, _P]),
     "rebert_profile_finalize": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "rebert_candidates_for_k": (C.c_int32, [C.c_int32]),

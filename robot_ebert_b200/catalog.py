@@ -290,7 +290,7 @@ class CatalogStore:
         s.d_in[:total].copy_(s.h_in[:total], non_blocking=True)
         base = s.d_in.data_ptr()
         if query is not None:
-            nat.check(lib.rebert_query_normalize(base, 1, d, ld, s.qn32.data_ptr(), s.qn64.data_ptr(), st))
+            nat.check(lib.rebert_query_normalize(base, 1, d, ld, s.qn32.data_ptr(), s.qn64.data_ptr(), None, st))
         else:
             nat.check(lib.rebert_profile_accumulate(C.byref(self._c), base + off_rp, base + off_c,
                                                     (base + off_w) if weights is not None else None, 1,
@@ -334,6 +334,102 @@ class CatalogStore:
         nat.check(lib.rebert_finalize_topk(C.byref(self._c), s.qn64.data_ptr(), s.cand.data_ptr(), kc, k, ob,
                                            ob + 8 * k, ob + 16 * k, ob + 16 * k + 8, st))
         return s.d_out
+
+    # ------------------------------------------------------------------ batched (tensor cores) --
+    def prepare_queries(self, queries: np.ndarray):
+        """Host fp32 [b, d] query matrix -> device (qn32, qn64, qnbf16) unit vectors [b, ld]."""
+        lib = nat.load()
+        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device)
+        b = q.shape[0]
+        if q.shape[1] != self.d:
+            raise ValueError(f"queries must be [b, {self.d}]")
+        qn32 = torch.empty((b, self.ld), dtype=torch.float32, device=self.device)
+        qn64 = torch.empty((b, self.ld), dtype=torch.float64, device=self.device)
+        qbf = torch.empty((b, self.ld), dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(lib.rebert_query_normalize(q.data_ptr(), b, self.d, self.ld, qn32.data_ptr(), qn64.data_ptr(),
+                                                 qbf.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return qn32, qn64, qbf
+
+    def gemm_scores(self, qbf16: torch.Tensor, row0: int, nrows: int) -> torch.Tensor:
+        """fp32 scores [b, nrows] of rows [row0, row0+nrows) on the tensor cores (bf16 catalogs; multiples of 256)."""
+        lib = nat.load()
+        b = qbf16.shape[0]
+        out = torch.empty((b, nrows), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(lib.rebert_gemm_scores(C.byref(self._c), qbf16.data_ptr(), b, row0, nrows, out.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def gemm_plan(self, b: int, k: int) -> "nat.GemmPlan":
+        lib = nat.load()
+        plan = nat.GemmPlan()
+        nat.check(lib.rebert_gemm_plan(self.n, b, k, C.byref(plan)))
+        return plan
+
+    def enqueue_batch(self, plan, qbf16, q64, excl_ptr, excl_col, ws, out_rows, out_scores, out_count, out_status):
+        """Device-resident batched step (sample -> thresholds -> filtered GEMM -> select -> exact pass)."""
+        lib = nat.load()
+        nat.check(lib.rebert_gemm_topk(C.byref(self._c), qbf16.data_ptr(), q64.data_ptr(), _ptr(excl_ptr), _ptr(excl_col),
+                                       C.byref(plan), ws.data_ptr(), ws.numel(), out_rows.data_ptr(), out_scores.data_ptr(),
+                                       out_count.data_ptr(), out_status.data_ptr(), torch.cuda.current_stream().cuda_stream))
+
+    def recommend_batch(self, *, queries: Optional[np.ndarray] = None, liked_ptr: Optional[np.ndarray] = None,
+                        liked_col: Optional[np.ndarray] = None, liked_w: Optional[np.ndarray] = None,
+                        excl_ptr: Optional[np.ndarray] = None, excl_col: Optional[np.ndarray] = None, k: int = 10,
+                        return_info: bool = False):
+        """Top-k for many users at once (lib.py:51-55 per user) on the tcgen05 path.
+
+        queries [b, d] fp32, OR a ragged CSR of liked rows (liked_ptr[b+1], liked_col, optional weights).
+        excl_ptr/excl_col: per-user CSR of GLOBAL rows that must not be returned (sorted within a user).
+        Returns rows int64 [b, k] (-1 padded), scores float64 [b, k], counts int32 [b].  Queries the batched pass could
+        not prove exact (status != 0) are transparently re-run through the single-query kernel.
+        """
+        if (queries is None) == (liked_ptr is None):
+            raise ValueError("pass exactly one of queries / liked CSR")
+        lib = nat.load()
+        dev = self.device
+        with torch.cuda.device(dev):
+            if queries is not None:
+                qn32, qn64, qbf = self.prepare_queries(queries)
+            else:
+                lp = np.asarray(liked_ptr, dtype=np.int64)
+                if np.any(np.diff(lp) == 0):
+                    raise ValueError("Found array with 0 sample(s): a user has no liked movies in the catalog")
+                qn32, qn64, qbf = self.build_profiles(lp, liked_col, liked_w)
+            b = qbf.shape[0]
+            plan = self.gemm_plan(b, k)
+            ep = ec = None
+            if excl_ptr is not None:
+                ep = torch.from_numpy(np.asarray(excl_ptr, dtype=np.int64)).to(dev)
+                ec = torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(dev)
+            ws = torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(self._c), C.byref(plan)), dtype=torch.uint8, device=dev)
+            out_rows = torch.empty((b, k), dtype=torch.int64, device=dev)
+            out_scores = torch.empty((b, k), dtype=torch.float64, device=dev)
+            out_count = torch.empty(b, dtype=torch.int32, device=dev)
+            out_status = torch.empty(b, dtype=torch.int32, device=dev)
+            self.enqueue_batch(plan, qbf, qn64, ep, ec, ws, out_rows, out_scores, out_count, out_status)
+            rows, scores = out_rows.cpu().numpy(), out_scores.cpu().numpy()
+            counts, status = out_count.cpu().numpy(), out_status.cpu().numpy()
+            redo = np.nonzero(status)[0]
+            if len(redo):
+                s = self._scratch()
+                kc = lib.rebert_candidates_for_k(k)
+                ecp = None if excl_ptr is None else np.asarray(excl_ptr, dtype=np.int64)
+                for u in redo:                                   # exact single-query kernel for the unproven ones
+                    s.ensure_out(k, kc)
+                    s.qn32.copy_(qn32[u])
+                    s.qn64.copy_(qn64[u])
+                    ptr, ne = None, 0
+                    if ecp is not None and ecp[u + 1] > ecp[u]:
+                        ptr, ne = ec.data_ptr() + 4 * int(ecp[u]), int(ecp[u + 1] - ecp[u])
+                    self.enqueue_topk(k, kc, ptr, ne)
+                    r, sc, _ = unpack_result(s.d_out.cpu().numpy(), k)
+                    rows[u, :], scores[u, :] = -1, -np.inf
+                    rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
+        if return_info:
+            return rows, scores, counts, {"status": status, "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
+        return rows, scores, counts
 
     # ------------------------------------------------------------------ diagnostics -------------
     def scores_dense(self, q32: torch.Tensor) -> torch.Tensor:

@@ -140,7 +140,7 @@ __global__ void norms_kernel(const T* __restrict__ rows, int64_t n, int ld, floa
 
 // One CTA per query.
 __global__ void query_normalize_kernel(const float* __restrict__ q, int d, int ld, float* __restrict__ qn32,
-                                       double* __restrict__ qn64) {
+                                       double* __restrict__ qn64, __nv_bfloat16* __restrict__ qnbf16) {
     __shared__ double red[32];
     const float* src = q + (int64_t)blockIdx.x * d;
     double acc = 0.0;
@@ -163,6 +163,7 @@ __global__ void query_normalize_kernel(const float* __restrict__ q, int d, int l
         double v = c < d ? (double)src[c] / nrm : 0.0;
         if (qn64) qn64[(int64_t)blockIdx.x * ld + c] = v;
         if (qn32) qn32[(int64_t)blockIdx.x * ld + c] = (float)v;
+        if (qnbf16) qnbf16[(int64_t)blockIdx.x * ld + c] = __ushort_as_bfloat16(f32_to_bf16_rne((float)v));
     }
 }
 
@@ -317,9 +318,9 @@ REBERT_API int rebert_catalog_norms(const void* rows, int64_t n, int32_t ld, int
 }
 
 REBERT_API int rebert_query_normalize(const float* q, int32_t b, int32_t d, int32_t ld, float* qn32, double* qn64,
-                           rebert_stream stream) {
-    REBERT_REQUIRE(q && b > 0 && d > 0 && ld >= d && (qn32 || qn64), "query_normalize: bad arguments");
-    query_normalize_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(q, d, ld, qn32, qn64);
+                           void* qnbf16, rebert_stream stream) {
+    REBERT_REQUIRE(q && b > 0 && d > 0 && ld >= d && (qn32 || qn64 || qnbf16), "query_normalize: bad arguments");
+    query_normalize_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(q, d, ld, qn32, qn64, (__nv_bfloat16*)qnbf16);
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }

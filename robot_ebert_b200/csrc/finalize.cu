@@ -25,11 +25,12 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
     __shared__ int64_t s_row[kMaxKc];
     __shared__ int s_valid;
     __shared__ double s_kth;
+    __shared__ unsigned long long s_maxerr;      // bits of a non-negative double: integer order == numeric order
     const int u = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const uint64_t* keys = cand_keys + (size_t)u * kc;
     const double* q = q64 + (size_t)u * ld;
-    if (threadIdx.x == 0) { s_valid = 0; s_kth = 0.0; }
+    if (threadIdx.x == 0) { s_valid = 0; s_kth = 0.0; s_maxerr = 0ull; }
     __syncthreads();
 
     for (int c = warp; c < kc; c += nwarps) {
@@ -48,7 +49,10 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
         if (lane == 0) {
             s_score[c] = sc;
             s_row[c] = gr;
-            if (key != 0) atomicAdd(&s_valid, 1);
+            if (key != 0) {
+                atomicAdd(&s_valid, 1);
+                atomicMax(&s_maxerr, (unsigned long long)__double_as_longlong(fabs(sc - (double)key_score(key))));
+            }
         }
     }
     __syncthreads();
@@ -79,7 +83,10 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
         if (out_margin) {
             const uint64_t last = keys[kc - 1];
             // list full => rows outside it have fast score <= key_score(last); compare against the exact k-th
-            out_margin[u] = (last != 0 && valid >= k) ? s_kth - (double)key_score(last) : INFINITY;
+            // minus 4x the largest fast-vs-exact deviation seen on the candidates themselves: calibrates whatever
+            // rounding the fast pass had (fp32 accumulation, bf16 queries on the tensor-core path)
+            const double maxerr = __longlong_as_double((long long)s_maxerr);
+            out_margin[u] = (last != 0 && valid >= k) ? s_kth - (double)key_score(last) - 4.0 * maxerr : INFINITY;
         }
     }
 }

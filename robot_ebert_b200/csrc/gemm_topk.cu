@@ -1,10 +1,592 @@
-// Batched queries on the tensor cores — placeholder until the tcgen05 kernel lands (fails loudly, no fallback).
+// Batched queries on the 5th-gen tensor cores  (reference: lib.py:51-55 for many users at once).
+//
+// scores[q, j] = <Q[q, :], rows[j, :]> * inv_norm[j]  is a genuine dense contraction (B x N x D), so it runs as a
+// bf16 tcgen05 GEMM with fp32 accumulators in TMEM; the B x N score matrix is NEVER written.  Pipeline of
+// rebert_gemm_topk (everything enqueued on the caller's stream):
+//
+//   1. gemm<STORE>  over a strided SAMPLE of row tiles  -> sample scores [B, S]            (~1.5 % of the flops)
+//   2. select_threshold: per query, mask excluded sample rows, radix-select the r-th largest -> tau[q]
+//      (a lower bound of the query's k-th best that leaves ~8*kc rows above it in expectation)
+//   3. gemm<FILTER> over ALL row tiles: epilogue scales by inv_norm, compares with tau[q] (one FSETP per score,
+//      predicated smem staging, one atomicAdd per thread per tile) and appends (score,row) keys to cand[q]
+//   4. select_candidates: per query, drop excluded rows, bitonic top-kc of the few hundred survivors
+//   5. finalize_topk (csrc/finalize.cu): fp64 re-score, (score desc, row asc), best k, proof margin
+//   status[q] != 0 tells the caller to re-run that query through the single-query kernel (threshold too
+//   optimistic, buffer overflow or margin below eps) — exactness never depends on the sample being lucky.
+//
+// GEMM kernel anatomy (one CTA per SM, persistent, 192 threads):
+//   warp 0  : TMA producer  - cp.async.bulk.tensor.2d (SWIZZLE_128B) of Q tile [128 x 64] and row tile [256 x 64]
+//             per k-block into a 4-stage smem ring (48 KB / stage), mbarrier complete_tx
+//   warp 1  : MMA issuer    - one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) x4 per
+//             k-block, tcgen05.commit frees the smem stage; accumulators double-buffered in TMEM (2 x 256 columns)
+//   warps 2-5: epilogue     - tcgen05.ld 32x32b.x32 (thread = query row, 32 catalog columns per load), scale, filter
+//   Tile order: row-tile-major over (row tile, query tile) so concurrently running CTAs share the same catalog tile
+//   in L2 and the catalog streams from HBM once; Q (12.6 MB at B=4096) stays L2-resident.
+#include <cuda.h>
+
 #include "common.cuh"
-using namespace rebert;
-extern "C" {
-REBERT_API int rebert_gemm_plan(int64_t, int32_t, int32_t, rebert_gemm_plan_t*) { set_error("gemm path not built yet"); return REBERT_ERR_UNSUPPORTED; }
-REBERT_API size_t rebert_gemm_workspace_bytes(const rebert_catalog_t*, const rebert_gemm_plan_t*) { return 0; }
-REBERT_API int rebert_gemm_topk(const rebert_catalog_t*, const void*, const double*, const int64_t*, const int32_t*, const rebert_gemm_plan_t*,
-                     void*, size_t, int64_t*, double*, int32_t*, int32_t*, rebert_stream) { set_error("gemm path not built yet"); return REBERT_ERR_UNSUPPORTED; }
-REBERT_API int rebert_gemm_scores(const rebert_catalog_t*, const void*, int32_t, int64_t, int64_t, float*, rebert_stream) { set_error("gemm path not built yet"); return REBERT_ERR_UNSUPPORTED; }
+
+namespace rebert {
+
+int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
+                    int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st);
+
+constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
+constexpr int GEMM_STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 4, GEMM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int STAGE_SLOTS = 24;                                 // per-thread staged candidates per tile
+constexpr int SMEM_STAGING = STAGE_SLOTS * 128 * 8;
+constexpr int SMEM_INV = 2 * BN * 4;
+constexpr int GEMM_SMEM = GEMM_STAGES * STAGE_BYTES + SMEM_STAGING + SMEM_INV + 256 + 1024;   // + alignment slack
+constexpr uint32_t TMEM_COLS = 512;
+
+enum { MODE_STORE = 0, MODE_FILTER = 1 };
+
+struct GemmParams {
+    int b;                  // queries
+    int num_qt;             // query tiles (ceil(b / 128))
+    int num_rt;             // row tiles in this launch
+    int64_t tile0;          // first global row tile
+    int64_t tile_stride;    // global row-tile stride between consecutive launch tiles (1 = contiguous)
+    int64_t n;              // shard rows
+    int kblocks;            // ld / 64
+    const float* inv_norm;
+    // MODE_STORE
+    float* out;             // [b, out_ld], column = launch tile index * 256 + c
+    int64_t out_ld;
+    // MODE_FILTER
+    const float* tau;       // [b]
+    uint64_t* cand;         // [b, cand_cap]
+    unsigned* cand_count;   // [b]
+    int cand_cap;
+    int* status;            // [b]
+};
+
+// ---------------------------------------------------------------- PTX wrappers ------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
 }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
+// bits [0,14), LBO unused for swizzled K-major (0), SBO = 1024 B (8 rows x 128 B) >> 4 in bits [32,46),
+// version 1 in bits [46,48), layout SWIZZLE_128B (2) in bits [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24.
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_rows, const GemmParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* stages = smem;
+    uint64_t* staging = (uint64_t*)(smem + GEMM_STAGES * STAGE_BYTES);               // [STAGE_SLOTS][128]
+    float* s_inv = (float*)(smem + GEMM_STAGES * STAGE_BYTES + SMEM_STAGING);         // [2][BN]
+    uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * STAGE_BYTES + SMEM_STAGING + SMEM_INV);
+    uint64_t* full_bar = bars;                       // [GEMM_STAGES]
+    uint64_t* empty_bar = bars + GEMM_STAGES;        // [GEMM_STAGES]
+    uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;    // [2]
+    uint64_t* tempty_bar = bars + 2 * GEMM_STAGES + 2;   // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * GEMM_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total_tiles = (int64_t)p.num_rt * p.num_qt;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_q);
+        prefetch_tmap(&map_rows);
+        for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            const uint64_t pol_rows = l2_policy_evict_first();   // catalog tiles: streamed, shared by the current wave only
+            const uint64_t pol_q = l2_policy_evict_last();       // query tiles: reused by every row tile
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int64_t rt = t / p.num_qt;
+                const int qt = (int)(t - rt * p.num_qt);
+                const int row0 = (int)((p.tile0 + rt * p.tile_stride) * BN);
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const int s = it % GEMM_STAGES;
+                    mbar_wait(&empty_bar[s], ((it / GEMM_STAGES) & 1u) ^ 1u);
+                    unsigned char* sa = stages + s * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[s], pol_q);
+                    tma_load_2d(sa + A_BYTES, &map_rows, kb * BK, row0, &full_bar[s], pol_rows);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer ============================
+        if (lane == 0) {
+            uint32_t it = 0, tile_i = 0;
+            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_i) {
+                const int acc = tile_i & 1;
+                mbar_wait(&tempty_bar[acc], ((tile_i >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const int s = it % GEMM_STAGES;
+                    mbar_wait(&full_bar[s], (it / GEMM_STAGES) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stages + s * STAGE_BYTES);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        // advancing K by 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (>>4) address field
+                        tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[s]);            // smem stage reusable once these MMAs have read it
+                }
+                tc_commit(&tfull_bar[acc]);              // accumulator complete
+            }
+        }
+    } else {
+        // ============================ epilogue warps ============================
+        const int ew = warp - 2;                          // 0..3
+        const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+        const int et = ew * 32 + lane;                    // 0..127 epilogue thread id
+        const int qrow = quarter * 32 + lane;             // accumulator row (query within the tile)
+        uint32_t tile_i = 0;
+        for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_i) {
+            const int64_t rt = t / p.num_qt;
+            const int qt = (int)(t - rt * p.num_qt);
+            const int64_t row0 = (p.tile0 + rt * p.tile_stride) * BN;
+            const int acc = tile_i & 1;
+            const int q = qt * BM + qrow;
+            // inv_norm slice of this row tile -> smem (NaN marks rows beyond the shard so they never pass / are skipped)
+            float* inv = s_inv + (tile_i & 1) * BN;
+            for (int c = et; c < BN; c += 128) {
+                const int64_t r = row0 + c;
+                inv[c] = r < p.n ? __ldg(p.inv_norm + r) : __int_as_float(0x7FC00000);
+            }
+            float tau = INFINITY;
+            if (MODE == MODE_FILTER && q < p.b) tau = __ldg(p.tau + q);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            int cnt = 0;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t v[32];
+                tc_ld32(taddr + ch * 32, v);
+                tc_wait_ld();
+                if (MODE == MODE_STORE) {
+                    if (q < p.b) {
+                        float* o = p.out + (int64_t)q * p.out_ld + rt * BN + ch * 32;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            float4 f;
+                            f.x = __uint_as_float(v[c + 0]) * inv[ch * 32 + c + 0];
+                            f.y = __uint_as_float(v[c + 1]) * inv[ch * 32 + c + 1];
+                            f.z = __uint_as_float(v[c + 2]) * inv[ch * 32 + c + 2];
+                            f.w = __uint_as_float(v[c + 3]) * inv[ch * 32 + c + 3];
+                            *(float4*)(o + c) = f;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float s = __uint_as_float(v[c]) * inv[ch * 32 + c];
+                        if (s > tau) {                                            // predicated; false for NaN (padding rows)
+                            if (cnt < STAGE_SLOTS) staging[cnt * 128 + et] = make_key(s, (uint32_t)(row0 + ch * 32 + c));
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+            // accumulator drained: hand it back to the MMA warp before the (slow) global appends
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (MODE == MODE_FILTER && cnt > 0) {
+                if (cnt > STAGE_SLOTS) { p.status[q] = 1; cnt = STAGE_SLOTS; }    // tau far too low for this query
+                const unsigned base = atomicAdd(p.cand_count + q, (unsigned)cnt);
+                uint64_t* dst = p.cand + (size_t)q * p.cand_cap;
+                for (int i = 0; i < cnt; ++i)
+                    if (base + i < (unsigned)p.cand_cap) dst[base + i] = staging[i * 128 + et];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // s_inv / staging of this parity are free again
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per query: r-th largest sample score after masking excluded rows (4-pass radix select on orderable keys).
+// Sample column j*256 + c is catalog row (tile0 + j*stride)*256 + c.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) select_threshold_kernel(float* sample, int keys_in_smem, int64_t s_cols, int64_t n,
+                                                               int64_t row_base, int64_t tile0, int64_t tile_stride, int rank,
+                                                               const int64_t* __restrict__ excl_ptr,
+                                                               const int32_t* __restrict__ excl_col, float* __restrict__ tau) {
+    extern __shared__ uint32_t smem_keys[];        // [s_cols] when it fits, else the sample row is rewritten in place
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_rank;
+    const int q = blockIdx.x;
+    float* src = sample + (int64_t)q * s_cols;
+    uint32_t* keys = keys_in_smem ? smem_keys : (uint32_t*)src;
+    const int32_t* ex = nullptr;
+    int nex = 0;
+    if (excl_ptr) { ex = excl_col + excl_ptr[q]; nex = (int)(excl_ptr[q + 1] - excl_ptr[q]); }
+    for (int64_t j = threadIdx.x; j < s_cols; j += blockDim.x) {
+        const int64_t row = (tile0 + (j / BN) * tile_stride) * BN + (j % BN);
+        const float v = src[j];
+        uint32_t key = (row < n && v == v) ? f32_orderable(v) : 0u;
+        if (key && nex && sorted_contains(ex, nex, (int32_t)(row_base + row))) key = 0u;
+        keys[j] = key;
+    }
+    if (threadIdx.x == 0) { s_prefix = 0; s_rank = (unsigned)rank; }
+    __syncthreads();
+    for (int pass = 3; pass >= 0; --pass) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        const unsigned himask = pass == 3 ? 0u : (0xFFFFFFFFu << (8 * (pass + 1)));
+        for (int64_t j = threadIdx.x; j < s_cols; j += blockDim.x) {
+            const uint32_t k = keys[j];
+            if (k != 0 && (k & himask) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 0xFF], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned need = s_rank, cum = 0;
+            int bin = 255;
+            for (; bin >= 0; --bin) {
+                if (cum + hist[bin] >= need) break;
+                cum += hist[bin];
+            }
+            if (bin < 0) { s_prefix = 0; s_rank = 0xFFFFFFFFu; }     // fewer than `rank` valid samples
+            else { s_prefix = prefix | ((unsigned)bin << (8 * pass)); s_rank = need - cum; }
+        }
+        __syncthreads();
+        if (s_rank == 0xFFFFFFFFu) break;
+    }
+    if (threadIdx.x == 0) tau[q] = (s_rank == 0xFFFFFFFFu || s_prefix == 0) ? -INFINITY : orderable_f32(s_prefix);
+}
+
+// Per query: survivors of the filter -> drop excluded rows -> bitonic sort -> best kc keys (zero padded).
+__global__ void __launch_bounds__(512) select_candidates_kernel(const uint64_t* __restrict__ cand, const unsigned* __restrict__ cand_count,
+                                                                int cand_cap, int kc, int64_t row_base,
+                                                                const int64_t* __restrict__ excl_ptr, const int32_t* __restrict__ excl_col,
+                                                                const float* __restrict__ tau, uint64_t* __restrict__ out_keys,
+                                                                int* __restrict__ status) {
+    extern __shared__ __align__(16) uint64_t buf[];        // [pow2 >= cand_cap]
+    __shared__ int s_valid;
+    const int q = blockIdx.x;
+    const unsigned cnt_raw = cand_count[q];
+    const int cnt = cnt_raw < (unsigned)cand_cap ? (int)cnt_raw : cand_cap;
+    const int32_t* ex = nullptr;
+    int nex = 0;
+    if (excl_ptr) { ex = excl_col + excl_ptr[q]; nex = (int)(excl_ptr[q + 1] - excl_ptr[q]); }
+    int p2 = 2;
+    while (p2 < cnt || p2 < kc) p2 <<= 1;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+        uint64_t key = i < cnt ? cand[(size_t)q * cand_cap + i] : 0;
+        if (key && nex && sorted_contains(ex, nex, (int32_t)(row_base + key_row(key)))) key = 0;
+        buf[i] = key;
+        mine += key != 0;
+    }
+    if (mine) atomicAdd(&s_valid, mine);
+    __syncthreads();
+    block_bitonic_sort_desc(buf, p2);
+    for (int i = threadIdx.x; i < kc; i += blockDim.x) out_keys[(size_t)q * kc + i] = buf[i];
+    if (threadIdx.x == 0) {
+        int st = status[q];
+        if (cnt_raw > (unsigned)cand_cap) st |= 2;                         // buffer overflow: some survivors were dropped
+        if (s_valid < kc && tau[q] != -INFINITY) st |= 4;                  // threshold too optimistic: not enough candidates
+        status[q] = st;
+    }
+}
+
+__global__ void margin_status_kernel(const double* __restrict__ margin, double eps, int b, int* __restrict__ status) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < b && !(margin[q] > eps)) status[q] |= 8;
+}
+
+// ---------------------------------------------------------------- host side ----------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, ld] matrix, box = [box_rows x 64 columns], 128-byte swizzle.
+static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int ld, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable from the driver"); return REBERT_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld ld=%d", (int)r, (long long)rows, ld); return REBERT_ERR_CUDA; }
+    return REBERT_OK;
+}
+
+static int check_gemm_catalog(const rebert_catalog_t* cat, const char* who) {
+    REBERT_REQUIRE(cat && cat->rows && cat->inv_norm, "%s: null catalog", who);
+    if (cat->dtype != REBERT_BF16) { set_error("%s: the tensor-core path needs a bf16 catalog", who); return REBERT_ERR_UNSUPPORTED; }
+    if (cat->ld % BK != 0) { set_error("%s: ld=%d is not a multiple of %d", who, cat->ld, BK); return REBERT_ERR_UNSUPPORTED; }
+    REBERT_REQUIRE(cat->n > 0 && cat->n < (1ll << 31) - BN, "%s: shard rows %lld out of range", who, (long long)cat->n);
+    REBERT_REQUIRE(((uintptr_t)cat->rows & 127) == 0, "%s: catalog rows must be 128-byte aligned", who);
+    return REBERT_OK;
+}
+
+template <int MODE>
+static int launch_gemm(const rebert_catalog_t* cat, const void* qbf16, GemmParams& p, cudaStream_t st) {
+    CUtensorMap map_q, map_rows;
+    int rc = make_tmap(&map_q, qbf16, p.b, cat->ld, BM);
+    if (rc != REBERT_OK) return rc;
+    rc = make_tmap(&map_rows, cat->rows, cat->n, cat->ld, BN);
+    if (rc != REBERT_OK) return rc;
+    p.kblocks = cat->ld / BK;
+    p.n = cat->n;
+    p.inv_norm = cat->inv_norm;
+    p.num_qt = (p.b + BM - 1) / BM;
+    const int64_t tiles = (int64_t)p.num_rt * p.num_qt;
+    int grid = num_sms();
+    if (tiles < grid) grid = (int)tiles;
+    auto kern = gemm_kernel<MODE>;
+    REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_q, map_rows, p);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+struct GemmWorkspace {
+    float* sample;        // [b, sample_rows]
+    float* tau;           // [b]
+    unsigned* cand_count; // [b]
+    uint64_t* cand;       // [b, cand_cap]
+    uint64_t* cand_keys;  // [b, kc]
+    double* margin;       // [b]
+    size_t bytes;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static GemmWorkspace carve(void* base, const rebert_gemm_plan_t* pl) {
+    GemmWorkspace w;
+    size_t off = 0;
+    unsigned char* b0 = (unsigned char*)align_up((uintptr_t)base, 256);
+    auto take = [&](size_t bytes) { void* ptr = b0 ? b0 + off : nullptr; off += align_up(bytes, 256); return ptr; };
+    w.sample = (float*)take((size_t)pl->b * pl->sample_rows * 4);
+    w.tau = (float*)take((size_t)pl->b * 4);
+    w.cand_count = (unsigned*)take((size_t)pl->b * 4);
+    w.cand = (uint64_t*)take((size_t)pl->b * pl->cand_cap * 8);
+    w.cand_keys = (uint64_t*)take((size_t)pl->b * pl->kc * 8);
+    w.margin = (double*)take((size_t)pl->b * 8);
+    w.bytes = off + 256;
+    return w;
+}
+
+}  // namespace rebert
+
+using namespace rebert;
+
+extern "C" {
+
+REBERT_API int rebert_gemm_plan(int64_t n, int32_t b, int32_t k, rebert_gemm_plan_t* plan) {
+    REBERT_REQUIRE(plan && n > 0 && b > 0 && k > 0, "gemm_plan: bad arguments");
+    const int kc = rebert_candidates_for_k(k);
+    if (kc == 0) { set_error("gemm_plan: k=%d unsupported", k); return REBERT_ERR_UNSUPPORTED; }
+    // Expected survivors per query E = rank * n / sample_rows.  Want E >= 8 kc (the kc best are then inside with
+    // overwhelming probability: the survivor count is Gamma(rank)-distributed around E) plus headroom for excluded
+    // rows, which tend to score high; and E <= n / 64 so a thread stages ~4 keys per tile on average (24 slots).
+    double e = 8.0 * kc;
+    double head = (double)n / 64.0 < 1024.0 ? (double)n / 64.0 : 1024.0;
+    if (head > e) e = head;
+    if (e > (double)n / 64.0) {
+        set_error("gemm_plan: catalog of %lld rows is too small for the batched path at k=%d (needs >= %d rows); "
+                  "use the single-query path", (long long)n, k, 512 * kc);
+        return REBERT_ERR_UNSUPPORTED;
+    }
+    const int rank = 16;                                    // order statistic of the sample used as threshold
+    const int64_t tiles = (n + BN - 1) / BN;
+    int64_t st = (int64_t)((double)n * rank / e / BN + 0.5); // sample tiles so that rank * n / sample_rows ~= e
+    if (st < 1) st = 1;
+    if (st > tiles) st = tiles;
+    plan->b = b;
+    plan->k = k;
+    plan->kc = kc;
+    plan->sample_rows = (int32_t)(st * BN);
+    plan->sample_rank = rank;
+    int cap = 2 * kc;
+    while (cap < 4.0 * e) cap <<= 1;
+    plan->cand_cap = cap;
+    return REBERT_OK;
+}
+
+REBERT_API size_t rebert_gemm_workspace_bytes(const rebert_catalog_t* cat, const rebert_gemm_plan_t* plan) {
+    (void)cat;
+    if (!plan) return 0;
+    return carve(nullptr, plan).bytes;
+}
+
+REBERT_API int rebert_gemm_scores(const rebert_catalog_t* cat, const void* qbf16, int32_t b, int64_t row0, int64_t nrows,
+                                  float* out, rebert_stream stream) {
+    int rc = check_gemm_catalog(cat, "gemm_scores");
+    if (rc != REBERT_OK) return rc;
+    REBERT_REQUIRE(qbf16 && out && b > 0 && nrows > 0, "gemm_scores: bad arguments");
+    REBERT_REQUIRE(row0 % BN == 0 && nrows % BN == 0 && row0 >= 0, "gemm_scores: row0 and nrows must be multiples of %d", BN);
+    REBERT_REQUIRE(((uintptr_t)out & 15) == 0, "gemm_scores: out must be 16-byte aligned");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.b = b;
+    p.num_rt = (int)(nrows / BN);
+    p.tile0 = row0 / BN;
+    p.tile_stride = 1;
+    p.out = out;
+    p.out_ld = nrows;
+    return launch_gemm<MODE_STORE>(cat, qbf16, p, (cudaStream_t)stream);
+}
+
+REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, const double* q64, const int64_t* excl_row_ptr,
+                                const int32_t* excl_col, const rebert_gemm_plan_t* plan, void* workspace, size_t workspace_bytes,
+                                int64_t* out_rows, double* out_scores, int32_t* out_count, int32_t* out_status,
+                                rebert_stream stream) {
+    int rc = check_gemm_catalog(cat, "gemm_topk");
+    if (rc != REBERT_OK) return rc;
+    REBERT_REQUIRE(qbf16 && q64 && plan && workspace && out_rows && out_scores && out_count && out_status && cat->norm64,
+                   "gemm_topk: null argument");
+    REBERT_REQUIRE((excl_row_ptr == nullptr) == (excl_col == nullptr), "gemm_topk: exclusion CSR needs both arrays");
+    GemmWorkspace w = carve(workspace, plan);
+    if (workspace_bytes < w.bytes) { set_error("gemm_topk: workspace %zu < %zu", workspace_bytes, w.bytes); return REBERT_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int b = plan->b;
+    const int64_t tiles = (cat->n + BN - 1) / BN;
+    const int64_t s_tiles = plan->sample_rows / BN;
+    const int64_t stride = tiles / s_tiles;                  // sample tile j = global tile j * stride
+
+    REBERT_CUDA(cudaMemsetAsync(w.cand_count, 0, (size_t)b * 4, st));
+    REBERT_CUDA(cudaMemsetAsync(out_status, 0, (size_t)b * 4, st));
+
+    // 1. sample scores
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.b = b;
+    p.num_rt = (int)s_tiles;
+    p.tile0 = 0;
+    p.tile_stride = stride;
+    p.out = w.sample;
+    p.out_ld = plan->sample_rows;
+    rc = launch_gemm<MODE_STORE>(cat, qbf16, p, st);
+    if (rc != REBERT_OK) return rc;
+    // 2. thresholds
+    const int keys_in_smem = plan->sample_rows <= 48 * 1024;
+    const size_t tsmem = keys_in_smem ? (size_t)plan->sample_rows * 4 : 16;
+    REBERT_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    select_threshold_kernel<<<b, 256, tsmem, st>>>(w.sample, keys_in_smem, plan->sample_rows, cat->n, cat->row_base, 0, stride,
+                                                   plan->sample_rank, excl_row_ptr, excl_col, w.tau);
+    REBERT_CUDA(cudaGetLastError());
+    // 3. full pass with fused filter
+    memset(&p, 0, sizeof(p));
+    p.b = b;
+    p.num_rt = (int)tiles;
+    p.tile0 = 0;
+    p.tile_stride = 1;
+    p.tau = w.tau;
+    p.cand = w.cand;
+    p.cand_count = w.cand_count;
+    p.cand_cap = plan->cand_cap;
+    p.status = out_status;
+    rc = launch_gemm<MODE_FILTER>(cat, qbf16, p, st);
+    if (rc != REBERT_OK) return rc;
+    // 4. per-query candidate selection
+    int p2 = 2;
+    while (p2 < plan->cand_cap) p2 <<= 1;
+    const size_t csmem = (size_t)p2 * 8;
+    REBERT_CUDA(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+    select_candidates_kernel<<<b, 512, csmem, st>>>(w.cand, w.cand_count, plan->cand_cap, plan->kc, cat->row_base, excl_row_ptr,
+                                                    excl_col, w.tau, w.cand_keys, out_status);
+    REBERT_CUDA(cudaGetLastError());
+    // 5. exact pass
+    rc = finalize_launch(cat, q64, w.cand_keys, b, plan->kc, plan->k, out_rows, out_scores, out_count, w.margin, st);
+    if (rc != REBERT_OK) return rc;
+    // The margin already has 4 x (largest observed |fast - exact| over the kc candidates) subtracted (finalize.cu), which
+    // calibrates the bf16 rounding of the query; on top require the model bound for that rounding, 3 sigma with
+    // sigma = 2^-9 / sqrt(3 d) for a spread-out unit vector, plus the fp32 accumulation term.
+    const double eps = 3.0 * 0.001953125 / sqrt(3.0 * (double)cat->d) + 64.0 * 5.96e-8;
+    margin_status_kernel<<<(b + 255) / 256, 256, 0, st>>>(w.margin, eps, b, out_status);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+"""GPU parity of the batched tcgen05 path: the GEMM building block against the plain dense-score kernel, and
+recommend_batch against the oracle (ids bit-exact, scores 1e-9)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_scoring as ora
+from robot_ebert_b200 import CatalogStore, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _stored_f64(store):
+    return store.rows[:store.n, :store.d].to(torch.float64).cpu().numpy()
+
+
+def _queries(b, d, seed=11):
+    return synth.catalog_rows_f32(seed, 0, b, d)
+
+
+@pytest.mark.parametrize("n,d,b", [(4096, 1536, 200), (5000, 1536, 128), (2048, 256, 1), (70_000, 64, 300)])
+def test_gemm_scores_match_dense_kernel(n, d, b):
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    qn32, qn64, qbf = store.prepare_queries(_queries(b, d))
+    nrows = (n + 255) // 256 * 256
+    got = store.gemm_scores(qbf, 0, nrows)[:, :n]
+    want = store.scores_dense(qbf.to(torch.float32))          # same bf16-rounded queries, fp32 CUDA-core dot
+    torch.cuda.synchronize()
+    err = (got - want).abs().max().item()
+    assert err < 2e-6, err
+    # and against float64 on the host for a few rows
+    m = _stored_f64(store)
+    qh = qbf.to(torch.float64).cpu().numpy()[:, :d]
+    ref = (qh[:4] @ m[:512].T) / np.linalg.norm(m[:512], axis=1)
+    np.testing.assert_allclose(got[:4, :512].cpu().numpy(), ref, atol=3e-6)
+
+
+def test_gemm_scores_row_window():
+    store = CatalogStore.synthetic(0, 8192, 128, "bf16")
+    _, _, qbf = store.prepare_queries(_queries(130, 128))
+    full = store.gemm_scores(qbf, 0, 8192)
+    win = store.gemm_scores(qbf, 2048, 1024)
+    torch.cuda.synchronize()
+    assert torch.equal(full[:, 2048:3072], win)
+
+
+@pytest.mark.parametrize("n,d,b,k", [(40_000, 1536, 300, 10), (100_000, 256, 1000, 10), (150_000, 128, 257, 100)])
+def test_recommend_batch_queries_vs_oracle(n, d, b, k):
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    m = _stored_f64(store)
+    q = _queries(b, d)
+    rng = np.random.default_rng(5)
+    ptr = [0]
+    cols = []
+    for u in range(b):
+        c = np.sort(rng.choice(n, size=int(rng.integers(0, 200)), replace=False))
+        cols.append(c)
+        ptr.append(ptr[-1] + len(c))
+    rows, scores, counts, info = store.recommend_batch(queries=q, excl_ptr=np.array(ptr), excl_col=np.concatenate(cols), k=k,
+                                                       return_info=True)
+    assert (info["status"] != 0).mean() < 0.05, info["status"]          # the fast path must carry almost everything
+    unit = m / np.linalg.norm(m, axis=1, keepdims=True)
+    qn = q.astype(np.float64)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    for u in range(b):
+        want_rows, want_scores = ora.topk_rows(unit @ qn[u], k, cols[u])
+        assert counts[u] == len(want_rows)
+        np.testing.assert_array_equal(rows[u, :counts[u]], want_rows, err_msg=f"query {u} status {info['status'][u]}")
+        np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
+
+
+def test_recommend_batch_profiles_vs_oracle():
+    n, d, b, k = 60_000, 1536, 64, 10
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    m = _stored_f64(store)
+    users = synth.user_ratings(2, n, b)
+    lp, lc, ep, ec = [0], [], [0], []
+    for rated, rts in users:
+        liked = rated[rts >= 3.5]
+        if len(liked) == 0:
+            liked = rated[:1]
+        lc.append(liked)
+        lp.append(lp[-1] + len(liked))
+        ec.append(rated)
+        ep.append(ep[-1] + len(rated))
+    rows, scores, counts = store.recommend_batch(liked_ptr=np.array(lp), liked_col=np.concatenate(lc), excl_ptr=np.array(ep),
+                                                 excl_col=np.concatenate(ec), k=k)
+    for u in range(b):
+        want_rows, want_scores = ora.recommend_rows(m, lc[u], ec[u], k)
+        np.testing.assert_array_equal(rows[u, :counts[u]], want_rows)
+        np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
+
+
+def test_batched_path_rejects_small_or_fp32_catalogs():
+    store = CatalogStore.synthetic(0, 2000, 64, "bf16")
+    with pytest.raises(Exception):
+        store.recommend_batch(queries=_queries(4, 64), k=10)
+    store = CatalogStore.synthetic(0, 40_000, 64, "fp32")
+    with pytest.raises(Exception):
+        store.recommend_batch(queries=_queries(4, 64), k=10)
