@@ -453,8 +453,11 @@ class CatalogStore:
                                               torch.cuda.current_stream().cuda_stream))
         return out.cpu().numpy()
 
-    def build_profiles(self, row_ptr: np.ndarray, col: np.ndarray, w: Optional[np.ndarray] = None):
-        """Batched profile build from a ragged CSR of liked rows: returns (p32, p64, pbf16) device tensors [b, ld]."""
+    def build_profiles(self, row_ptr: np.ndarray, col: np.ndarray, w: Optional[np.ndarray] = None, reduce_fn=None):
+        """Batched profile build from a ragged CSR of liked rows: returns (p32, p64, pbf16) device tensors [b, ld].
+
+        On a row shard only the local liked rows contribute; `reduce_fn(sum64)` (an in-place all-reduce) completes the
+        fp64 partial sums before they are divided by the weight sums."""
         lib = nat.load()
         dev = self.device
         rp = torch.from_numpy(np.asarray(row_ptr, dtype=np.int64)).to(dev)
@@ -470,6 +473,8 @@ class CatalogStore:
             st = torch.cuda.current_stream().cuda_stream
             nat.check(lib.rebert_profile_accumulate(C.byref(self._c), rp.data_ptr(), cl.data_ptr(), _ptr(wt), b,
                                                     sum64.data_ptr(), wsum.data_ptr(), st))
+            if reduce_fn is not None:
+                reduce_fn(sum64)
             nat.check(lib.rebert_profile_finalize(sum64.data_ptr(), wsum.data_ptr(), b, self.ld, p32.data_ptr(),
                                                   p64.data_ptr(), pbf.data_ptr(), st))
         return p32, p64, pbf

@@ -294,9 +294,17 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(float* sample, in
     for (int64_t j = threadIdx.x; j < s_cols; j += blockDim.x) {
         const int64_t row = (tile0 + (j / BN) * tile_stride) * BN + (j % BN);
         const float v = src[j];
-        uint32_t key = (row < n && v == v) ? f32_orderable(v) : 0u;
-        if (key && nex && sorted_contains(ex, nex, (int32_t)(row_base + row))) key = 0u;
-        keys[j] = key;
+        keys[j] = (row < n && v == v) ? f32_orderable(v) : 0u;
+    }
+    __syncthreads();
+    // knock out excluded rows that fall inside the sample: ~|excluded| scattered stores instead of a search per key
+    for (int e = threadIdx.x; e < nex; e += blockDim.x) {
+        const int64_t row = (int64_t)ex[e] - row_base;
+        if (row < 0 || row >= n) continue;
+        const int64_t tile = row / BN - tile0;
+        if (tile < 0 || tile % tile_stride != 0) continue;
+        const int64_t j = (tile / tile_stride) * BN + row % BN;
+        if (j < s_cols) keys[j] = 0u;
     }
     if (threadIdx.x == 0) { s_prefix = 0; s_rank = (unsigned)rank; }
     __syncthreads();

@@ -149,3 +149,65 @@ class ShardedCatalog:
         if return_info:
             return rows, scores, {"kc": kc, "margin": margin, "proven_exact": margin > eps}
         return rows, scores
+
+    # ------------------------------------------------------------------ batched (tensor-core) path ----------
+    def recommend_batch(self, *, queries=None, liked_ptr=None, liked_col=None, liked_w=None, excl_ptr=None, excl_col=None,
+                        k: int = 10, return_info: bool = False):
+        """Sharded form of CatalogStore.recommend_batch: every rank runs the tcgen05 pass over its rows, the per-rank
+        [b, k] results are all-gathered in ONE packed buffer and merged on every rank.  CUDA backend only."""
+        import ctypes as C
+        store: CatalogStore = self.backend.store
+        lib = nat.load()
+        dev = store.device
+        if (queries is None) == (liked_ptr is None):
+            raise ValueError("pass exactly one of queries / liked CSR")
+        with torch.cuda.device(dev):
+            if queries is not None:
+                qn32, qn64, qbf = store.prepare_queries(queries)
+            else:
+                lp = np.asarray(liked_ptr, dtype=np.int64)
+                if np.any(np.diff(lp) == 0):
+                    raise ValueError("Found array with 0 sample(s): a user has no liked movies in the catalog")
+                qn32, qn64, qbf = store.build_profiles(
+                    lp, liked_col, liked_w, reduce_fn=lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group))
+            b = qbf.shape[0]
+            plan = store.gemm_plan(b, k)
+            ep = ec = None
+            if excl_ptr is not None:
+                ep = torch.from_numpy(np.asarray(excl_ptr, dtype=np.int64)).to(dev)
+                ec = torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(dev)
+            ws = torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan)), dtype=torch.uint8, device=dev)
+            hb = (b + 1) // 2
+            words = 2 * b * k + 2 * hb                                   # rows | scores | counts | status
+            local = torch.empty(words, dtype=torch.int64, device=dev)
+            o_rows, o_scores = local[:b * k], local[b * k:2 * b * k].view(torch.float64)
+            o_count = local[2 * b * k:2 * b * k + hb].view(torch.int32)[:b]
+            o_status = local[2 * b * k + hb:].view(torch.int32)[:b]
+            store.enqueue_batch(plan, qbf, qn64, ep, ec, ws, o_rows, o_scores, o_count, o_status)
+            gathered = torch.empty((self.world, words), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered.view(-1), local, group=self.group)
+            m_rows = torch.empty((b, k), dtype=torch.int64, device=dev)
+            m_scores = torch.empty((b, k), dtype=torch.float64, device=dev)
+            m_count = torch.empty(b, dtype=torch.int32, device=dev)
+            base = gathered.data_ptr()
+            nat.check(lib.rebert_merge_topk(base, base + 8 * b * k, base + 16 * b * k, words, words, 2 * words, self.world, b, k,
+                                            m_rows.data_ptr(), m_scores.data_ptr(), m_count.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+            status = gathered[:, 2 * b * k + hb:].contiguous().view(torch.int32)[:, :b].max(dim=0).values   # any rank unsure
+            rows, scores = m_rows.cpu().numpy(), m_scores.cpu().numpy()
+            counts, status = m_count.cpu().numpy(), status.cpu().numpy()
+        ecp = None if excl_ptr is None else np.asarray(excl_ptr, dtype=np.int64)
+        eca = None if excl_col is None else np.asarray(excl_col)
+        for u in np.nonzero(status)[0]:                                  # identical on every rank -> collectives stay aligned
+            ex = None if ecp is None else eca[ecp[u]:ecp[u + 1]]
+            if queries is not None:
+                r, sc = self.recommend(query=np.asarray(queries[u]), exclude_rows=ex, k=k)
+            else:
+                lpn = np.asarray(liked_ptr, dtype=np.int64)
+                lw = None if liked_w is None else np.asarray(liked_w)[lpn[u]:lpn[u + 1]]
+                r, sc = self.recommend(liked_rows=np.asarray(liked_col)[lpn[u]:lpn[u + 1]], weights=lw, exclude_rows=ex, k=k)
+            rows[u, :], scores[u, :] = -1, -np.inf
+            rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
+        if return_info:
+            return rows, scores, counts, {"status": status}
+        return rows, scores, counts

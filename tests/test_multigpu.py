@@ -59,3 +59,59 @@ def test_sharded_equals_single_gpu(dtype):
         assert r1r == w1[0].tolist() and r2r == w2[0].tolist(), rank
         np.testing.assert_allclose(r1s, w1[1], rtol=1e-12)
         np.testing.assert_allclose(r2s, w2[1], rtol=1e-12)
+
+
+def _batch_worker(rank, world, port, n, d, b, k, out_q):
+    import torch.distributed as dist
+    from robot_ebert_b200 import synth
+    from robot_ebert_b200.sharding import ShardedCatalog
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        sc = ShardedCatalog.synthetic(0, n, d, "bf16", scale_rows=True, device=torch.device("cuda", rank))
+        lp, lc, ep, ec = _csr_users(n, b)
+        r = sc.recommend_batch(liked_ptr=lp, liked_col=lc, excl_ptr=ep, excl_col=ec, k=k)
+        out_q.put((rank, r[0].tolist(), r[1].tolist(), r[2].tolist()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _csr_users(n, b):
+    from robot_ebert_b200 import synth
+    lp, lc, ep, ec = [0], [], [0], []
+    for rated, rts in synth.user_ratings(2, n, b):
+        liked = rated[rts >= 3.5]
+        if len(liked) == 0:
+            liked = rated[:1]
+        lc.append(liked); lp.append(lp[-1] + len(liked)); ec.append(rated); ep.append(ep[-1] + len(rated))
+    return np.array(lp), np.concatenate(lc), np.array(ep), np.concatenate(ec)
+
+
+def test_sharded_batch_equals_single_gpu_batch():
+    """BASELINE config 5 shape at test size: CSR profiles + exclusions, sharded tcgen05 pass == one-GPU result."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    from robot_ebert_b200 import CatalogStore
+    n, d, b, k = 140_000, 512, 200, 50
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, n, d, b, k, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out_q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True, device="cuda:0")
+    lp, lc, ep, ec = _csr_users(n, b)
+    want = store.recommend_batch(liked_ptr=lp, liked_col=lc, excl_ptr=ep, excl_col=ec, k=k)
+    for rank, rows, scores, counts in results:
+        assert rows == want[0].tolist() and counts == want[2].tolist(), rank
+        np.testing.assert_allclose(scores, want[1], rtol=1e-12)
