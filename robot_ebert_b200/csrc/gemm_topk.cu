@@ -23,6 +23,7 @@
 //   Tile order: row-tile-major over (row tile, query tile) so concurrently running CTAs share the same catalog tile
 //   in L2 and the catalog streams from HBM once; Q (12.6 MB at B=4096) stays L2-resident.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -116,6 +117,73 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), both K-major,
 // N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue of one 128 x 256 accumulator (shared by the 1-CTA and 2-CTA kernels).  Thread = one query row.
+// Per 32-column chunk: tcgen05.ld (software-pipelined against the previous chunk's math), 8 x LDS.128 of inv_norm,
+// 32 independent FMULs, a max tree and ONE compare against the query's threshold; only a chunk that holds a winner
+// (2.5 % of thread-chunks) builds the pass mask and stages keys.  No per-element branches, no per-element LDS.
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, const float* inv_chunk, float tau, int q,
+                                               float* out_row, uint32_t row_chunk0, uint64_t* staging, int et, int& cnt) {
+    float s[32];
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 iv = ((const float4*)inv_chunk)[c4];
+        s[c4 * 4 + 0] = __uint_as_float(v[c4 * 4 + 0]) * iv.x;
+        s[c4 * 4 + 1] = __uint_as_float(v[c4 * 4 + 1]) * iv.y;
+        s[c4 * 4 + 2] = __uint_as_float(v[c4 * 4 + 2]) * iv.z;
+        s[c4 * 4 + 3] = __uint_as_float(v[c4 * 4 + 3]) * iv.w;
+    }
+    if (MODE == MODE_STORE) {
+        if (q < p.b) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) *(float4*)(out_row + c) = make_float4(s[c], s[c + 1], s[c + 2], s[c + 3]);
+        }
+    } else {
+        float m[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m[i] = fmaxf(s[2 * i], s[2 * i + 1]);       // fmaxf drops NaN (padding rows)
+#pragma unroll
+        for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+            for (int i = 0; i < w; ++i) m[i] = fmaxf(m[i], m[i + w]);
+        if (m[0] > tau) {                                                       // rare: this chunk holds a candidate
+            uint32_t mask = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) mask |= (s[c] > tau) ? (1u << c) : 0u;
+            while (mask) {
+                const int c = __ffs(mask) - 1;
+                mask &= mask - 1;
+                float val = s[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) val = (c == j) ? s[j] : val;       // register select, no local memory
+                if (cnt < STAGE_SLOTS) staging[cnt * 128 + et] = make_key(val, row_chunk0 + (uint32_t)c);
+                ++cnt;
+            }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, const float* inv, float tau, int q, int64_t row0,
+                                              int64_t rt, uint64_t* staging, int et, int& cnt) {
+    float* out_row = nullptr;
+    if (MODE == MODE_STORE) out_row = p.out + (int64_t)q * p.out_ld + rt * BN;
+    uint32_t va[32], vb[32];
+    tc_ld32(taddr, va);
+    tc_wait_ld();
+#pragma unroll
+    for (int ch = 0; ch < BN / 32; ch += 2) {
+        tc_ld32(taddr + (ch + 1) * 32, vb);                                     // in flight while chunk ch is processed
+        epilogue_chunk<MODE>(p, va, inv + ch * 32, tau, q, out_row + ch * 32, (uint32_t)(row0 + ch * 32), staging, et, cnt);
+        tc_wait_ld();
+        if (ch + 2 < BN / 32) tc_ld32(taddr + (ch + 2) * 32, va);
+        epilogue_chunk<MODE>(p, vb, inv + (ch + 1) * 32, tau, q, out_row + (ch + 1) * 32, (uint32_t)(row0 + (ch + 1) * 32), staging, et, cnt);
+        if (ch + 2 < BN / 32) tc_wait_ld();
+    }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -222,35 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             int cnt = 0;
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t v[32];
-                tc_ld32(taddr + ch * 32, v);
-                tc_wait_ld();
-                if (MODE == MODE_STORE) {
-                    if (q < p.b) {
-                        float* o = p.out + (int64_t)q * p.out_ld + rt * BN + ch * 32;
-#pragma unroll
-                        for (int c = 0; c < 32; c += 4) {
-                            float4 f;
-                            f.x = __uint_as_float(v[c + 0]) * inv[ch * 32 + c + 0];
-                            f.y = __uint_as_float(v[c + 1]) * inv[ch * 32 + c + 1];
-                            f.z = __uint_as_float(v[c + 2]) * inv[ch * 32 + c + 2];
-                            f.w = __uint_as_float(v[c + 3]) * inv[ch * 32 + c + 3];
-                            *(float4*)(o + c) = f;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float s = __uint_as_float(v[c]) * inv[ch * 32 + c];
-                        if (s > tau) {                                            // predicated; false for NaN (padding rows)
-                            if (cnt < STAGE_SLOTS) staging[cnt * 128 + et] = make_key(s, (uint32_t)(row0 + ch * 32 + c));
-                            ++cnt;
-                        }
-                    }
-                }
-            }
+            epilogue_tile<MODE>(p, taddr, inv, tau, q, row0, rt, staging, et, cnt);
             // accumulator drained: hand it back to the MMA warp before the (slow) global appends
             tc_fence_before();
             __syncwarp();
@@ -271,6 +311,184 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// =========================================================================================================
+// cta_group::2 variant: a cluster of two CTAs (one SM pair) computes a 256-query x 256-row tile.  CTA r stages its own
+// 128 query rows (A half) and its own 128 catalog rows (B half) per k-block — 32 KB per stage instead of 48 KB, and the
+// MMA reads each operand byte from shared memory once per PAIR, which is what lifts the shared-memory-bandwidth cap
+// of the 1-CTA kernel.  The leader CTA (rank 0) owns the full barriers and issues tcgen05.mma.cta_group::2 (M=256,
+// N=256, K=16); its commits are multicast to both CTAs' empty / tmem-full barriers; both CTAs' epilogue warps drain
+// their own 128 x 256 accumulator half and arrive on the leader's tmem-empty barrier (the peer remotely).
+// =========================================================================================================
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = 128 * BK * 2, G2_B_BYTES = 128 * BK * 2, G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + SMEM_STAGING + SMEM_INV + 256 + 1024;
+constexpr uint32_t kInstrDesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_rows, const GemmParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* stages = smem;
+    uint64_t* staging = (uint64_t*)(smem + G2_STAGES * G2_STAGE_BYTES);
+    float* s_inv = (float*)(smem + G2_STAGES * G2_STAGE_BYTES + SMEM_STAGING);
+    uint64_t* bars = (uint64_t*)(smem + G2_STAGES * G2_STAGE_BYTES + SMEM_STAGING + SMEM_INV);
+    uint64_t* full_bar = bars;                         // [G2_STAGES]  used in the leader CTA only
+    uint64_t* empty_bar = bars + G2_STAGES;            // [G2_STAGES]  per CTA, arrived by the multicast commit
+    uint64_t* tfull_bar = bars + 2 * G2_STAGES;        // [2]          per CTA, arrived by the multicast commit
+    uint64_t* tempty_bar = bars + 2 * G2_STAGES + 2;   // [2]          leader only: 2 x EPI_WARPS arrivals
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * G2_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int num_qt2 = (p.b + 255) / 256;                                     // 256-query tiles
+    const int64_t total_tiles = (int64_t)p.num_rt * num_qt2;
+    const int64_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_q);
+        prefetch_tmap(&map_rows);
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                 // both CTAs' barriers are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================ TMA producer (both CTAs, each for its own halves) ============================
+        if (lane == 0) {
+            const uint64_t pol_rows = l2_policy_evict_first();
+            const uint64_t pol_q = l2_policy_evict_last();
+            uint32_t it = 0;
+            for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
+                const int64_t rt = t / num_qt2;
+                const int qt = (int)(t - rt * num_qt2);
+                const int row0 = (int)((p.tile0 + rt * p.tile_stride) * BN) + (int)cta_rank * 128;
+                const int q0 = qt * 256 + (int)cta_rank * 128;
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const int s = it % G2_STAGES;
+                    mbar_wait(&empty_bar[s], ((it / G2_STAGES) & 1u) ^ 1u);
+                    unsigned char* sa = stages + s * G2_STAGE_BYTES;
+                    const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);        // the leader's full barrier
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G2_STAGE_BYTES); // bytes of BOTH CTAs land on it
+                    tma_load_2d_2sm(sa, &map_q, kb * BK, q0, lbar, pol_q);
+                    tma_load_2d_2sm(sa + G2_A_BYTES, &map_rows, kb * BK, row0, lbar, pol_rows);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer (leader CTA only) ============================
+        if (leader && lane == 0) {
+            uint32_t it = 0, tile_i = 0;
+            for (int64_t t = cluster_id; t < total_tiles; t += num_clusters, ++tile_i) {
+                const int acc = tile_i & 1;
+                mbar_wait(&tempty_bar[acc], ((tile_i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const int s = it % G2_STAGES;
+                    mbar_wait(&full_bar[s], (it / G2_STAGES) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stages + s * G2_STAGE_BYTES);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + G2_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        tc_mma_bf16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc2, (kb | k) ? 1u : 0u);
+                    tc_commit_2sm(&empty_bar[s]);
+                }
+                tc_commit_2sm(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ============================ epilogue warps (both CTAs, own 128 queries x 256 rows) ============================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int et = ew * 32 + lane;
+        const int qrow = quarter * 32 + lane;
+        const uint32_t leader_tempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t leader_tempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+        uint32_t tile_i = 0;
+        for (int64_t t = cluster_id; t < total_tiles; t += num_clusters, ++tile_i) {
+            const int64_t rt = t / num_qt2;
+            const int qt = (int)(t - rt * num_qt2);
+            const int64_t row0 = (p.tile0 + rt * p.tile_stride) * BN;
+            const int acc = tile_i & 1;
+            const int q = qt * 256 + (int)cta_rank * 128 + qrow;
+            float* inv = s_inv + (tile_i & 1) * BN;
+            for (int c = et; c < BN; c += 128) {
+                const int64_t r = row0 + c;
+                inv[c] = r < p.n ? __ldg(p.inv_norm + r) : __int_as_float(0x7FC00000);
+            }
+            float tau = INFINITY;
+            if (MODE == MODE_FILTER && q < p.b) tau = __ldg(p.tau + q);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            int cnt = 0;
+            epilogue_tile<MODE>(p, taddr, inv, tau, q, row0, rt, staging, et, cnt);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(acc ? leader_tempty1 : leader_tempty0);
+            if (MODE == MODE_FILTER && cnt > 0) {
+                if (cnt > STAGE_SLOTS) { p.status[q] = 1; cnt = STAGE_SLOTS; }
+                const unsigned base = atomicAdd(p.cand_count + q, (unsigned)cnt);
+                uint64_t* dst = p.cand + (size_t)q * p.cand_cap;
+                for (int i = 0; i < cnt; ++i)
+                    if (base + i < (unsigned)p.cand_cap) dst[base + i] = staging[i * 128 + et];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                 // nobody leaves while the peer may still touch its smem / TMEM
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
 
@@ -419,21 +637,31 @@ static int check_gemm_catalog(const rebert_catalog_t* cat, const char* who) {
 
 template <int MODE>
 static int launch_gemm(const rebert_catalog_t* cat, const void* qbf16, GemmParams& p, cudaStream_t st) {
+    const bool pair = p.b > BM && getenv("REBERT_GEMM_1CTA") == nullptr;   // cta_group::2 needs >= 2 query tiles to pay off
     CUtensorMap map_q, map_rows;
     int rc = make_tmap(&map_q, qbf16, p.b, cat->ld, BM);
     if (rc != REBERT_OK) return rc;
-    rc = make_tmap(&map_rows, cat->rows, cat->n, cat->ld, BN);
+    rc = make_tmap(&map_rows, cat->rows, cat->n, cat->ld, pair ? 128 : BN);
     if (rc != REBERT_OK) return rc;
     p.kblocks = cat->ld / BK;
     p.n = cat->n;
     p.inv_norm = cat->inv_norm;
     p.num_qt = (p.b + BM - 1) / BM;
-    const int64_t tiles = (int64_t)p.num_rt * p.num_qt;
-    int grid = num_sms();
-    if (tiles < grid) grid = (int)tiles;
-    auto kern = gemm_kernel<MODE>;
-    REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_q, map_rows, p);
+    if (pair) {
+        const int64_t tiles = (int64_t)p.num_rt * ((p.b + 255) / 256);
+        int grid = num_sms() & ~1;
+        if (tiles * 2 < grid) grid = (int)(tiles * 2);
+        auto kern = gemm2_kernel<MODE>;
+        REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+        kern<<<grid, GEMM_THREADS, G2_SMEM, st>>>(map_q, map_rows, p);
+    } else {
+        const int64_t tiles = (int64_t)p.num_rt * p.num_qt;
+        int grid = num_sms();
+        if (tiles < grid) grid = (int)tiles;
+        auto kern = gemm_kernel<MODE>;
+        REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_q, map_rows, p);
+    }
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }
