@@ -71,6 +71,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -222,7 +227,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (lane == 0) {
-            const uint64_t pol_rows = l2_policy_evict_first();   // catalog tiles: streamed, shared by the current wave only
+            const uint64_t pol_rows = l2_policy_evict_normal();  // catalog tiles: re-read from L2 by the other query tiles of the wave
             const uint64_t pol_q = l2_policy_evict_last();       // query tiles: reused by every row tile
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -400,7 +405,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     if (warp == 0) {
         // ============================ TMA producer (both CTAs, each for its own halves) ============================
         if (lane == 0) {
-            const uint64_t pol_rows = l2_policy_evict_first();
+            const uint64_t pol_rows = l2_policy_evict_normal();
             const uint64_t pol_q = l2_policy_evict_last();
             uint32_t it = 0;
             for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {

@@ -151,13 +151,49 @@ class ShardedCatalog:
         return rows, scores
 
     # ------------------------------------------------------------------ batched (tensor-core) path ----------
+    def batch_context(self, qbf: torch.Tensor, qn64: torch.Tensor, k: int, excl_ptr=None, excl_col=None):
+        """Allocate everything a batched step needs (device tensors only) for prepared queries [b, ld]."""
+        import ctypes as C
+        store: CatalogStore = self.backend.store
+        lib = nat.load()
+        dev = store.device
+        b = qbf.shape[0]
+        plan = store.gemm_plan(b, k)
+        ep = ec = None
+        if excl_ptr is not None:
+            ep = torch.from_numpy(np.asarray(excl_ptr, dtype=np.int64)).to(dev)
+            ec = torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(dev)
+        hb = (b + 1) // 2
+        words = 2 * b * k + 2 * hb                                       # rows | scores | counts | status
+        ctx = {"b": b, "k": k, "plan": plan, "qbf": qbf, "qn64": qn64, "ep": ep, "ec": ec, "hb": hb, "words": words,
+               "ws": torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan)), dtype=torch.uint8, device=dev),
+               "local": torch.empty(words, dtype=torch.int64, device=dev),
+               "gathered": torch.empty((self.world, words), dtype=torch.int64, device=dev),
+               "m_rows": torch.empty((b, k), dtype=torch.int64, device=dev),
+               "m_scores": torch.empty((b, k), dtype=torch.float64, device=dev),
+               "m_count": torch.empty(b, dtype=torch.int32, device=dev)}
+        return ctx
+
+    def batch_step(self, ctx) -> None:
+        """Device-resident batched step: per-rank tcgen05 pass -> ONE packed all-gather -> merge.  No host sync."""
+        store: CatalogStore = self.backend.store
+        lib = nat.load()
+        b, k, hb, words, local = ctx["b"], ctx["k"], ctx["hb"], ctx["words"], ctx["local"]
+        o_rows, o_scores = local[:b * k], local[b * k:2 * b * k].view(torch.float64)
+        o_count = local[2 * b * k:2 * b * k + hb].view(torch.int32)
+        o_status = local[2 * b * k + hb:].view(torch.int32)
+        store.enqueue_batch(ctx["plan"], ctx["qbf"], ctx["qn64"], ctx["ep"], ctx["ec"], ctx["ws"], o_rows, o_scores, o_count, o_status)
+        dist.all_gather_into_tensor(ctx["gathered"].view(-1), local, group=self.group)
+        base = ctx["gathered"].data_ptr()
+        nat.check(lib.rebert_merge_topk(base, base + 8 * b * k, base + 16 * b * k, words, words, 2 * words, self.world, b, k,
+                                        ctx["m_rows"].data_ptr(), ctx["m_scores"].data_ptr(), ctx["m_count"].data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream))
+
     def recommend_batch(self, *, queries=None, liked_ptr=None, liked_col=None, liked_w=None, excl_ptr=None, excl_col=None,
                         k: int = 10, return_info: bool = False):
         """Sharded form of CatalogStore.recommend_batch: every rank runs the tcgen05 pass over its rows, the per-rank
         [b, k] results are all-gathered in ONE packed buffer and merged on every rank.  CUDA backend only."""
-        import ctypes as C
         store: CatalogStore = self.backend.store
-        lib = nat.load()
         dev = store.device
         if (queries is None) == (liked_ptr is None):
             raise ValueError("pass exactly one of queries / liked CSR")
@@ -170,32 +206,12 @@ class ShardedCatalog:
                     raise ValueError("Found array with 0 sample(s): a user has no liked movies in the catalog")
                 qn32, qn64, qbf = store.build_profiles(
                     lp, liked_col, liked_w, reduce_fn=lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group))
-            b = qbf.shape[0]
-            plan = store.gemm_plan(b, k)
-            ep = ec = None
-            if excl_ptr is not None:
-                ep = torch.from_numpy(np.asarray(excl_ptr, dtype=np.int64)).to(dev)
-                ec = torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(dev)
-            ws = torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan)), dtype=torch.uint8, device=dev)
-            hb = (b + 1) // 2
-            words = 2 * b * k + 2 * hb                                   # rows | scores | counts | status
-            local = torch.empty(words, dtype=torch.int64, device=dev)
-            o_rows, o_scores = local[:b * k], local[b * k:2 * b * k].view(torch.float64)
-            o_count = local[2 * b * k:2 * b * k + hb].view(torch.int32)[:b]
-            o_status = local[2 * b * k + hb:].view(torch.int32)[:b]
-            store.enqueue_batch(plan, qbf, qn64, ep, ec, ws, o_rows, o_scores, o_count, o_status)
-            gathered = torch.empty((self.world, words), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(gathered.view(-1), local, group=self.group)
-            m_rows = torch.empty((b, k), dtype=torch.int64, device=dev)
-            m_scores = torch.empty((b, k), dtype=torch.float64, device=dev)
-            m_count = torch.empty(b, dtype=torch.int32, device=dev)
-            base = gathered.data_ptr()
-            nat.check(lib.rebert_merge_topk(base, base + 8 * b * k, base + 16 * b * k, words, words, 2 * words, self.world, b, k,
-                                            m_rows.data_ptr(), m_scores.data_ptr(), m_count.data_ptr(),
-                                            torch.cuda.current_stream().cuda_stream))
-            status = gathered[:, 2 * b * k + hb:].contiguous().view(torch.int32)[:, :b].max(dim=0).values   # any rank unsure
-            rows, scores = m_rows.cpu().numpy(), m_scores.cpu().numpy()
-            counts, status = m_count.cpu().numpy(), status.cpu().numpy()
+            ctx = self.batch_context(qbf, qn64, k, excl_ptr, excl_col)
+            self.batch_step(ctx)
+            b, hb = ctx["b"], ctx["hb"]
+            status = ctx["gathered"][:, 2 * b * k + hb:].contiguous().view(torch.int32)[:, :b].max(dim=0).values   # any rank unsure
+            rows, scores = ctx["m_rows"].cpu().numpy(), ctx["m_scores"].cpu().numpy()
+            counts, status = ctx["m_count"].cpu().numpy(), status.cpu().numpy()
         ecp = None if excl_ptr is None else np.asarray(excl_ptr, dtype=np.int64)
         eca = None if excl_col is None else np.asarray(excl_col)
         for u in np.nonzero(status)[0]:                                  # identical on every rank -> collectives stay aligned

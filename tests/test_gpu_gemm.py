@@ -69,6 +69,31 @@ def test_recommend_batch_queries_vs_oracle(n, d, b, k):
         np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
 
 
+def test_recommend_batch_large_sample_path():
+    """n large enough that the threshold sample (> 48K rows) is radix-selected in place in global memory."""
+    n, d, b, k = 3_200_000, 64, 48, 10
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    plan = store.gemm_plan(b, k)
+    assert plan.sample_rows > 48 * 1024
+    q = _queries(b, d)
+    rows, scores, counts, info = store.recommend_batch(queries=q, k=k, return_info=True)
+    assert (info["status"] != 0).sum() <= 2
+    qn = q.astype(np.float64)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    best = np.full((b, k), -np.inf)
+    best_rows = np.zeros((b, k), dtype=np.int64)
+    for s0 in range(0, n, 400_000):                      # streamed oracle: keep the running top-k per query
+        m = store.rows[s0:s0 + 400_000, :d].to(torch.float64).cpu().numpy()
+        sc = (m / np.linalg.norm(m, axis=1, keepdims=True)) @ qn.T          # [chunk, b]
+        for u in range(b):
+            r, v = ora.topk_rows(sc[:, u], k)
+            allv = np.concatenate([best[u], v]); allr = np.concatenate([best_rows[u], r + s0])
+            order = np.lexsort((allr, -allv))[:k]
+            best[u], best_rows[u] = allv[order], allr[order]
+    np.testing.assert_array_equal(rows, best_rows)
+    np.testing.assert_allclose(scores, best, rtol=1e-9)
+
+
 def test_recommend_batch_profiles_vs_oracle():
     n, d, b, k = 60_000, 1536, 64, 10
     store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
