@@ -121,6 +121,8 @@ REBERT_API int rebert_profile_finalize(const double* sum64, const double* wsum, 
 /* ---- single query: fused score + mask + top-k (lib.py:51-55, L = 1 or a prebuilt profile) -- */
 /* Candidate count the fast pass keeps for a request of k: a multiple of 32 >= k + margin; 0 if k is unsupported. */
 REBERT_API int32_t rebert_candidates_for_k(int32_t k);
+/* The workspace must be ZERO-FILLED once before its first use (it holds a ticket counter that every launch leaves at
+ * zero again); after that it can be reused by consecutive calls on the same stream without further clearing. */
 REBERT_API size_t  rebert_gemv_workspace_bytes(int64_t n, int32_t kc);
 /* Fast pass.  score(r) = <qn32, row r> * inv_norm[r] in fp32; keeps the kc best allowed rows of the shard.
  * Output: cand_keys[kc] sorted best-first (packed (score, local row) keys; unused slots are 0). */
@@ -133,6 +135,24 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
 REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* qn64, const uint64_t* cand_keys, int32_t kc,
                          int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin,
                          rebert_stream stream);
+
+/* ---- host-buffer entry point: one call = one request, end to end -------------------------- */
+/* Scratch sizes for rebert_recommend_host with lists of at most n_liked_cap / n_exclude_cap entries and results of k.
+ * pinned: page-locked host memory (cudaHostAlloc / pinned torch tensor); device: device memory, ZERO-FILLED once. */
+REBERT_API int rebert_recommend_host_scratch(const rebert_catalog_t* cat, int32_t n_liked_cap, int32_t n_exclude_cap, int32_t k,
+                                             size_t* pinned_bytes, size_t* device_bytes);
+/* lib.py:43-55 for one request with HOST buffers: pass `query` [d] fp32 (not normalised) OR `liked_rows` (+ optional
+ * weights), plus the sorted unique GLOBAL `exclude_rows`; device_filter may add device-resident bitmap / genre / year
+ * tests.  Packs the request, ONE H2D copy, normalise or build the profile, fused score+mask+top-k, fp64 exact pass, ONE
+ * D2H copy, and synchronises the stream.  out_rows / out_scores are host [k] (-1 / -inf padded), *out_count <= k.
+ * Returns REBERT_ERR_INVALID with "Found array with 0 sample(s)" when liked_rows is given but empty (the reference's
+ * own failure for a user without liked movies). */
+REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* query, const int32_t* liked_rows,
+                                     const float* liked_w, int32_t n_liked, const int32_t* exclude_rows, int32_t n_exclude,
+                                     const rebert_filter_t* device_filter, int32_t k, int32_t kc, int32_t n_liked_cap,
+                                     int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
+                                     size_t device_bytes, int64_t* out_rows, double* out_scores, int32_t* out_count,
+                                     double* out_margin, rebert_stream stream);
 
 /* ---- merge of per-shard results (lib.py:55 across shards) --------------------------------- */
 /* For each of b queries merge `lists` sorted result lists into the best k.  List l of query u is at

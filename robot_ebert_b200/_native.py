@@ -51,6 +51,9 @@ _SIGS = {
     "rebert_gemv_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "rebert_gemv_topk": (C.c_int, [C.POINTER(Catalog), _P, C.POINTER(Filter), C.c_int32, _P, C.c_size_t, _P, _P]),
     "rebert_finalize_topk": (C.c_int, [C.POINTER(Catalog), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "rebert_recommend_host_scratch": (C.c_int, [C.POINTER(Catalog), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "rebert_recommend_host": (C.c_int, [C.POINTER(Catalog), _P, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(Filter), C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, _P, C.c_size_t, _P, C.c_size_t, _P, _P, _P, _P, _P]),
     "rebert_merge_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "rebert_score_subset": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "rebert_scores_dense": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, _P]),

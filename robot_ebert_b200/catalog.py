@@ -44,12 +44,28 @@ class _Scratch:
         self.in_cap = 0
         self.kc = 0
         self.k_cap = 0
+        self.nl_cap = self.ne_cap = self.hk_cap = 0
         dev = store.device
         ld = store.ld
         self.qn32 = torch.zeros(ld, dtype=torch.float32, device=dev)
         self.qn64 = torch.zeros(ld, dtype=torch.float64, device=dev)
         self.sum64 = torch.zeros(ld, dtype=torch.float64, device=dev)
         self.wsum = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def ensure_host(self, n_liked: int, n_excl: int, k: int):
+        """Pinned + device scratch of rebert_recommend_host, grown geometrically."""
+        if n_liked > self.nl_cap or n_excl > self.ne_cap or k > self.hk_cap:
+            lib = nat.load()
+            self.nl_cap = max(self.nl_cap, 1024, 1 << max(n_liked - 1, 0).bit_length())
+            self.ne_cap = max(self.ne_cap, 1024, 1 << max(n_excl - 1, 0).bit_length())
+            self.hk_cap = max(self.hk_cap, 16, 1 << (k - 1).bit_length())
+            pb, db = C.c_size_t(0), C.c_size_t(0)
+            nat.check(lib.rebert_recommend_host_scratch(C.byref(self.store._c), self.nl_cap, self.ne_cap, self.hk_cap,
+                                                        C.byref(pb), C.byref(db)))
+            self.hpin = torch.empty(pb.value, dtype=torch.uint8).pin_memory()
+            self.hdev = torch.zeros(db.value, dtype=torch.uint8, device=self.store.device)   # zero once (ticket counter)
+            self.h_rows = np.empty(self.hk_cap, dtype=np.int64)
+            self.h_scores = np.empty(self.hk_cap, dtype=np.float64)
 
     def ensure_in(self, nbytes: int):
         if nbytes > self.in_cap:
@@ -63,7 +79,7 @@ class _Scratch:
         if kc != self.kc:
             lib = nat.load()
             wsb = lib.rebert_gemv_workspace_bytes(self.store.n, kc)
-            self.ws = torch.empty(wsb, dtype=torch.uint8, device=self.store.device)
+            self.ws = torch.zeros(wsb, dtype=torch.uint8, device=self.store.device)   # zero once: holds the ticket counter
             self.cand = torch.empty(kc, dtype=torch.int64, device=self.store.device)   # u64 keys
             self.kc = kc
         if k != self.k_cap:
@@ -239,14 +255,56 @@ class CatalogStore:
         return rows, scores
 
     def _recommend_once(self, lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter):
+        """One rebert_recommend_host call: host buffers in, host buffers out, copies + kernels + sync inside."""
         s = self._scratch()
+        d = self.d
+        q = lk = w = ex = None
+        nl = ne = 0
+        if query is not None:
+            q = np.ascontiguousarray(query, dtype=np.float32)
+            if q.shape != (d,):
+                raise ValueError(f"query must have shape ({d},)")
+        else:
+            lk = np.ascontiguousarray(liked_rows, dtype=np.int32)
+            nl = int(lk.shape[0])
+            if weights is not None:
+                w = np.ascontiguousarray(weights, dtype=np.float32)
+        if exclude_rows is not None and len(exclude_rows):
+            ex = np.unique(np.asarray(exclude_rows, dtype=np.int32))
+            ne = int(ex.shape[0])
+        s.ensure_host(nl, ne, k)
+        f = self._filter_struct(row_filter)
+        cnt, margin = C.c_int32(0), C.c_double(0.0)
+        off_rp = _align(4 * d)
+        self.last_h2d_bytes = (off_rp + 16 + _align(4 * ne) + 2 * _align(4 * nl)) if lk is not None else \
+            (off_rp + 16 + _align(4 * ne) if ne else off_rp)
         with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream()
-            excl_ptr, ne = self.stage_inputs(query, liked_rows, weights, exclude_rows, k, kc)
-            self.enqueue_topk(k, kc, excl_ptr, ne, row_filter)
-            s.h_out.copy_(s.d_out, non_blocking=True)
-            stream.synchronize()
-        return unpack_result(s.h_out_np, k)
+            rc = lib.rebert_recommend_host(
+                C.byref(self._c), None if q is None else q.ctypes.data, None if lk is None else lk.ctypes.data,
+                None if w is None else w.ctypes.data, nl, None if ex is None else ex.ctypes.data, ne,
+                None if f is None else C.byref(f), k, kc, s.nl_cap, s.ne_cap, s.hpin.data_ptr(), s.hpin.numel(),
+                s.hdev.data_ptr(), s.hdev.numel(), s.h_rows.ctypes.data, s.h_scores.ctypes.data, C.byref(cnt),
+                C.byref(margin), torch.cuda.current_stream().cuda_stream)
+        nat.check(rc)
+        n = cnt.value
+        return s.h_rows[:n].copy(), s.h_scores[:n].copy(), margin.value
+
+    def _filter_struct(self, row_filter: Optional[RowFilter]):
+        """rebert_filter_t for the device-resident predicates of a RowFilter (None when there are none)."""
+        if row_filter is None:
+            return None
+        f = nat.Filter()
+        if row_filter.exclude_bitmap is not None:
+            f.exclude_bitmap = row_filter.exclude_bitmap.data_ptr()
+        if row_filter.genre_any:
+            if self.genre_bits is None:
+                raise ValueError("row_filter.genre_any needs set_metadata()")
+            f.genre_bits, f.genre_any = self.genre_bits.data_ptr(), row_filter.genre_any
+        if (row_filter.year_lo, row_filter.year_hi) != (0, 65535):
+            if self.year is None:
+                raise ValueError("row_filter year range needs set_metadata()")
+            f.year, f.year_lo, f.year_hi = self.year.data_ptr(), row_filter.year_lo, row_filter.year_hi
+        return f
 
     def stage_inputs(self, query, liked_rows, weights, exclude_rows, k, kc, profile_partial_only: bool = False):
         """Pack the request into one pinned buffer, issue ONE H2D copy, and enqueue query normalisation or the
@@ -314,20 +372,9 @@ class CatalogStore:
         s = self._scratch()
         s.ensure_out(k, kc)
         st = torch.cuda.current_stream().cuda_stream
-        f = nat.Filter()
+        f = self._filter_struct(row_filter) or nat.Filter()
         if n_excl:
             f.exclude_rows, f.n_exclude = excl_ptr, n_excl
-        if row_filter is not None:
-            if row_filter.exclude_bitmap is not None:
-                f.exclude_bitmap = row_filter.exclude_bitmap.data_ptr()
-            if row_filter.genre_any:
-                if self.genre_bits is None:
-                    raise ValueError("row_filter.genre_any needs set_metadata()")
-                f.genre_bits, f.genre_any = self.genre_bits.data_ptr(), row_filter.genre_any
-            if (row_filter.year_lo, row_filter.year_hi) != (0, 65535):
-                if self.year is None:
-                    raise ValueError("row_filter year range needs set_metadata()")
-                f.year, f.year_lo, f.year_hi = self.year.data_ptr(), row_filter.year_lo, row_filter.year_hi
         nat.check(lib.rebert_gemv_topk(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
                                        s.ws.numel(), s.cand.data_ptr(), st))
         ob = s.d_out.data_ptr()

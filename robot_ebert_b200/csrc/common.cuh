@@ -89,10 +89,24 @@ __device__ __forceinline__ bool sorted_contains(const int32_t* __restrict__ a, i
     return lo < n && __ldg(a + lo) == v;
 }
 
+// same search on a list staged in shared memory (plain loads, ~30-cycle steps instead of L2 round trips)
+__device__ __forceinline__ bool sorted_contains_smem(const int32_t* a, int n, int32_t v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && a[lo] == v;
+}
+
 // Evaluated only for rows that beat the running threshold, so its cost is off the streaming path.
-__device__ __forceinline__ bool row_allowed(const DevFilter& f, uint32_t local_row) {
+// excl_s: the exclusion list staged in shared memory by the caller, or nullptr to search the global copy.
+__device__ __forceinline__ bool row_allowed(const DevFilter& f, uint32_t local_row, const int32_t* excl_s = nullptr) {
     if (f.exclude_bitmap && ((__ldg(f.exclude_bitmap + (local_row >> 5)) >> (local_row & 31)) & 1u)) return false;
-    if (f.n_exclude > 0 && sorted_contains(f.exclude_rows, f.n_exclude, (int32_t)(f.row_base + local_row))) return false;
+    if (f.n_exclude > 0) {
+        const int32_t g = (int32_t)(f.row_base + local_row);
+        if (excl_s ? sorted_contains_smem(excl_s, f.n_exclude, g) : sorted_contains(f.exclude_rows, f.n_exclude, g)) return false;
+    }
     if (f.genre_bits && (__ldg(f.genre_bits + local_row) & f.genre_any) == 0) return false;
     if (f.year) {
         uint32_t y = __ldg(f.year + local_row);

@@ -19,6 +19,7 @@ constexpr int kConsumerWarps = 8;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kStageBytes = 48 * 1024;
 constexpr int kMaxStages = 4;
+constexpr int kMaxExclSmem = 4096;   // exclusion rows staged in shared memory (larger lists are searched in global memory)
 
 struct GemvParams {
     const void*  rows;
@@ -157,12 +158,20 @@ __device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int
     }
     __syncthreads();
     const uint64_t T = s_t0 > s_t1 ? s_t0 : s_t1;
-    // gather survivors
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const uint64_t key = ldcg_u64(lists_g + i);
-        if (key != 0 && key >= T) {
-            const int idx = atomicAdd(&s_cnt, 1);
-            if (idx < cap) buf[idx] = key;
+    // gather survivors (loads issued four at a time so their L2 latencies overlap)
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+        uint64_t kk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * blockDim.x;
+            kk[j] = i < total ? ldcg_u64(lists_g + i) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (kk[j] != 0 && kk[j] >= T) {
+                const int idx = atomicAdd(&s_cnt, 1);
+                if (idx < cap) buf[idx] = kk[j];
+            }
         }
     }
     __syncthreads();
@@ -196,6 +205,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_stride);
     uint64_t* empty_bar = full_bar + kMaxStages;
     float* q_smem = (float*)(empty_bar + kMaxStages);            // generic kernel only: [ld]
+    int32_t* excl_smem = (int32_t*)(q_smem + (kRegQ ? 0 : p.ld));
+    const bool excl_staged = p.filter.n_exclude > 0 && p.filter.n_exclude <= kMaxExclSmem;
+    const int32_t* excl_s = excl_staged ? excl_smem : nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -208,6 +220,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     }
     if (!kRegQ) {
         for (int c = threadIdx.x; c < p.ld; c += blockDim.x) q_smem[c] = p.q[c];
+    }
+    if (excl_staged) {
+        for (int c = threadIdx.x; c < p.filter.n_exclude; c += blockDim.x) excl_smem[c] = __ldg(p.filter.exclude_rows + c);
     }
     __syncthreads();
 
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                     ma &= ma - 1;
                     const float sc = __shfl_sync(0xffffffffu, sa, src);
                     const uint32_t lr = (uint32_t)(row0 + base + src / LANES);
-                    if (sc > top.thr && row_allowed(p.filter, lr)) top.insert(make_key(sc, lr), lane);
+                    if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) top.insert(make_key(sc, lr), lane);
                 }
                 unsigned mb = __ballot_sync(0xffffffffu, vB && cl == 0 && sb > top.thr);
                 while (mb) {
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                     mb &= mb - 1;
                     const float sc = __shfl_sync(0xffffffffu, sb, src);
                     const uint32_t lr = (uint32_t)(row0 + base + kConsumerWarps * RPW + src / LANES);
-                    if (sc > top.thr && row_allowed(p.filter, lr)) top.insert(make_key(sc, lr), lane);
+                    if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) top.insert(make_key(sc, lr), lane);
                 }
             }
             __syncwarp();
@@ -379,7 +394,7 @@ struct GemvLaunch {
     size_t smem;
 };
 
-static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic) {
+static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic, int n_exclude) {
     GemvLaunch g;
     const int row_bytes = L.ld * L.esize;
     const int rpw = 32 / L.lanes;
@@ -389,10 +404,14 @@ static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic)
     else if (tr >= unit) tr = unit;
     tr &= ~3;
     if (tr < 4) tr = 4;
+    // small catalogs: shrink the tile (down to one step of all warps) so the rows spread over more SMs
+    const int sms = num_sms();
+    while (tr >= 2 * unit && (n + tr - 1) / tr < sms && ((tr / 2) & 3) == 0) tr /= 2;
     g.tile_rows = tr;
     const int tile_bytes = tr * row_bytes;
     const int stage_stride = tile_bytes + ((tr * 4 + 127) & ~127);
-    const size_t fixed = 2 * kMaxStages * sizeof(uint64_t) + (generic ? (size_t)L.ld * 4 : 0) + 128;
+    const size_t excl_bytes = (n_exclude > 0 && n_exclude <= kMaxExclSmem) ? (size_t)n_exclude * 4 : 0;
+    const size_t fixed = 2 * kMaxStages * sizeof(uint64_t) + (generic ? (size_t)L.ld * 4 : 0) + excl_bytes + 128;
     int stages = kMaxStages;
     while (stages > 1 && (size_t)stages * stage_stride + fixed > 220 * 1024) --stages;
     g.stages = stages;
@@ -504,7 +523,8 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
         return REBERT_OK;
     }
     const bool generic = use_generic(L);
-    GemvLaunch g = plan_gemv(L, cat->n, kc, generic);
+    const int n_excl = (filter && filter->exclude_rows && filter->n_exclude > 0) ? filter->n_exclude : 0;
+    GemvLaunch g = plan_gemv(L, cat->n, kc, generic, n_excl);
     GemvParams p;
     p.rows = cat->rows;
     p.inv_norm = cat->inv_norm;
@@ -521,7 +541,6 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.counter = (unsigned*)(p.cta_lists + (size_t)num_sms() * kc);
     p.cand_keys = cand_keys;
     p.merge_cap = g.merge_cap;
-    REBERT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned), st));
 
     return cat->dtype == REBERT_F32 ? launch_gemv<float>(L, p, g, kc, st) : launch_gemv<__nv_bfloat16>(L, p, g, kc, st);
 }
