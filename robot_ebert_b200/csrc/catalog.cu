@@ -3,6 +3,9 @@
 // lib.py:105-106 (subset scoring).  All of these are one-pass HBM-bound or tiny kernels.
 #include <stdarg.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "common.cuh"
 
 namespace rebert {
@@ -21,6 +24,24 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return REBERT_ERR_CUDA;
+}
+// Opt-in shared-memory ceiling of the device.  Kernels always raise their limit to THIS constant: the attribute is a
+// per-function global, so setting a per-call size would race between concurrent callers.
+int max_optin_smem() {
+    int dev = 0, v = 227 * 1024;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return v;
+}
+int raise_smem_limit_impl(const void* kern) {
+    static std::mutex mu;
+    static std::unordered_set<const void*> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count(kern)) return REBERT_OK;
+    cudaFuncAttributes a;
+    REBERT_CUDA(cudaFuncGetAttributes(&a, kern));
+    REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem() - (int)a.sharedSizeBytes));
+    done.insert(kern);
+    return REBERT_OK;
 }
 int num_sms() {
     int dev = 0, sms = 148;

@@ -27,6 +27,11 @@ int  cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 int num_sms();
+int max_optin_smem();
+// Raise a kernel's dynamic shared-memory limit to the device ceiling (opt-in max minus the kernel's static shared
+// memory), once per kernel.  Always the same constant, so concurrent callers cannot race each other's launches.
+int raise_smem_limit_impl(const void* kern);
+template <typename K> static inline int raise_smem_limit(K kern) { return raise_smem_limit_impl((const void*)kern); }
 
 // ---------------------------------------------------------------- layout --------------------
 // A stored row is LANES * CPL chunks of 16 bytes: LANES lanes of a warp each own CPL chunks.

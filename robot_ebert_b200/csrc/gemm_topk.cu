@@ -657,14 +657,14 @@ static int launch_gemm(const rebert_catalog_t* cat, const void* qbf16, GemmParam
         int grid = num_sms() & ~1;
         if (tiles * 2 < grid) grid = (int)(tiles * 2);
         auto kern = gemm2_kernel<MODE>;
-        REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+        { int rc__ = raise_smem_limit(kern); if (rc__ != REBERT_OK) return rc__; }
         kern<<<grid, GEMM_THREADS, G2_SMEM, st>>>(map_q, map_rows, p);
     } else {
         const int64_t tiles = (int64_t)p.num_rt * p.num_qt;
         int grid = num_sms();
         if (tiles < grid) grid = (int)tiles;
         auto kern = gemm_kernel<MODE>;
-        REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        { int rc__ = raise_smem_limit(kern); if (rc__ != REBERT_OK) return rc__; }
         kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_q, map_rows, p);
     }
     REBERT_CUDA(cudaGetLastError());
@@ -793,7 +793,7 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     // 2. thresholds
     const int keys_in_smem = plan->sample_rows <= 48 * 1024;
     const size_t tsmem = keys_in_smem ? (size_t)plan->sample_rows * 4 : 16;
-    REBERT_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    { int rc__ = raise_smem_limit(select_threshold_kernel); if (rc__ != REBERT_OK) return rc__; }
     select_threshold_kernel<<<b, 256, tsmem, st>>>(w.sample, keys_in_smem, plan->sample_rows, cat->n, cat->row_base, 0, stride,
                                                    plan->sample_rank, excl_row_ptr, excl_col, w.tau);
     REBERT_CUDA(cudaGetLastError());
@@ -814,7 +814,7 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     int p2 = 2;
     while (p2 < plan->cand_cap) p2 <<= 1;
     const size_t csmem = (size_t)p2 * 8;
-    REBERT_CUDA(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+    { int rc__ = raise_smem_limit(select_candidates_kernel); if (rc__ != REBERT_OK) return rc__; }
     select_candidates_kernel<<<b, 512, csmem, st>>>(w.cand, w.cand_count, plan->cand_cap, plan->kc, cat->row_base, excl_row_ptr,
                                                     excl_col, w.tau, w.cand_keys, out_status);
     REBERT_CUDA(cudaGetLastError());

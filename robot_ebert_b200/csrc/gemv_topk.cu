@@ -437,7 +437,7 @@ static int launch_gemv_m(const GemvParams& p, const GemvLaunch& g, int kc, cudaS
 #define REBERT_LAUNCH_M(MM)                                                                                      \
     {                                                                                                            \
         auto kern = gemv_topk_kernel<T, CPL, LANES, MM>;                                                         \
-        REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));       \
+        { int rc__ = raise_smem_limit(kern); if (rc__ != REBERT_OK) return rc__; }       \
         kern<<<g.grid, kThreads, g.smem, st>>>(p);                                                               \
     }
     switch (kc) {

@@ -178,3 +178,33 @@ def test_unsupported_and_invalid_arguments():
         store.recommend(query=q[:5], k=3)
     with pytest.raises(ValueError):
         store.recommend(query=q, liked_rows=np.array([1]), k=3)
+
+
+def test_concurrent_requests_from_threads():
+    """FastAPI's threadpool pattern: many threads share one immutable catalog, each with its own scratch + stream."""
+    import threading
+    n, d = 60_000, 256
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    m = _stored_f64(store)
+    users = synth.user_ratings(2, n, 8)
+    want = [ora.recommend_rows(m, r[x >= 3.5], r, 10) for r, x in users]
+    errors = []
+
+    def worker(u):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(25):
+                    r, x = users[u]
+                    rows, scores = store.recommend(liked_rows=r[x >= 3.5], exclude_rows=r, k=10)
+                    assert np.array_equal(rows, want[u][0])
+                    assert np.allclose(scores, want[u][1], rtol=1e-9)
+        except Exception as e:  # noqa: BLE001
+            errors.append((u, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(u,)) for u in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
