@@ -445,7 +445,14 @@ class CatalogStore:
                     raise ValueError("Found array with 0 sample(s): a user has no liked movies in the catalog")
                 qn32, qn64, qbf = self.build_profiles(lp, liked_col, liked_w)
             b = qbf.shape[0]
-            plan = self.gemm_plan(b, k)
+            try:
+                plan = self.gemm_plan(b, k)
+            except nat.NativeError as e:
+                if e.code != nat.ERR_UNSUPPORTED:
+                    raise
+                plan = None          # catalog too small for the sampled-threshold scheme: one fused GEMV per user instead
+            if plan is None or self.dtype != "bf16":
+                return self._recommend_batch_loop(qn32, qn64, excl_ptr, excl_col, k, return_info)
             ep = ec = None
             if excl_ptr is not None:
                 ep = torch.from_numpy(np.asarray(excl_ptr, dtype=np.int64)).to(dev)
@@ -476,6 +483,33 @@ class CatalogStore:
                     rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
         if return_info:
             return rows, scores, counts, {"status": status, "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
+        return rows, scores, counts
+
+    def _recommend_batch_loop(self, qn32, qn64, excl_ptr, excl_col, k, return_info):
+        """Small or fp32 catalogs: the batch is served by the single-query kernel, one launch per prepared query."""
+        lib = nat.load()
+        b = qn32.shape[0]
+        kc = lib.rebert_candidates_for_k(k)
+        if kc == 0:
+            raise ValueError(f"k={k} is outside the supported range (1..240)")
+        rows = np.full((b, k), -1, dtype=np.int64)
+        scores = np.full((b, k), -np.inf, dtype=np.float64)
+        counts = np.zeros(b, dtype=np.int32)
+        s = self._scratch()
+        ecp = None if excl_ptr is None else np.asarray(excl_ptr, dtype=np.int64)
+        ec = None if excl_col is None else torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(self.device)
+        for u in range(b):
+            s.ensure_out(k, kc)
+            s.qn32.copy_(qn32[u])
+            s.qn64.copy_(qn64[u])
+            ptr, ne = None, 0
+            if ecp is not None and ecp[u + 1] > ecp[u]:
+                ptr, ne = ec.data_ptr() + 4 * int(ecp[u]), int(ecp[u + 1] - ecp[u])
+            self.enqueue_topk(k, kc, ptr, ne)
+            r, sc, _ = unpack_result(s.d_out.cpu().numpy(), k)
+            rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
+        if return_info:
+            return rows, scores, counts, {"status": np.zeros(b, dtype=np.int32), "plan": None}
         return rows, scores, counts
 
     # ------------------------------------------------------------------ diagnostics -------------

@@ -116,10 +116,19 @@ def test_recommend_batch_profiles_vs_oracle():
         np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
 
 
-def test_batched_path_rejects_small_or_fp32_catalogs():
-    store = CatalogStore.synthetic(0, 2000, 64, "bf16")
-    with pytest.raises(Exception):
-        store.recommend_batch(queries=_queries(4, 64), k=10)
+def test_small_or_fp32_catalogs_are_served_by_the_single_query_kernel():
+    """Below the batched path's minimum size (or for fp32 storage) recommend_batch loops the fused GEMV: same answers."""
+    for n, d, dtype in [(2000, 64, "bf16"), (30_000, 64, "fp32")]:
+        store = CatalogStore.synthetic(0, n, d, dtype)
+        m = _stored_f64(store)
+        q = _queries(5, d)
+        rows, scores, counts, info = store.recommend_batch(queries=q, k=10, return_info=True)
+        assert info["plan"] is None
+        for u in range(5):
+            want_rows, want_scores = ora.query_rows(m, q[u].astype(np.float64), None, 10)
+            np.testing.assert_array_equal(rows[u], want_rows)
+            np.testing.assert_allclose(scores[u], want_scores, rtol=1e-9)
     store = CatalogStore.synthetic(0, 40_000, 64, "fp32")
+    _, _, qbf = store.prepare_queries(_queries(4, 64))
     with pytest.raises(Exception):
-        store.recommend_batch(queries=_queries(4, 64), k=10)
+        store.gemm_scores(qbf, 0, 256)          # the tensor-core building block itself is bf16-only
