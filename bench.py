@@ -290,9 +290,12 @@ def run_b200(args):
         nat.check(lib.rebert_finalize_topk(C.byref(store._c), scratch.qn64.data_ptr(), scratch.cand.data_ptr(), kc, K, ob,
                                            ob + 8 * K, ob + 16 * K, ob + 16 * K + 8, st))
         if sharded is not None:
-            buf = sharded._gather_buf(K, scratch.d_out)
-            dist.all_gather_into_tensor(buf.view(-1), scratch.d_out)
-            sharded.backend.merge(buf, K)
+            if sharded.backend.exchange == "p2p":
+                sharded.backend.exchange_merge(scratch.d_out, K)          # one kernel: P2P stores + flags + merge
+            else:
+                buf = sharded._gather_buf(K, scratch.d_out)
+                dist.all_gather_into_tensor(buf.view(-1), scratch.d_out)
+                sharded.backend.merge(buf, K)
 
     for _ in range(warmup):
         step()
@@ -350,6 +353,8 @@ def run_b200(args):
             "dtype": "bf16 storage, fp32 accumulate, fp64 re-score", "data": "synthetic",
             "config": {"workload": workload_name(rows), "rows": rows, "dim": DIM, "k": K, "exclusions": N_EXCL,
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                       "exchange": (("fused P2P store+flag+merge kernel over NVLink peer memory" if sharded.backend.exchange == "p2p"
+                                     else "NCCL all-gather + merge kernel") if world > 1 else None),
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e9:.2f} GB read per step per GPU)"},
             "roofline": {"bound": "hbm", "kernel": "gemv_topk_kernel<bf16,6,32,1> (scores + mask + top-k + cross-CTA merge, one launch)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,

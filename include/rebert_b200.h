@@ -163,6 +163,19 @@ REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, cons
                       int64_t scores_stride, int64_t counts_stride, int32_t lists, int32_t b, int32_t k,
                       int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_stream stream);
 
+/* Fused exchange + merge over NVLink peer memory for the row-sharded single-query path (one kernel instead of an
+ * all-gather plus a merge).  Every rank owns a peer-mapped buffer of rebert_exchange_buffer_bytes(world, k_max) bytes,
+ * ZERO-FILLED once; peer_buffers is a HOST array of the `world` device addresses under which THIS process sees the
+ * ranks' buffers (e.g. torch symmetric memory's buffer_ptrs).  local_packed / out_packed are packed result blocks of
+ * 2k+2 64-bit words: rows[k] | fp64 scores[k] | count | margin (what rebert_finalize_topk writes when its four outputs
+ * point into one block).  seq is the call number, starting at 1 and incremented by every rank on every call.
+ * The kernel stores the local block into every peer, publishes a flag, waits for all peers' flags and merges under
+ * (score desc, row asc); *err_flag (device int32) becomes non-zero if a peer did not deliver within ~10 s. */
+REBERT_API size_t rebert_exchange_buffer_bytes(int32_t world, int32_t k_max);
+REBERT_API int rebert_exchange_merge(const uint64_t* peer_buffers, int32_t world, int32_t rank, int32_t k, int32_t k_max,
+                                     uint32_t seq, const int64_t* local_packed, int64_t* out_packed, int32_t* err_flag,
+                                     rebert_stream stream);
+
 /* ---- subset scoring for the search re-rank (lib.py:105-106) ------------------------------- */
 /* out[u, j] = <p64[u], row sub_rows[j]> / norm64 in fp64 for m candidate GLOBAL rows (all must be in this shard). */
 REBERT_API int rebert_score_subset(const rebert_catalog_t* cat, const double* p64, int32_t b, const int32_t* sub_rows, int32_t m,

@@ -28,8 +28,11 @@ int cuda_fail(cudaError_t e, const char* what) {
 // Opt-in shared-memory ceiling of the device.  Kernels always raise their limit to THIS constant: the attribute is a
 // per-function global, so setting a per-call size would race between concurrent callers.
 int max_optin_smem() {
+    static int cached = 0;                       // one process drives one GPU model; benign if two threads race to fill it
+    if (cached) return cached;
     int dev = 0, v = 227 * 1024;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cached = v;
     return v;
 }
 int raise_smem_limit_impl(const void* kern) {
@@ -44,8 +47,11 @@ int raise_smem_limit_impl(const void* kern) {
     return REBERT_OK;
 }
 int num_sms() {
+    static int cached = 0;
+    if (cached) return cached;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached = sms;
     return sms;
 }
 

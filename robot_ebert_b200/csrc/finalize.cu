@@ -132,6 +132,98 @@ __global__ void merge_topk_kernel(const int64_t* __restrict__ rows, const double
     if (threadIdx.x == 0) out_count[u] = nout;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused exchange + merge over NVLink peer memory (row-sharded single-query path; replaces all-gather + merge).
+// Every rank's symmetric buffer holds, for both parities of the call sequence number,
+//     gather[parity][rank][words_cap]  packed results (rows k | fp64 scores k | count | margin)
+//     flag  [parity][rank]            the sequence number of the last result that rank delivered
+// One CTA per rank: (1) store my packed result straight into every peer's gather slot (P2P stores through
+// NVLink/NVSwitch), (2) system-scope fence, then publish my flag in every peer, (3) acquire-spin on my own flags until
+// all ranks delivered, (4) rank-merge the G lists under (score desc, row asc).  Parity double-buffering is enough:
+// a rank can be at most one call ahead of a peer, because it needs that peer's flag of the current call to finish it.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerBufs { unsigned long long* p[kMaxPeers]; };
+
+__device__ __forceinline__ size_t xchg_gather_off(int parity, int rank, int world, int words_cap) {
+    return ((size_t)parity * world + rank) * words_cap;
+}
+__device__ __forceinline__ size_t xchg_flag_off(int parity, int rank, int world, int words_cap) {
+    return (size_t)2 * world * words_cap + (size_t)parity * world + rank;
+}
+
+__global__ void __launch_bounds__(256) exchange_merge_kernel(PeerBufs peers, int world, int my_rank, int k, int words_cap,
+                                                             unsigned seq, const unsigned long long* __restrict__ local,
+                                                             unsigned long long* __restrict__ out, int* __restrict__ err,
+                                                             long long timeout_cycles) {
+    const int words = 2 * k + 2;
+    const int parity = (int)(seq & 1u);
+    unsigned long long* mine = peers.p[my_rank];
+    // (1) deliver my result to every rank (myself included)
+    for (int i = threadIdx.x; i < world * words; i += blockDim.x) {
+        const int pr = i / words, w = i - pr * words;
+        peers.p[pr][xchg_gather_off(parity, my_rank, world, words_cap) + w] = local[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    // (2) publish, (3) wait for everybody
+    if (threadIdx.x < world) {
+        unsigned long long* f = peers.p[threadIdx.x] + xchg_flag_off(parity, my_rank, world, words_cap);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)seq) : "memory");
+        const unsigned long long* w = mine + xchg_flag_off(parity, threadIdx.x, world, words_cap);
+        const long long t0 = clock64();
+        unsigned long long v;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if (v == (unsigned long long)seq) break;
+            if (clock64() - t0 > timeout_cycles) { atomicExch(err, 1 + threadIdx.x); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    // (4) merge the `world` sorted lists
+    const unsigned long long* g = mine + xchg_gather_off(parity, 0, world, words_cap);
+    int total = 0;
+    double margin = INFINITY;
+    for (int l = 0; l < world; ++l) {
+        const unsigned long long* L = g + (size_t)l * words_cap;
+        total += min((int)(unsigned)L[2 * k], k);
+        margin = fmin(margin, __longlong_as_double((long long)L[2 * k + 1]));
+    }
+    const int nout = total < k ? total : k;
+    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+        const int l = i / k, e = i - l * k;
+        const unsigned long long* L = g + (size_t)l * words_cap;
+        if (e >= (int)(unsigned)L[2 * k]) continue;
+        const int64_t r = (int64_t)L[e];
+        const double sc = __longlong_as_double((long long)L[k + e]);
+        int rank = e;
+        for (int o = 0; o < world; ++o) {
+            if (o == l) continue;
+            const unsigned long long* O = g + (size_t)o * words_cap;
+            int lo = 0, hi = min((int)(unsigned)O[2 * k], k);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (better(__longlong_as_double((long long)O[k + mid]), (int64_t)O[mid], sc, r)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            out[rank] = (unsigned long long)r;
+            out[k + rank] = (unsigned long long)__double_as_longlong(sc);
+        }
+    }
+    for (int i = nout + threadIdx.x; i < k; i += blockDim.x) {
+        out[i] = (unsigned long long)(-1ll);
+        out[k + i] = (unsigned long long)__double_as_longlong(-INFINITY);
+    }
+    if (threadIdx.x == 0) {
+        out[2 * k] = (unsigned long long)(unsigned)nout;
+        out[2 * k + 1] = (unsigned long long)__double_as_longlong(margin);
+    }
+}
+
 int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
                     int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st) {
     if (cat->dtype == REBERT_F32)
@@ -169,6 +261,31 @@ REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, cons
     REBERT_REQUIRE(lists > 0 && b > 0 && k > 0, "merge_topk: lists=%d b=%d k=%d", lists, b, k);
     merge_topk_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(rows, scores, counts, rows_stride, scores_stride, counts_stride,
                                                            lists, k, out_rows, out_scores, out_count);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API size_t rebert_exchange_buffer_bytes(int32_t world, int32_t k_max) {
+    if (world <= 0 || world > kMaxPeers || k_max <= 0) return 0;
+    const size_t words_cap = (size_t)2 * k_max + 2;
+    return ((size_t)2 * world * words_cap + (size_t)2 * world) * 8;
+}
+
+REBERT_API int rebert_exchange_merge(const uint64_t* peer_buffers, int32_t world, int32_t rank, int32_t k, int32_t k_max,
+                                     uint32_t seq, const int64_t* local_packed, int64_t* out_packed, int32_t* err_flag,
+                                     rebert_stream stream) {
+    REBERT_REQUIRE(peer_buffers && local_packed && out_packed && err_flag, "exchange_merge: null argument");
+    REBERT_REQUIRE(world > 0 && world <= kMaxPeers && rank >= 0 && rank < world, "exchange_merge: world=%d rank=%d", world, rank);
+    REBERT_REQUIRE(k > 0 && k <= k_max && seq != 0, "exchange_merge: k=%d k_max=%d seq=%u", k, k_max, seq);
+    PeerBufs pb;
+    memset(&pb, 0, sizeof(pb));
+    for (int i = 0; i < world; ++i) pb.p[i] = (unsigned long long*)(uintptr_t)peer_buffers[i];
+    // ~10 s of SM clocks at 2 GHz: only a dead peer gets here.  (A constant: querying the clock rate is a slow driver
+    // call and this function sits on the per-request path.)
+    const long long timeout_cycles = 20000000000ll;
+    exchange_merge_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pb, world, rank, k, 2 * k_max + 2, seq,
+                                                               (const unsigned long long*)local_packed,
+                                                               (unsigned long long*)out_packed, err_flag, timeout_cycles);
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }

@@ -51,10 +51,54 @@ class ShardPlan:
 class CudaShardBackend:
     """Product backend: the local shard is a CatalogStore; every step is a kernel enqueued on the current stream."""
 
+    K_MAX = 240          # largest k of the single-query path
+
     def __init__(self, store: CatalogStore):
         self.store = store
         self.device = store.device
         self._merged = {}
+        self.exchange = "nccl"       # becomes "p2p" once setup_p2p() has mapped the peers' buffers
+        self._seq = 0
+
+    def setup_p2p(self, group=None) -> bool:
+        """Map one small symmetric buffer per rank (torch symmetric memory = CUDA VMM + fabric handles) so that the
+        exchange step becomes ONE kernel of P2P stores + flags + merge.  Falls back to NCCL all-gather if the
+        platform cannot provide peer mappings.  Collective: every rank must call it."""
+        lib = nat.load()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ok = torch.zeros(1, dtype=torch.int32, device=self.device)
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nbytes = lib.rebert_exchange_buffer_bytes(world, self.K_MAX)
+            if nbytes == 0:
+                raise RuntimeError("world size not supported by the exchange kernel")
+            buf = symm.empty(nbytes // 8, dtype=torch.int64, device=self.device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            self._symm_buf, self._symm_hdl = buf, hdl
+            self._peer_ptrs = (C.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
+            self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._p2p_out = {}
+            self._p2p_world, self._p2p_rank = world, rank
+            ok.fill_(1)
+        except Exception as e:  # noqa: BLE001 - any failure of the plumbing means: keep NCCL
+            self._p2p_error = repr(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all or nothing, and a barrier after the zero-fill
+        torch.cuda.synchronize(self.device)
+        self.exchange = "p2p" if int(ok.item()) == 1 else "nccl"
+        return self.exchange == "p2p"
+
+    def exchange_merge(self, local: torch.Tensor, k: int) -> torch.Tensor:
+        """P2P exchange + merge of the packed local result (int64 [2k+2]) -> packed merged result."""
+        lib = nat.load()
+        out = self._p2p_out.get(k)
+        if out is None:
+            out = self._p2p_out[k] = torch.empty(2 * k + 2, dtype=torch.int64, device=self.device)
+        self._seq += 1
+        nat.check(lib.rebert_exchange_merge(self._peer_ptrs, self._p2p_world, self._p2p_rank, k, self.K_MAX,
+                                            self._seq & 0xFFFFFFFF or 1, local.data_ptr(), out.data_ptr(),
+                                            self._err.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return out
 
     def stage(self, query, liked_rows, weights, exclude_rows, k, kc):
         st = self.store
@@ -91,7 +135,10 @@ class CudaShardBackend:
         return out
 
     def fetch(self, packed: torch.Tensor, k: int):
-        return unpack_result(packed.cpu().numpy(), k)
+        res = unpack_result(packed.cpu().numpy(), k)
+        if self.exchange == "p2p" and int(self._err.item()) != 0:
+            raise RuntimeError(f"peer {int(self._err.item()) - 1} did not deliver its result to the exchange kernel")
+        return res
 
 
 class ShardedCatalog:
@@ -112,7 +159,9 @@ class ShardedCatalog:
         plan = ShardPlan(n_total, dist.get_world_size(group))
         row0, n = plan.range(dist.get_rank(group))
         store = CatalogStore.synthetic(seed, n, d, dtype, scale_rows=scale_rows, device=device, row0=row0)
-        return cls(CudaShardBackend(store), n_total, group)
+        backend = CudaShardBackend(store)
+        backend.setup_p2p(group)
+        return cls(backend, n_total, group)
 
     def _gather_buf(self, k: int, like: torch.Tensor) -> torch.Tensor:
         buf = self._gather.get(k)
@@ -123,6 +172,8 @@ class ShardedCatalog:
     def enqueue(self, k: int, kc: int, row_filter=None) -> torch.Tensor:
         """Device-resident step for an already staged query: local top-k -> all-gather -> merge (packed result)."""
         local = self.backend.local_topk(k, kc, row_filter)
+        if getattr(self.backend, "exchange", "nccl") == "p2p":
+            return self.backend.exchange_merge(local, k)             # one kernel: P2P stores + flags + merge
         buf = self._gather_buf(k, local)
         dist.all_gather_into_tensor(buf.view(-1), local, group=self.group)
         return self.backend.merge(buf, k)
