@@ -112,20 +112,32 @@ def ncu_traffic(key):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_leg(rows_full: int, steps: int, warmup: int, sample_rows: int):
-    """The reference's own CPU path (restated lib.py:51-55, L=1) on `sample_rows` rows; returns (q/s scaled to
-    rows_full, description, seconds per sample query, cores)."""
+def cpu_reference_leg(rows_full: int, steps: int, warmup: int, sample_rows: int, budget_s: float = 90.0):
+    """The reference's own CPU path (restated lib.py:51-55, L=1) on a bounded row sample; returns (q/s scaled to
+    rows_full, description, seconds per sample query, cores).  The sample is sized from a short calibration so that
+    the whole (warmup + steps) run stays near `budget_s` seconds whatever K the caller asks for."""
     from oracle import reference_scoring as ora
     from robot_ebert_b200 import synth
-    sample_rows = min(sample_rows, rows_full)
-    m = np.empty((sample_rows, DIM), dtype=np.float64)
-    for s in range(0, sample_rows, 8192):
-        e = min(sample_rows, s + 8192)
-        m[s:e] = synth.quantise(synth.catalog_rows_f32(0, s, e - s, DIM), DTYPE)
-    emb = ora.catalog_frame(synth.row_ids(sample_rows), m)              # float64 frame, string index (constants.py:56)
+
+    def build(nrows):
+        m = np.empty((nrows, DIM), dtype=np.float64)
+        for s in range(0, nrows, 8192):
+            e = min(nrows, s + 8192)
+            m[s:e] = synth.quantise(synth.catalog_rows_f32(0, s, e - s, DIM), DTYPE)
+        emb = ora.catalog_frame(synth.row_ids(nrows), m)               # float64 frame, string index (constants.py:56)
+        excl_rows = np.random.default_rng(1).choice(nrows, size=min(N_EXCL, nrows // 2), replace=False)
+        return emb, [emb.index[r] for r in excl_rows]
+
     q = synth.query_f32(1, DIM).astype(np.float64)
-    excl_rows = np.random.default_rng(1).choice(sample_rows, size=N_EXCL, replace=False)
-    excl_ids = [emb.index[r] for r in excl_rows]
+    cal_rows = min(8192, rows_full)
+    emb, excl_ids = build(cal_rows)
+    ora.single_query(emb, q, excl_ids, K)
+    t0 = time.perf_counter()
+    ora.single_query(emb, q, excl_ids, K)
+    per_row = (time.perf_counter() - t0) / cal_rows
+    fit = int(budget_s / max(1, steps + warmup) / per_row)
+    sample_rows = int(max(4096, min(sample_rows, rows_full, fit)))
+    emb, excl_ids = build(sample_rows)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
