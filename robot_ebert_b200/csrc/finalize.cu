@@ -14,13 +14,51 @@ __device__ __forceinline__ bool better(double sa, int64_t ra, double sb, int64_t
     return sa > sb || (sa == sb && ra < rb);
 }
 
+// 16-byte chunk of a stored row -> fp64 dot with the matching slice of the query.  The query sits in shared memory in
+// "pair planes": element e of chunk ch lives at ((e >> 1) * chunks + ch) * 2 + (e & 1), so the 32 lanes of a warp
+// (consecutive chunks) read consecutive 16-byte double2's — conflict-free LDS.128.
+__device__ __forceinline__ double2 q_pair(const double* sq, int chunks, int ch, int p) {
+    return *(const double2*)(sq + ((size_t)p * chunks + ch) * 2);
+}
+template <typename T> struct ChunkDot;
+template <> struct ChunkDot<float> {
+    static constexpr int EPC = 4;
+    __device__ static __forceinline__ double dot(const uint4& v, const double* sq, int chunks, int ch, double acc) {
+        const double2 q0 = q_pair(sq, chunks, ch, 0), q1 = q_pair(sq, chunks, ch, 1);
+        acc = fma(q0.x, (double)__uint_as_float(v.x), acc);
+        acc = fma(q0.y, (double)__uint_as_float(v.y), acc);
+        acc = fma(q1.x, (double)__uint_as_float(v.z), acc);
+        acc = fma(q1.y, (double)__uint_as_float(v.w), acc);
+        return acc;
+    }
+};
+template <> struct ChunkDot<__nv_bfloat16> {
+    static constexpr int EPC = 8;
+    __device__ static __forceinline__ double dot(const uint4& v, const double* sq, int chunks, int ch, double acc) {
+        const double2 q0 = q_pair(sq, chunks, ch, 0), q1 = q_pair(sq, chunks, ch, 1);
+        const double2 q2 = q_pair(sq, chunks, ch, 2), q3 = q_pair(sq, chunks, ch, 3);
+        acc = fma(q0.x, (double)bf16lo(v.x), acc);
+        acc = fma(q0.y, (double)bf16hi(v.x), acc);
+        acc = fma(q1.x, (double)bf16lo(v.y), acc);
+        acc = fma(q1.y, (double)bf16hi(v.y), acc);
+        acc = fma(q2.x, (double)bf16lo(v.z), acc);
+        acc = fma(q2.y, (double)bf16hi(v.z), acc);
+        acc = fma(q3.x, (double)bf16lo(v.w), acc);
+        acc = fma(q3.y, (double)bf16hi(v.w), acc);
+        return acc;
+    }
+};
+
 // grid = (b); one CTA per query.  cand_keys [b, kc], q64 [b, ld], outputs [b, k].
+// The fp64 query is staged in shared memory once; every warp re-scores candidates with 16-byte row loads.
 template <typename T>
 __global__ void __launch_bounds__(kFinalThreads, 1)
 finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t row_base, int ld,
                      const double* __restrict__ q64, const uint64_t* __restrict__ cand_keys, int kc, int k,
                      int64_t* __restrict__ out_rows, double* __restrict__ out_scores, int32_t* __restrict__ out_count,
                      double* __restrict__ out_margin) {
+    constexpr int EPC = ChunkDot<T>::EPC;
+    extern __shared__ __align__(16) double s_q[];   // [ld]
     __shared__ double s_score[kMaxKc];
     __shared__ int64_t s_row[kMaxKc];
     __shared__ int s_valid;
@@ -30,6 +68,11 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const uint64_t* keys = cand_keys + (size_t)u * kc;
     const double* q = q64 + (size_t)u * ld;
+    const int chunks = ld / EPC;
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        const int ch = i / EPC, e = i - ch * EPC;
+        s_q[((size_t)(e >> 1) * chunks + ch) * 2 + (e & 1)] = q[i];
+    }
     if (threadIdx.x == 0) { s_valid = 0; s_kth = 0.0; s_maxerr = 0ull; }
     __syncthreads();
 
@@ -39,11 +82,16 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
         int64_t gr = -1;
         if (key != 0) {
             const uint32_t lr = key_row(key);
-            const T* row = rows + (size_t)lr * ld;
-            double acc = 0.0;
-            for (int i = lane; i < ld; i += 32) acc = fma(q[i], elem_f64<T>(row, i), acc);
-            acc = warp_sum(acc);
-            sc = acc / norm64[lr];
+            const uint4* row = (const uint4*)(rows + (size_t)lr * ld);
+            double a0 = 0.0, a1 = 0.0;
+            int ch = lane;
+            for (; ch + 32 < chunks; ch += 64) {                 // two independent 16-byte loads in flight per lane
+                const uint4 v0 = __ldg(row + ch), v1 = __ldg(row + ch + 32);
+                a0 = ChunkDot<T>::dot(v0, s_q, chunks, ch, a0);
+                a1 = ChunkDot<T>::dot(v1, s_q, chunks, ch + 32, a1);
+            }
+            if (ch < chunks) a0 = ChunkDot<T>::dot(__ldg(row + ch), s_q, chunks, ch, a0);
+            sc = warp_sum(a0 + a1) / norm64[lr];
             gr = row_base + lr;
         }
         if (lane == 0) {
@@ -226,14 +274,19 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(PeerBufs peers, int
 
 int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
                     int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st) {
-    if (cat->dtype == REBERT_F32)
-        finalize_topk_kernel<float><<<b, kFinalThreads, 0, st>>>((const float*)cat->rows, cat->norm64, cat->row_base, cat->ld,
-                                                                  q64, cand_keys, kc, k, out_rows, out_scores, out_count,
-                                                                  out_margin);
-    else
-        finalize_topk_kernel<__nv_bfloat16><<<b, kFinalThreads, 0, st>>>((const __nv_bfloat16*)cat->rows, cat->norm64,
-                                                                          cat->row_base, cat->ld, q64, cand_keys, kc, k,
-                                                                          out_rows, out_scores, out_count, out_margin);
+    const size_t smem = (size_t)cat->ld * sizeof(double);
+    const int threads = kFinalThreads;      // one candidate per warp at kc = 32: the DRAM latencies of the row reads overlap
+    if (cat->dtype == REBERT_F32) {
+        auto kern = finalize_topk_kernel<float>;
+        { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
+        kern<<<b, threads, smem, st>>>((const float*)cat->rows, cat->norm64, cat->row_base, cat->ld, q64, cand_keys, kc, k, out_rows,
+                                       out_scores, out_count, out_margin);
+    } else {
+        auto kern = finalize_topk_kernel<__nv_bfloat16>;
+        { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
+        kern<<<b, threads, smem, st>>>((const __nv_bfloat16*)cat->rows, cat->norm64, cat->row_base, cat->ld, q64, cand_keys, kc, k,
+                                       out_rows, out_scores, out_count, out_margin);
+    }
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }

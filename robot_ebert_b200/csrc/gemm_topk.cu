@@ -529,6 +529,51 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(float* sample, in
         const int64_t j = (tile / tile_stride) * BN + row % BN;
         if (j < s_cols) keys[j] = 0u;
     }
+    // ---- fast path: prune with the rank-th largest of the per-thread maxima (a lower bound of the answer, because
+    // `rank` distinct keys are >= it), gather the handful of keys above it, rank-count exactly.  No histogram atomics.
+    __shared__ uint32_t s_max[256];
+    __shared__ uint32_t s_buf[1024];
+    __shared__ uint32_t s_low, s_ans;
+    __shared__ int s_n, s_found;
+    {
+        uint32_t mx = 0;
+        for (int64_t j = threadIdx.x; j < s_cols; j += blockDim.x) mx = max(mx, keys[j]);
+        s_max[threadIdx.x] = mx;
+        if (threadIdx.x == 0) { s_low = 0; s_n = 0; s_found = 0; s_ans = 0; }
+        __syncthreads();
+        if (rank <= (int)blockDim.x) {
+            int c = 0;
+            for (int t = 0; t < (int)blockDim.x; ++t) c += (s_max[t] > mx) || (s_max[t] == mx && t < (int)threadIdx.x);
+            if (c == rank - 1) s_low = mx;                      // exactly one thread has this position
+        }
+        __syncthreads();
+        const uint32_t low = s_low;
+        if (low != 0) {
+            for (int64_t j = threadIdx.x; j < s_cols; j += blockDim.x) {
+                const uint32_t kk = keys[j];
+                if (kk >= low) {
+                    const int idx = atomicAdd(&s_n, 1);
+                    if (idx < 1024) s_buf[idx] = kk;
+                }
+            }
+        }
+        __syncthreads();
+        const int nb = s_n;
+        if (low != 0 && nb >= rank && nb <= 1024) {
+            for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+                const uint32_t kk = s_buf[t];
+                int c = 0;
+                for (int i = 0; i < nb; ++i) c += (s_buf[i] > kk) || (s_buf[i] == kk && i < t);
+                if (c == rank - 1) { s_ans = kk; s_found = 1; }
+            }
+        }
+        __syncthreads();
+        if (s_found) {
+            if (threadIdx.x == 0) tau[q] = orderable_f32(s_ans);
+            return;
+        }
+    }
+    // ---- general path (tiny samples, mass ties): 4-pass radix select
     if (threadIdx.x == 0) { s_prefix = 0; s_rank = (unsigned)rank; }
     __syncthreads();
     for (int pass = 3; pass >= 0; --pass) {
