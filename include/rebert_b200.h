@@ -181,6 +181,14 @@ REBERT_API int rebert_exchange_merge(const uint64_t* peer_buffers, int32_t world
 REBERT_API int rebert_score_subset(const rebert_catalog_t* cat, const double* p64, int32_t b, const int32_t* sub_rows, int32_t m,
                         double* out /* [b, m] */, rebert_stream stream);
 
+/* ---- exact fallback for unprovable results (mass ties in fp64 that fp32 rounding breaks) ---- */
+/* Appends (unordered) the GLOBAL row id of every allowed row whose fast score <qn32,row>*inv_norm >= threshold to
+ * out_rows[cap]; *out_count (device int32) receives the number found (may exceed cap: then only cap were stored).
+ * With threshold = (exact k-th score so far) - 2 eps this set provably contains the true top-k; the caller re-scores
+ * it in fp64 with rebert_score_subset and orders it.  A plain one-warp-per-row kernel: correctness path, not the hot path. */
+REBERT_API int rebert_collect_above(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, float threshold,
+                                    int32_t* out_rows, int32_t cap, int32_t* out_count, rebert_stream stream);
+
 /* ---- dense scores (test / diagnostics: the materialised matrix of lib.py:51) --------------- */
 /* out[u, r] = <q32[u], row r> * inv_norm[r], fp32, plain CUDA-core kernel independent of the fused paths. */
 REBERT_API int rebert_scores_dense(const rebert_catalog_t* cat, const float* q32, int32_t b, float* out /* [b, n] */,

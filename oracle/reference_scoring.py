@@ -146,10 +146,15 @@ def topk_rows(scores: np.ndarray, k: int, exclude_rows: Optional[np.ndarray] = N
 
 
 def recommend_rows(matrix: np.ndarray, liked_rows: np.ndarray, exclude_rows: Optional[np.ndarray], k: int,
-                   keep_mask: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
-    """Row-index form of user_recs_ranked."""
+                   keep_mask: Optional[np.ndarray] = None, weights: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """Row-index form of user_recs_ranked.  `weights` generalises lib.py:52's unweighted mean to
+    sum_i w_i cos_i / sum_i w_i (the reference is w = 1[rating >= 3.5])."""
     lhs = np.asarray(matrix[np.asarray(liked_rows, dtype=np.int64)], dtype=np.float64)
-    return topk_rows(scores_rows(matrix, lhs), k, exclude_rows, keep_mask)
+    if weights is None:
+        return topk_rows(scores_rows(matrix, lhs), k, exclude_rows, keep_mask)
+    w = np.asarray(weights, dtype=np.float64)
+    sims = _normalize_rows(lhs) @ _normalize_rows(matrix).T
+    return topk_rows((w[:, None] * sims).sum(axis=0) / w.sum(), k, exclude_rows, keep_mask)
 
 
 def query_rows(matrix: np.ndarray, query: np.ndarray, exclude_rows: Optional[np.ndarray], k: int,

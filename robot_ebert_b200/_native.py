@@ -58,6 +58,7 @@ _SIGS = {
     "rebert_exchange_buffer_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rebert_exchange_merge": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P]),
     "rebert_score_subset": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "rebert_collect_above": (C.c_int, [C.POINTER(Catalog), _P, C.POINTER(Filter), C.c_float, _P, C.c_int32, _P, _P]),
     "rebert_scores_dense": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, _P]),
     "rebert_gemm_plan": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(GemmPlan)]),
     "rebert_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(Catalog), C.POINTER(GemmPlan)]),

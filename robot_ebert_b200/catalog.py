@@ -248,11 +248,48 @@ class CatalogStore:
                 break
             kc = min(256, kc * 4)                       # candidate set not provably exact: widen and redo
         proven = margin > self.fast_eps
+        swept = False
+        if not proven and len(rows) == k:
+            # Mass ties: more rows than any candidate list holds sit within fp32 noise of the k-th score.  Sweep for every
+            # allowed row that could still belong to the top-k, re-score those in fp64, order them: provably exact.
+            res = self._exact_sweep(lib, query, liked_rows, weights, exclude_rows, k, row_filter, float(scores[k - 1]))
+            if res is not None:
+                rows, scores = res
+                proven = swept = True
         if not proven:
             warnings.warn(f"top-{k}: fp32 candidate margin {margin:.3e} <= {self.fast_eps:.3e}; ids may differ from fp64 order")
         if return_info:
-            return rows, scores, {"kc": kc, "margin": margin, "proven_exact": proven}
+            return rows, scores, {"kc": kc, "margin": margin, "proven_exact": proven, "exact_sweep": swept}
         return rows, scores
+
+    SWEEP_CAP = 1 << 16
+
+    def _exact_sweep(self, lib, query, liked_rows, weights, exclude_rows, k, row_filter, kth_score):
+        """Fallback for results no candidate list can prove: collect every allowed row with fast score >= k-th exact
+        score - 2 eps (a superset of the true top-k), fp64 re-score them, order by (score desc, row asc)."""
+        s = self._scratch()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream()
+            kc = lib.rebert_candidates_for_k(k)
+            excl_ptr, ne = self.stage_inputs(query, liked_rows, weights, exclude_rows, k, kc)   # refreshes qn32 / qn64
+            f = self._filter_struct(row_filter) or nat.Filter()
+            if ne:
+                f.exclude_rows, f.n_exclude = excl_ptr, ne
+            out_rows = torch.empty(self.SWEEP_CAP, dtype=torch.int32, device=self.device)
+            out_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+            thr = kth_score - 2.0 * self.fast_eps
+            nat.check(lib.rebert_collect_above(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), C.c_float(thr), out_rows.data_ptr(),
+                                               self.SWEEP_CAP, out_count.data_ptr(), stream.cuda_stream))
+            cnt = int(out_count.item())
+            if cnt < k or cnt > self.SWEEP_CAP:
+                return None
+            sub = out_rows[:cnt].contiguous()
+            exact = torch.empty((1, cnt), dtype=torch.float64, device=self.device)
+            nat.check(lib.rebert_score_subset(C.byref(self._c), s.qn64.data_ptr(), 1, sub.data_ptr(), cnt, exact.data_ptr(),
+                                              stream.cuda_stream))
+            rr, sc = sub.cpu().numpy().astype(np.int64), exact[0].cpu().numpy()
+        order = np.lexsort((rr, -sc))[:k]            # bookkeeping on the handful of survivors
+        return rr[order], sc[order]
 
     def _recommend_once(self, lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter):
         """One rebert_recommend_host call: host buffers in, host buffers out, copies + kernels + sync inside."""

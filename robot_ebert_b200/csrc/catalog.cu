@@ -278,6 +278,27 @@ __global__ void scores_dense_kernel(const T* __restrict__ rows, const float* __r
     }
 }
 
+// Exact-fallback sweep: every allowed row whose fast fp32 score reaches `threshold` is appended (unordered) to out_rows.
+// Only used when a candidate list could not prove the result (mass ties in fp64 that fp32 rounding breaks).
+template <typename T>
+__global__ void collect_above_kernel(const T* __restrict__ rows, const float* __restrict__ inv_norm, int64_t n, int ld,
+                                     const float* __restrict__ q32, DevFilter filter, float threshold,
+                                     int32_t* __restrict__ out_rows, int cap, int32_t* __restrict__ out_count) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const T* row = rows + r * ld;
+        float acc = 0.0f;
+        for (int c = lane; c < ld; c += 32) acc = fmaf(q32[c], (float)elem_f64<T>(row, c), acc);
+        acc = warp_sum(acc) * inv_norm[r];
+        if (lane == 0 && acc >= threshold && row_allowed(filter, (uint32_t)r)) {
+            const int idx = atomicAdd(out_count, 1);
+            if (idx < cap) out_rows[idx] = (int32_t)(filter.row_base + r);
+        }
+    }
+}
+
 static int grid_for(int64_t work_items, int block) {
     int64_t g = (work_items + block - 1) / block;
     int64_t cap = (int64_t)num_sms() * 16;
@@ -401,6 +422,24 @@ REBERT_API int rebert_scores_dense(const rebert_catalog_t* cat, const float* q32
     else
         scores_dense_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)cat->rows, cat->inv_norm, cat->n, cat->ld,
                                                               q32, b, out);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_collect_above(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, float threshold,
+                                    int32_t* out_rows, int32_t cap, int32_t* out_count, rebert_stream stream) {
+    REBERT_REQUIRE(cat && cat->rows && cat->inv_norm && qn32 && out_rows && out_count && cap > 0, "collect_above: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    REBERT_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t), st));
+    if (cat->n == 0) return REBERT_OK;
+    DevFilter f = make_filter(filter, cat->row_base);
+    int g = grid_for(cat->n * 32, 256);
+    if (cat->dtype == REBERT_F32)
+        collect_above_kernel<float><<<g, 256, 0, st>>>((const float*)cat->rows, cat->inv_norm, cat->n, cat->ld, qn32, f, threshold,
+                                                       out_rows, cap, out_count);
+    else
+        collect_above_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)cat->rows, cat->inv_norm, cat->n, cat->ld, qn32,
+                                                               f, threshold, out_rows, cap, out_count);
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }

@@ -208,3 +208,23 @@ def test_concurrent_requests_from_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n,d,k", [(624, 1, 1), (3000, 1, 10), (5000, 2, 25)])
+def test_mass_ties_are_resolved_by_the_exact_sweep(n, d, k):
+    """Hundreds of rows tie EXACTLY in float64 (d = 1: every cosine is +-1; d = 2: rows on a few rays) but not in fp32.
+    No candidate list can prove that; the exact sweep must, and the row-ascending tie-break must hold."""
+    m = synth.catalog_rows_f32(0, 0, n, d, scale_rows=True)
+    if d == 2:
+        rays = np.array([[1.0, 1.0], [1.0, -1.0], [-1.0, 1.0], [3.0, 1.0]], dtype=np.float32)
+        scale = np.exp2(np.random.default_rng(0).integers(-8, 8, size=n)).astype(np.float32)
+        m = rays[np.arange(n) % 4] * scale[:, None]
+    store = CatalogStore.from_host(synth.row_ids(n), m, "fp32")
+    q = np.ones(d, dtype=np.float32)
+    excl = np.arange(0, n, 7)
+    with np.errstate(all="ignore"):
+        rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True)
+    want_rows, want_scores = ora.query_rows(m.astype(np.float64), q.astype(np.float64), excl, k)
+    assert info["proven_exact"]
+    np.testing.assert_array_equal(rows, want_rows)
+    np.testing.assert_allclose(scores, want_scores, rtol=1e-12)
