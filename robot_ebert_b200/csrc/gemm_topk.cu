@@ -71,11 +71,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
