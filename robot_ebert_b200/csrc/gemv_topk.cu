@@ -11,6 +11,8 @@
 //   * at the end the 8 warp lists are rank-merged through shared memory into one sorted list per CTA, and the last
 //     CTA to finish (atomic ticket) merges the per-CTA lists behind two pruning thresholds — one launch per query.
 //     The N-long score vector never exists.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rebert {
@@ -18,7 +20,7 @@ namespace rebert {
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kStageBytes = 48 * 1024;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kMaxExclSmem = 4096;   // exclusion rows staged in shared memory (larger lists are searched in global memory)
 
 struct GemvParams {
@@ -32,6 +34,7 @@ struct GemvParams {
     int          tile_rows;
     int          stages;
     int          kc;
+    int          l2_policy; // 0 = evict_first (default), 1 = evict_normal, 2 = evict_last  (tuning knob)
     DevFilter    filter;
     uint64_t*    cta_lists; // [grid, kc]
     uint64_t*    cand_keys; // [kc] final output
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     if (warp == kConsumerWarps) {
         // ===================== producer warp: one elected lane issues the bulk copies =====================
         if (lane == 0) {
-            const uint64_t policy = l2_policy_evict_first();
+            const uint64_t policy = p.l2_policy == 0 ? l2_policy_evict_first() : (p.l2_policy == 2 ? l2_policy_evict_last() : l2_policy_evict_normal());
             int it = 0;
             for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
                 const int s = it % p.stages;
@@ -398,7 +401,9 @@ static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic,
     GemvLaunch g;
     const int row_bytes = L.ld * L.esize;
     const int rpw = 32 / L.lanes;
-    int tr = kStageBytes / row_bytes;
+    int stage_bytes = kStageBytes;
+    if (const char* e = getenv("REBERT_GEMV_STAGE_BYTES")) { int v = atoi(e); if (v >= 4096 && v <= 96 * 1024) stage_bytes = v; }   // tools/tune_gemv.py
+    int tr = stage_bytes / row_bytes;
     const int unit = kConsumerWarps * rpw;           // rows one step of all warps covers
     if (tr >= 2 * unit) tr = (tr / (2 * unit)) * (2 * unit);
     else if (tr >= unit) tr = unit;
@@ -412,7 +417,8 @@ static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic,
     const int stage_stride = tile_bytes + ((tr * 4 + 127) & ~127);
     const size_t excl_bytes = (n_exclude > 0 && n_exclude <= kMaxExclSmem) ? (size_t)n_exclude * 4 : 0;
     const size_t fixed = 2 * kMaxStages * sizeof(uint64_t) + (generic ? (size_t)L.ld * 4 : 0) + excl_bytes + 128;
-    int stages = kMaxStages;
+    int stages = 4;
+    if (const char* e = getenv("REBERT_GEMV_STAGES")) { int v = atoi(e); if (v >= 1 && v <= kMaxStages) stages = v; }                  // tools/tune_gemv.py
     while (stages > 1 && (size_t)stages * stage_stride + fixed > 220 * 1024) --stages;
     g.stages = stages;
     g.smem = (size_t)stages * stage_stride + fixed;
@@ -536,6 +542,8 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.num_tiles = (cat->n + g.tile_rows - 1) / g.tile_rows;
     p.stages = g.stages;
     p.kc = kc;
+    p.l2_policy = 0;
+    if (const char* e = getenv("REBERT_GEMV_L2_POLICY")) p.l2_policy = atoi(e);                                                       // tools/tune_gemv.py
     p.filter = make_filter(filter, cat->row_base);
     p.cta_lists = (uint64_t*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
     p.counter = (unsigned*)(p.cta_lists + (size_t)num_sms() * kc);
