@@ -208,11 +208,15 @@ REBERT_API size_t rebert_gemm_workspace_bytes(const rebert_catalog_t* cat, const
 /* Whole batched path: sample -> per-query threshold -> full GEMM with fused scale + threshold filter -> per-query
  * select -> fp64 re-score -> ordered top-k.  qbf16 [b, ld] bf16 (fast pass), q64 [b, ld] (exact pass).
  * excl_row_ptr / excl_col: per-query CSR of excluded GLOBAL rows, sorted within a query (may be NULL).
+ * row_filter: optional per-ROW predicate shared by the whole batch (exclude_bitmap / genre_bits+genre_any / year range;
+ * its exclude_rows member is ignored — per-query exclusions are the CSR).  Filtered rows are dropped inside the GEMM
+ * epilogue at no extra cost and are left out of the threshold sample.
  * out_rows / out_scores are [b, k]; out_count[b]; out_status[b] is 0 when the query's result is proven exact and
  * non-zero when the caller must re-run that query through the single-query path (threshold sample too optimistic,
  * candidate buffer overflow, or margin below eps). */
 REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, const double* q64, const int64_t* excl_row_ptr,
-                     const int32_t* excl_col, const rebert_gemm_plan_t* plan, void* workspace, size_t workspace_bytes,
+                     const int32_t* excl_col, const rebert_filter_t* row_filter, const rebert_gemm_plan_t* plan, void* workspace,
+                     size_t workspace_bytes,
                      int64_t* out_rows, double* out_scores, int32_t* out_count, int32_t* out_status,
                      rebert_stream stream);
 /* Building block, also used by tests: out[u, j] = <q[u], row j> * inv_norm[j] for rows [row0, row0 + nrows) on the

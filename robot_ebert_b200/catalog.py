@@ -451,18 +451,22 @@ class CatalogStore:
         nat.check(lib.rebert_gemm_plan(self.n, b, k, C.byref(plan)))
         return plan
 
-    def enqueue_batch(self, plan, qbf16, q64, excl_ptr, excl_col, ws, out_rows, out_scores, out_count, out_status):
+    def enqueue_batch(self, plan, qbf16, q64, excl_ptr, excl_col, ws, out_rows, out_scores, out_count, out_status,
+                      row_filter: Optional[RowFilter] = None):
         """Device-resident batched step (sample -> thresholds -> filtered GEMM -> select -> exact pass)."""
         lib = nat.load()
+        f = self._filter_struct(row_filter)
         nat.check(lib.rebert_gemm_topk(C.byref(self._c), qbf16.data_ptr(), q64.data_ptr(), _ptr(excl_ptr), _ptr(excl_col),
+                                       None if f is None else C.byref(f),
                                        C.byref(plan), ws.data_ptr(), ws.numel(), out_rows.data_ptr(), out_scores.data_ptr(),
                                        out_count.data_ptr(), out_status.data_ptr(), torch.cuda.current_stream().cuda_stream))
 
     def recommend_batch(self, *, queries: Optional[np.ndarray] = None, liked_ptr: Optional[np.ndarray] = None,
                         liked_col: Optional[np.ndarray] = None, liked_w: Optional[np.ndarray] = None,
                         excl_ptr: Optional[np.ndarray] = None, excl_col: Optional[np.ndarray] = None, k: int = 10,
-                        return_info: bool = False):
+                        row_filter: Optional[RowFilter] = None, return_info: bool = False):
         """Top-k for many users at once (lib.py:51-55 per user) on the tcgen05 path.
+        row_filter: optional per-row predicate (genre / year / bitmap) shared by the whole batch.
 
         queries [b, d] fp32, OR a ragged CSR of liked rows (liked_ptr[b+1], liked_col, optional weights).
         excl_ptr/excl_col: per-user CSR of GLOBAL rows that must not be returned (sorted within a user).
@@ -489,7 +493,7 @@ class CatalogStore:
                     raise
                 plan = None          # catalog too small for the sampled-threshold scheme: one fused GEMV per user instead
             if plan is None or self.dtype != "bf16":
-                return self._recommend_batch_loop(qn32, qn64, excl_ptr, excl_col, k, return_info)
+                return self._recommend_batch_loop(qn32, qn64, excl_ptr, excl_col, k, return_info, row_filter)
             ep = ec = None
             if excl_ptr is not None:
                 ep = torch.from_numpy(np.asarray(excl_ptr, dtype=np.int64)).to(dev)
@@ -499,7 +503,7 @@ class CatalogStore:
             out_scores = torch.empty((b, k), dtype=torch.float64, device=dev)
             out_count = torch.empty(b, dtype=torch.int32, device=dev)
             out_status = torch.empty(b, dtype=torch.int32, device=dev)
-            self.enqueue_batch(plan, qbf, qn64, ep, ec, ws, out_rows, out_scores, out_count, out_status)
+            self.enqueue_batch(plan, qbf, qn64, ep, ec, ws, out_rows, out_scores, out_count, out_status, row_filter)
             rows, scores = out_rows.cpu().numpy(), out_scores.cpu().numpy()
             counts, status = out_count.cpu().numpy(), out_status.cpu().numpy()
             redo = np.nonzero(status)[0]
@@ -514,7 +518,7 @@ class CatalogStore:
                     ptr, ne = None, 0
                     if ecp is not None and ecp[u + 1] > ecp[u]:
                         ptr, ne = ec.data_ptr() + 4 * int(ecp[u]), int(ecp[u + 1] - ecp[u])
-                    self.enqueue_topk(k, kc, ptr, ne)
+                    self.enqueue_topk(k, kc, ptr, ne, row_filter)
                     r, sc, _ = unpack_result(s.d_out.cpu().numpy(), k)
                     rows[u, :], scores[u, :] = -1, -np.inf
                     rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
@@ -522,7 +526,7 @@ class CatalogStore:
             return rows, scores, counts, {"status": status, "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
         return rows, scores, counts
 
-    def _recommend_batch_loop(self, qn32, qn64, excl_ptr, excl_col, k, return_info):
+    def _recommend_batch_loop(self, qn32, qn64, excl_ptr, excl_col, k, return_info, row_filter=None):
         """Small or fp32 catalogs: the batch is served by the single-query kernel, one launch per prepared query."""
         lib = nat.load()
         b = qn32.shape[0]
@@ -542,7 +546,7 @@ class CatalogStore:
             ptr, ne = None, 0
             if ecp is not None and ecp[u + 1] > ecp[u]:
                 ptr, ne = ec.data_ptr() + 4 * int(ecp[u]), int(ecp[u + 1] - ecp[u])
-            self.enqueue_topk(k, kc, ptr, ne)
+            self.enqueue_topk(k, kc, ptr, ne, row_filter)
             r, sc, _ = unpack_result(s.d_out.cpu().numpy(), k)
             rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
         if return_info:

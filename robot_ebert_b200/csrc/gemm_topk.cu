@@ -53,6 +53,8 @@ struct GemmParams {
     int64_t n;              // shard rows
     int kblocks;            // ld / 64
     const float* inv_norm;
+    DevFilter pred;         // per-row predicate (bitmap / genre / year); n_exclude is always 0 here
+    int has_pred;
     // MODE_STORE
     float* out;             // [b, out_ld], column = launch tile index * 256 + c
     int64_t out_ld;
@@ -281,7 +283,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             float* inv = s_inv + (tile_i & 1) * BN;
             for (int c = et; c < BN; c += 128) {
                 const int64_t r = row0 + c;
-                inv[c] = r < p.n ? __ldg(p.inv_norm + r) : __int_as_float(0x7FC00000);
+                // rows beyond the shard, and rows the batch predicate filters out, get NaN: they can never pass tau
+                inv[c] = (r < p.n && (!p.has_pred || row_allowed(p.pred, (uint32_t)r))) ? __ldg(p.inv_norm + r) : __int_as_float(0x7FC00000);
             }
             float tau = INFINITY;
             if (MODE == MODE_FILTER && q < p.b) tau = __ldg(p.tau + q);
@@ -460,7 +463,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             float* inv = s_inv + (tile_i & 1) * BN;
             for (int c = et; c < BN; c += 128) {
                 const int64_t r = row0 + c;
-                inv[c] = r < p.n ? __ldg(p.inv_norm + r) : __int_as_float(0x7FC00000);
+                // rows beyond the shard, and rows the batch predicate filters out, get NaN: they can never pass tau
+                inv[c] = (r < p.n && (!p.has_pred || row_allowed(p.pred, (uint32_t)r))) ? __ldg(p.inv_norm + r) : __int_as_float(0x7FC00000);
             }
             float tau = INFINITY;
             if (MODE == MODE_FILTER && q < p.b) tau = __ldg(p.tau + q);
@@ -498,6 +502,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) select_threshold_kernel(float* sample, int keys_in_smem, int64_t s_cols, int64_t n,
                                                                int64_t row_base, int64_t tile0, int64_t tile_stride, int rank,
+                                                               DevFilter pred, int has_pred,
                                                                const int64_t* __restrict__ excl_ptr,
                                                                const int32_t* __restrict__ excl_col, float* __restrict__ tau) {
     extern __shared__ uint32_t smem_keys[];        // [s_cols] when it fits, else the sample row is rewritten in place
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(float* sample, in
     for (int64_t j = threadIdx.x; j < s_cols; j += blockDim.x) {
         const int64_t row = (tile0 + (j / BN) * tile_stride) * BN + (j % BN);
         const float v = src[j];
-        keys[j] = (row < n && v == v) ? f32_orderable(v) : 0u;
+        keys[j] = (row < n && v == v && (!has_pred || row_allowed(pred, (uint32_t)row))) ? f32_orderable(v) : 0u;
     }
     __syncthreads();
     // knock out excluded rows that fall inside the sample: ~|excluded| scattered stores instead of a search per key
@@ -680,6 +685,14 @@ static int check_gemm_catalog(const rebert_catalog_t* cat, const char* who) {
     return REBERT_OK;
 }
 
+static void set_pred(GemmParams& p, const rebert_catalog_t* cat, const rebert_filter_t* filter) {
+    rebert_filter_t f;
+    memset(&f, 0, sizeof(f));
+    if (filter) { f = *filter; f.exclude_rows = nullptr; f.n_exclude = 0; }       // per-query exclusions travel as CSR
+    p.pred = make_filter(&f, cat->row_base);
+    p.has_pred = (f.exclude_bitmap || f.genre_bits || f.year) ? 1 : 0;
+}
+
 template <int MODE>
 static int launch_gemm(const rebert_catalog_t* cat, const void* qbf16, GemmParams& p, cudaStream_t st) {
     const bool pair = p.b > BM && getenv("REBERT_GEMM_1CTA") == nullptr;   // cta_group::2 needs >= 2 query tiles to pay off
@@ -796,11 +809,13 @@ REBERT_API int rebert_gemm_scores(const rebert_catalog_t* cat, const void* qbf16
     p.tile_stride = 1;
     p.out = out;
     p.out_ld = nrows;
+    set_pred(p, cat, nullptr);
     return launch_gemm<MODE_STORE>(cat, qbf16, p, (cudaStream_t)stream);
 }
 
 REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, const double* q64, const int64_t* excl_row_ptr,
-                                const int32_t* excl_col, const rebert_gemm_plan_t* plan, void* workspace, size_t workspace_bytes,
+                                const int32_t* excl_col, const rebert_filter_t* row_filter, const rebert_gemm_plan_t* plan,
+                                void* workspace, size_t workspace_bytes,
                                 int64_t* out_rows, double* out_scores, int32_t* out_count, int32_t* out_status,
                                 rebert_stream stream) {
     int rc = check_gemm_catalog(cat, "gemm_topk");
@@ -828,14 +843,18 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     p.tile_stride = stride;
     p.out = w.sample;
     p.out_ld = plan->sample_rows;
+    set_pred(p, cat, nullptr);                   // the sample keeps every row; the predicate is applied by the selector
     rc = launch_gemm<MODE_STORE>(cat, qbf16, p, st);
     if (rc != REBERT_OK) return rc;
     // 2. thresholds
     const int keys_in_smem = plan->sample_rows <= 48 * 1024;
     const size_t tsmem = keys_in_smem ? (size_t)plan->sample_rows * 4 : 16;
     { int rc__ = raise_smem_limit(select_threshold_kernel); if (rc__ != REBERT_OK) return rc__; }
+    GemmParams pf;
+    memset(&pf, 0, sizeof(pf));
+    set_pred(pf, cat, row_filter);
     select_threshold_kernel<<<b, 256, tsmem, st>>>(w.sample, keys_in_smem, plan->sample_rows, cat->n, cat->row_base, 0, stride,
-                                                   plan->sample_rank, excl_row_ptr, excl_col, w.tau);
+                                                   plan->sample_rank, pf.pred, pf.has_pred, excl_row_ptr, excl_col, w.tau);
     REBERT_CUDA(cudaGetLastError());
     // 3. full pass with fused filter
     memset(&p, 0, sizeof(p));
@@ -848,6 +867,7 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     p.cand_count = w.cand_count;
     p.cand_cap = plan->cand_cap;
     p.status = out_status;
+    set_pred(p, cat, row_filter);
     rc = launch_gemm<MODE_FILTER>(cat, qbf16, p, st);
     if (rc != REBERT_OK) return rc;
     // 4. per-query candidate selection

@@ -202,7 +202,7 @@ class ShardedCatalog:
         return rows, scores
 
     # ------------------------------------------------------------------ batched (tensor-core) path ----------
-    def batch_context(self, qbf: torch.Tensor, qn64: torch.Tensor, k: int, excl_ptr=None, excl_col=None):
+    def batch_context(self, qbf: torch.Tensor, qn64: torch.Tensor, k: int, excl_ptr=None, excl_col=None, row_filter=None):
         """Allocate everything a batched step needs (device tensors only) for prepared queries [b, ld]."""
         import ctypes as C
         store: CatalogStore = self.backend.store
@@ -216,7 +216,7 @@ class ShardedCatalog:
             ec = torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(dev)
         hb = (b + 1) // 2
         words = 2 * b * k + 2 * hb                                       # rows | scores | counts | status
-        ctx = {"b": b, "k": k, "plan": plan, "qbf": qbf, "qn64": qn64, "ep": ep, "ec": ec, "hb": hb, "words": words,
+        ctx = {"b": b, "k": k, "plan": plan, "row_filter": row_filter, "qbf": qbf, "qn64": qn64, "ep": ep, "ec": ec, "hb": hb, "words": words,
                "ws": torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan)), dtype=torch.uint8, device=dev),
                "local": torch.empty(words, dtype=torch.int64, device=dev),
                "gathered": torch.empty((self.world, words), dtype=torch.int64, device=dev),
@@ -233,7 +233,8 @@ class ShardedCatalog:
         o_rows, o_scores = local[:b * k], local[b * k:2 * b * k].view(torch.float64)
         o_count = local[2 * b * k:2 * b * k + hb].view(torch.int32)
         o_status = local[2 * b * k + hb:].view(torch.int32)
-        store.enqueue_batch(ctx["plan"], ctx["qbf"], ctx["qn64"], ctx["ep"], ctx["ec"], ctx["ws"], o_rows, o_scores, o_count, o_status)
+        store.enqueue_batch(ctx["plan"], ctx["qbf"], ctx["qn64"], ctx["ep"], ctx["ec"], ctx["ws"], o_rows, o_scores, o_count, o_status,
+                            ctx.get("row_filter"))
         dist.all_gather_into_tensor(ctx["gathered"].view(-1), local, group=self.group)
         base = ctx["gathered"].data_ptr()
         nat.check(lib.rebert_merge_topk(base, base + 8 * b * k, base + 16 * b * k, words, words, 2 * words, self.world, b, k,
@@ -241,7 +242,7 @@ class ShardedCatalog:
                                         torch.cuda.current_stream().cuda_stream))
 
     def recommend_batch(self, *, queries=None, liked_ptr=None, liked_col=None, liked_w=None, excl_ptr=None, excl_col=None,
-                        k: int = 10, return_info: bool = False):
+                        k: int = 10, row_filter=None, return_info: bool = False):
         """Sharded form of CatalogStore.recommend_batch: every rank runs the tcgen05 pass over its rows, the per-rank
         [b, k] results are all-gathered in ONE packed buffer and merged on every rank.  CUDA backend only."""
         store: CatalogStore = self.backend.store
@@ -257,7 +258,7 @@ class ShardedCatalog:
                     raise ValueError("Found array with 0 sample(s): a user has no liked movies in the catalog")
                 qn32, qn64, qbf = store.build_profiles(
                     lp, liked_col, liked_w, reduce_fn=lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group))
-            ctx = self.batch_context(qbf, qn64, k, excl_ptr, excl_col)
+            ctx = self.batch_context(qbf, qn64, k, excl_ptr, excl_col, row_filter)
             self.batch_step(ctx)
             b, hb = ctx["b"], ctx["hb"]
             status = ctx["gathered"][:, 2 * b * k + hb:].contiguous().view(torch.int32)[:, :b].max(dim=0).values   # any rank unsure
@@ -268,11 +269,12 @@ class ShardedCatalog:
         for u in np.nonzero(status)[0]:                                  # identical on every rank -> collectives stay aligned
             ex = None if ecp is None else eca[ecp[u]:ecp[u + 1]]
             if queries is not None:
-                r, sc = self.recommend(query=np.asarray(queries[u]), exclude_rows=ex, k=k)
+                r, sc = self.recommend(query=np.asarray(queries[u]), exclude_rows=ex, k=k, row_filter=row_filter)
             else:
                 lpn = np.asarray(liked_ptr, dtype=np.int64)
                 lw = None if liked_w is None else np.asarray(liked_w)[lpn[u]:lpn[u + 1]]
-                r, sc = self.recommend(liked_rows=np.asarray(liked_col)[lpn[u]:lpn[u + 1]], weights=lw, exclude_rows=ex, k=k)
+                r, sc = self.recommend(liked_rows=np.asarray(liked_col)[lpn[u]:lpn[u + 1]], weights=lw, exclude_rows=ex, k=k,
+                                       row_filter=row_filter)
             rows[u, :], scores[u, :] = -1, -np.inf
             rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
         if return_info:

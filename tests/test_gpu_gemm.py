@@ -69,6 +69,33 @@ def test_recommend_batch_queries_vs_oracle(n, d, b, k):
         np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
 
 
+@pytest.mark.parametrize("sel", ["wide", "narrow"])
+def test_recommend_batch_with_genre_year_predicate(sel):
+    """BASELINE config 5 at test size: CSR profiles + per-user exclusions + a genre/year predicate, top-50."""
+    from robot_ebert_b200 import RowFilter
+    n, d, b, k = 120_000, 256, 96, 50
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    g, y = synth.movie_metadata(3, 0, n)
+    store.set_metadata(g, y)
+    want_g, y0, y1 = (0b1011, 1960, 2000) if sel == "wide" else (0b1, 1990, 1999)
+    keep = ((g & want_g) != 0) & (y >= y0) & (y <= y1)
+    m = _stored_f64(store)
+    users = synth.user_ratings(2, n, b)
+    lp, lc, ep, ec = [0], [], [0], []
+    for rated, rts in users:
+        liked = rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1]
+        lc.append(liked); lp.append(lp[-1] + len(liked)); ec.append(rated); ep.append(ep[-1] + len(rated))
+    rows, scores, counts, info = store.recommend_batch(liked_ptr=np.array(lp), liked_col=np.concatenate(lc), excl_ptr=np.array(ep),
+                                                       excl_col=np.concatenate(ec), k=k, return_info=True,
+                                                       row_filter=RowFilter(genre_any=want_g, year_lo=y0, year_hi=y1))
+    assert (info["status"] != 0).mean() < 0.2, (sel, info["status"])
+    for u in range(b):
+        want_rows, want_scores = ora.recommend_rows(m, lc[u], ec[u], k, keep_mask=keep)
+        np.testing.assert_array_equal(rows[u, :counts[u]], want_rows, err_msg=f"user {u}")
+        np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
+        assert keep[rows[u, :counts[u]]].all()
+
+
 def test_recommend_batch_large_sample_path():
     """n large enough that the threshold sample (> 48K rows) is radix-selected in place in global memory."""
     n, d, b, k = 3_200_000, 64, 48, 10

@@ -71,7 +71,11 @@ def _batch_worker(rank, world, port, n, d, b, k, out_q):
     try:
         sc = ShardedCatalog.synthetic(0, n, d, "bf16", scale_rows=True, device=torch.device("cuda", rank))
         lp, lc, ep, ec = _csr_users(n, b)
-        r = sc.recommend_batch(liked_ptr=lp, liked_col=lc, excl_ptr=ep, excl_col=ec, k=k)
+        from robot_ebert_b200 import RowFilter
+        g, y = synth.movie_metadata(3, sc.backend.store.row_base, sc.backend.store.n)      # this shard's slice of the side columns
+        sc.backend.store.set_metadata(g, y)
+        r = sc.recommend_batch(liked_ptr=lp, liked_col=lc, excl_ptr=ep, excl_col=ec, k=k,
+                               row_filter=RowFilter(genre_any=0b1011, year_lo=1960, year_hi=2000))
         out_q.put((rank, r[0].tolist(), r[1].tolist(), r[2].tolist()))
         dist.barrier()
     finally:
@@ -111,7 +115,13 @@ def test_sharded_batch_equals_single_gpu_batch():
         assert p.exitcode == 0
     store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True, device="cuda:0")
     lp, lc, ep, ec = _csr_users(n, b)
-    want = store.recommend_batch(liked_ptr=lp, liked_col=lc, excl_ptr=ep, excl_col=ec, k=k)
+    from robot_ebert_b200 import RowFilter, synth
+    g, y = synth.movie_metadata(3, 0, n)
+    store.set_metadata(g, y)
+    want = store.recommend_batch(liked_ptr=lp, liked_col=lc, excl_ptr=ep, excl_col=ec, k=k,
+                                 row_filter=RowFilter(genre_any=0b1011, year_lo=1960, year_hi=2000))
+    keep = ((g & 0b1011) != 0) & (y >= 1960) & (y <= 2000)
+    assert keep[want[0][want[0] >= 0]].all()
     for rank, rows, scores, counts in results:
         assert rows == want[0].tolist() and counts == want[2].tolist(), rank
         np.testing.assert_allclose(scores, want[1], rtol=1e-12)
