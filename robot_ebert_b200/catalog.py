@@ -90,6 +90,23 @@ class _Scratch:
             self.k_cap = k
 
 
+def sorted_csr(ptr, col):
+    """Validate a ragged CSR (ptr monotone, within bounds) and return it with every segment sorted ascending, as the
+    device-side binary searches require.  Already-sorted input (the common case) is returned without copying."""
+    ptr = np.asarray(ptr, dtype=np.int64)
+    col = np.asarray(col, dtype=np.int32)
+    if ptr.ndim != 1 or ptr.size < 1 or ptr[0] != 0 or ptr[-1] != col.size or np.any(np.diff(ptr) < 0):
+        raise ValueError("malformed CSR: ptr must start at 0, be non-decreasing and end at len(col)")
+    if col.size > 1:
+        desc = np.nonzero(np.diff(col) < 0)[0] + 1                 # positions where the order drops ...
+        bad = np.setdiff1d(desc, ptr[1:-1], assume_unique=False)   # ... other than at a segment boundary
+        if bad.size:
+            col = col.copy()
+            for u in np.unique(np.searchsorted(ptr, bad, side="right") - 1):
+                col[ptr[u]:ptr[u + 1]].sort()
+    return ptr, col
+
+
 def unpack_result(words: np.ndarray, k: int):
     """Split a packed result (see _Scratch.ensure_out) into (rows int64[k'], scores f64[k'], margin)."""
     cnt = int(words[2 * k:2 * k + 1].view(np.int32)[0])
@@ -496,8 +513,11 @@ class CatalogStore:
                 return self._recommend_batch_loop(qn32, qn64, excl_ptr, excl_col, k, return_info, row_filter)
             ep = ec = None
             if excl_ptr is not None:
-                ep = torch.from_numpy(np.asarray(excl_ptr, dtype=np.int64)).to(dev)
-                ec = torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(dev)
+                excl_ptr, excl_col = sorted_csr(excl_ptr, excl_col)
+                if len(excl_ptr) != b + 1:
+                    raise ValueError("exclusion CSR must have one segment per query")
+                ep = torch.from_numpy(excl_ptr).to(dev)
+                ec = torch.from_numpy(excl_col).to(dev)
             ws = torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(self._c), C.byref(plan)), dtype=torch.uint8, device=dev)
             out_rows = torch.empty((b, k), dtype=torch.int64, device=dev)
             out_scores = torch.empty((b, k), dtype=torch.float64, device=dev)
@@ -537,8 +557,10 @@ class CatalogStore:
         scores = np.full((b, k), -np.inf, dtype=np.float64)
         counts = np.zeros(b, dtype=np.int32)
         s = self._scratch()
-        ecp = None if excl_ptr is None else np.asarray(excl_ptr, dtype=np.int64)
-        ec = None if excl_col is None else torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(self.device)
+        ecp = ec = None
+        if excl_ptr is not None:
+            ecp, ecol = sorted_csr(excl_ptr, excl_col)
+            ec = torch.from_numpy(ecol).to(self.device)
         for u in range(b):
             s.ensure_out(k, kc)
             s.qn32.copy_(qn32[u])

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import _native as nat
-from .catalog import CatalogStore, RowFilter, unpack_result
+from .catalog import CatalogStore, RowFilter, sorted_csr, unpack_result
 
 
 class ShardPlan:
@@ -212,8 +212,9 @@ class ShardedCatalog:
         plan = store.gemm_plan(b, k)
         ep = ec = None
         if excl_ptr is not None:
-            ep = torch.from_numpy(np.asarray(excl_ptr, dtype=np.int64)).to(dev)
-            ec = torch.from_numpy(np.asarray(excl_col, dtype=np.int32)).to(dev)
+            excl_ptr, excl_col = sorted_csr(excl_ptr, excl_col)
+            ep = torch.from_numpy(excl_ptr).to(dev)
+            ec = torch.from_numpy(excl_col).to(dev)
         hb = (b + 1) // 2
         words = 2 * b * k + 2 * hb                                       # rows | scores | counts | status
         ctx = {"b": b, "k": k, "plan": plan, "row_filter": row_filter, "qbf": qbf, "qn64": qn64, "ep": ep, "ec": ec, "hb": hb, "words": words,

@@ -65,3 +65,15 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert not pat.search(open(os.path.join(root, f)).read()), f
+
+
+def test_sorted_csr_validates_and_sorts():
+    import numpy as np
+    from robot_ebert_b200.catalog import sorted_csr
+    ptr, col = sorted_csr([0, 3, 3, 5], [1, 5, 9, 2, 7])
+    assert col.tolist() == [1, 5, 9, 2, 7]                       # already sorted per segment: untouched
+    ptr, col = sorted_csr([0, 3, 3, 5], [9, 1, 5, 7, 2])
+    assert col.tolist() == [1, 5, 9, 2, 7]
+    for bad in ([1, 3], [0, 4, 2], [0, 2]):
+        with pytest.raises(ValueError):
+            sorted_csr(bad, [1, 2, 3])
