@@ -196,7 +196,7 @@ __global__ void query_normalize_kernel(const float* __restrict__ q, int d, int l
 
 // One CTA per user; thread c owns column c and walks the user's CSR entries in order, so the fp64 sum has a
 // fixed order (deterministic).  Entries outside this shard are skipped.
-template <typename T>
+template <typename T, bool DIV>
 __global__ void profile_accumulate_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n,
                                           int64_t row_base, int ld, const int64_t* __restrict__ row_ptr,
                                           const int32_t* __restrict__ col, const float* __restrict__ w,
@@ -209,9 +209,13 @@ __global__ void profile_accumulate_kernel(const T* __restrict__ rows, const doub
         for (int64_t e = e0; e < e1; ++e) {
             int64_t r = (int64_t)col[e] - row_base;
             if (r < 0 || r >= n) continue;
-            double wt = w ? (double)w[e] : 1.0;
-            double rn = wt / norm64[r];
-            if (c < ld) acc = fma(elem_f64<T>(rows + r * ld, c), rn, acc);
+            const double wt = w ? (double)w[e] : 1.0;
+            const double nrm = norm64[r];
+            if (c < ld) {
+                // DIV: sklearn's order (unit row element first, then weight) so +-1-type exact values stay exact
+                if (DIV) acc = fma(wt, elem_f64<T>(rows + r * ld, c) / nrm, acc);
+                else     acc = fma(elem_f64<T>(rows + r * ld, c), wt / nrm, acc);
+            }
         }
         if (c < ld) sum64[(int64_t)u * ld + c] = acc;
     }
@@ -250,8 +254,9 @@ __global__ void score_subset_kernel(const T* __restrict__ rows, const double* __
     if (r >= 0 && r < n) {
         const T* row = rows + r * ld;
         const double* p = p64 + (int64_t)u * ld;
-        for (int c = lane; c < ld; c += 32) acc = fma(p[c], elem_f64<T>(row, c), acc);
-        acc = warp_sum(acc) / norm64[r];
+        const double nrm = norm64[r];
+        for (int c = lane; c < ld; c += 32) acc = fma(p[c], elem_f64<T>(row, c) / nrm, acc);   // sklearn's order: unit row first
+        acc = warp_sum(acc);
     } else {
         acc = nan("");
     }
@@ -378,12 +383,14 @@ REBERT_API int rebert_profile_accumulate(const rebert_catalog_t* cat, const int6
     REBERT_REQUIRE(cat && cat->rows && cat->norm64 && row_ptr && col && sum64 && wsum && b > 0,
                    "profile_accumulate: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    if (cat->dtype == REBERT_F32)
-        profile_accumulate_kernel<float><<<b, 256, 0, st>>>((const float*)cat->rows, cat->norm64, cat->n, cat->row_base,
-                                                            cat->ld, row_ptr, col, w, sum64, wsum);
-    else
-        profile_accumulate_kernel<__nv_bfloat16><<<b, 256, 0, st>>>((const __nv_bfloat16*)cat->rows, cat->norm64, cat->n,
-                                                                    cat->row_base, cat->ld, row_ptr, col, w, sum64, wsum);
+    // few users: element-wise division like sklearn's normalize(); large batches: one reciprocal per liked row (1 ulp apart)
+    const bool div = b <= 8;
+#define REBERT_PROFILE_LAUNCH(TT, DD)                                                                                  \
+    profile_accumulate_kernel<TT, DD><<<b, 256, 0, st>>>((const TT*)cat->rows, cat->norm64, cat->n, cat->row_base, cat->ld, \
+                                                         row_ptr, col, w, sum64, wsum)
+    if (cat->dtype == REBERT_F32) { if (div) REBERT_PROFILE_LAUNCH(float, true); else REBERT_PROFILE_LAUNCH(float, false); }
+    else { if (div) REBERT_PROFILE_LAUNCH(__nv_bfloat16, true); else REBERT_PROFILE_LAUNCH(__nv_bfloat16, false); }
+#undef REBERT_PROFILE_LAUNCH
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }

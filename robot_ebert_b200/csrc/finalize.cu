@@ -21,37 +21,42 @@ __device__ __forceinline__ double2 q_pair(const double* sq, int chunks, int ch, 
     return *(const double2*)(sq + ((size_t)p * chunks + ch) * 2);
 }
 template <typename T> struct ChunkDot;
+// DIV = true follows sklearn's operation order exactly (normalize() divides every element by the row norm, then the
+// dot): needed so that rows which tie EXACTLY in the float64 reference (d = 1, scaled one-hot rows) tie here as well.
+template <bool DIV> __device__ __forceinline__ double unit(double x, double nrm) { return DIV ? x / nrm : x; }
 template <> struct ChunkDot<float> {
     static constexpr int EPC = 4;
-    __device__ static __forceinline__ double dot(const uint4& v, const double* sq, int chunks, int ch, double acc) {
+    template <bool DIV>
+    __device__ static __forceinline__ double dot(const uint4& v, const double* sq, int chunks, int ch, double acc, double nrm) {
         const double2 q0 = q_pair(sq, chunks, ch, 0), q1 = q_pair(sq, chunks, ch, 1);
-        acc = fma(q0.x, (double)__uint_as_float(v.x), acc);
-        acc = fma(q0.y, (double)__uint_as_float(v.y), acc);
-        acc = fma(q1.x, (double)__uint_as_float(v.z), acc);
-        acc = fma(q1.y, (double)__uint_as_float(v.w), acc);
+        acc = fma(q0.x, unit<DIV>((double)__uint_as_float(v.x), nrm), acc);
+        acc = fma(q0.y, unit<DIV>((double)__uint_as_float(v.y), nrm), acc);
+        acc = fma(q1.x, unit<DIV>((double)__uint_as_float(v.z), nrm), acc);
+        acc = fma(q1.y, unit<DIV>((double)__uint_as_float(v.w), nrm), acc);
         return acc;
     }
 };
 template <> struct ChunkDot<__nv_bfloat16> {
     static constexpr int EPC = 8;
-    __device__ static __forceinline__ double dot(const uint4& v, const double* sq, int chunks, int ch, double acc) {
+    template <bool DIV>
+    __device__ static __forceinline__ double dot(const uint4& v, const double* sq, int chunks, int ch, double acc, double nrm) {
         const double2 q0 = q_pair(sq, chunks, ch, 0), q1 = q_pair(sq, chunks, ch, 1);
         const double2 q2 = q_pair(sq, chunks, ch, 2), q3 = q_pair(sq, chunks, ch, 3);
-        acc = fma(q0.x, (double)bf16lo(v.x), acc);
-        acc = fma(q0.y, (double)bf16hi(v.x), acc);
-        acc = fma(q1.x, (double)bf16lo(v.y), acc);
-        acc = fma(q1.y, (double)bf16hi(v.y), acc);
-        acc = fma(q2.x, (double)bf16lo(v.z), acc);
-        acc = fma(q2.y, (double)bf16hi(v.z), acc);
-        acc = fma(q3.x, (double)bf16lo(v.w), acc);
-        acc = fma(q3.y, (double)bf16hi(v.w), acc);
+        acc = fma(q0.x, unit<DIV>((double)bf16lo(v.x), nrm), acc);
+        acc = fma(q0.y, unit<DIV>((double)bf16hi(v.x), nrm), acc);
+        acc = fma(q1.x, unit<DIV>((double)bf16lo(v.y), nrm), acc);
+        acc = fma(q1.y, unit<DIV>((double)bf16hi(v.y), nrm), acc);
+        acc = fma(q2.x, unit<DIV>((double)bf16lo(v.z), nrm), acc);
+        acc = fma(q2.y, unit<DIV>((double)bf16hi(v.z), nrm), acc);
+        acc = fma(q3.x, unit<DIV>((double)bf16lo(v.w), nrm), acc);
+        acc = fma(q3.y, unit<DIV>((double)bf16hi(v.w), nrm), acc);
         return acc;
     }
 };
 
 // grid = (b); one CTA per query.  cand_keys [b, kc], q64 [b, ld], outputs [b, k].
 // The fp64 query is staged in shared memory once; every warp re-scores candidates with 16-byte row loads.
-template <typename T>
+template <typename T, bool DIV>
 __global__ void __launch_bounds__(kFinalThreads, 1)
 finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t row_base, int ld,
                      const double* __restrict__ q64, const uint64_t* __restrict__ cand_keys, int kc, int k,
@@ -64,6 +69,7 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
     __shared__ int s_valid;
     __shared__ double s_kth;
     __shared__ unsigned long long s_maxerr;      // bits of a non-negative double: integer order == numeric order
+    __shared__ int s_neartie;
     const int u = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const uint64_t* keys = cand_keys + (size_t)u * kc;
@@ -73,7 +79,7 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
         const int ch = i / EPC, e = i - ch * EPC;
         s_q[((size_t)(e >> 1) * chunks + ch) * 2 + (e & 1)] = q[i];
     }
-    if (threadIdx.x == 0) { s_valid = 0; s_kth = 0.0; s_maxerr = 0ull; }
+    if (threadIdx.x == 0) { s_valid = 0; s_kth = 0.0; s_maxerr = 0ull; s_neartie = 0; }
     __syncthreads();
 
     for (int c = warp; c < kc; c += nwarps) {
@@ -83,15 +89,16 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
         if (key != 0) {
             const uint32_t lr = key_row(key);
             const uint4* row = (const uint4*)(rows + (size_t)lr * ld);
+            const double nrm = norm64[lr];
             double a0 = 0.0, a1 = 0.0;
             int ch = lane;
             for (; ch + 32 < chunks; ch += 64) {                 // two independent 16-byte loads in flight per lane
                 const uint4 v0 = __ldg(row + ch), v1 = __ldg(row + ch + 32);
-                a0 = ChunkDot<T>::dot(v0, s_q, chunks, ch, a0);
-                a1 = ChunkDot<T>::dot(v1, s_q, chunks, ch + 32, a1);
+                a0 = ChunkDot<T>::template dot<DIV>(v0, s_q, chunks, ch, a0, nrm);
+                a1 = ChunkDot<T>::template dot<DIV>(v1, s_q, chunks, ch + 32, a1, nrm);
             }
-            if (ch < chunks) a0 = ChunkDot<T>::dot(__ldg(row + ch), s_q, chunks, ch, a0);
-            sc = warp_sum(a0 + a1) / norm64[lr];
+            if (ch < chunks) a0 = ChunkDot<T>::template dot<DIV>(__ldg(row + ch), s_q, chunks, ch, a0, nrm);
+            sc = DIV ? warp_sum(a0 + a1) : warp_sum(a0 + a1) / nrm;
             gr = row_base + lr;
         }
         if (lane == 0) {
@@ -111,10 +118,16 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
         if (r < 0) continue;
         const double sc = s_score[c];
         int rank = 0;
+        bool near = false;
         for (int j = 0; j < kc; ++j) {
             const int64_t rj = s_row[j];
-            if (rj >= 0 && better(s_score[j], rj, sc, r)) ++rank;
+            if (rj < 0) continue;
+            const double sj = s_score[j];
+            if (better(sj, rj, sc, r)) ++rank;
+            const double gap = fabs(sj - sc);
+            near |= gap != 0.0 && gap <= 8.9e-16 * fmax(fabs(sc), 1e-300);   // distinct scores within 4 ulp
         }
+        if (!DIV && near && rank <= k) s_neartie = 1;    // the divide-after formula cannot be trusted to order these
         if (rank < k) {
             out_rows[(size_t)u * k + rank] = r;
             out_scores[(size_t)u * k + rank] = sc;
@@ -134,7 +147,9 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
             // minus 4x the largest fast-vs-exact deviation seen on the candidates themselves: calibrates whatever
             // rounding the fast pass had (fp32 accumulation, bf16 queries on the tensor-core path)
             const double maxerr = __longlong_as_double((long long)s_maxerr);
-            out_margin[u] = (last != 0 && valid >= k) ? s_kth - (double)key_score(last) - 4.0 * maxerr : INFINITY;
+            double mg = (last != 0 && valid >= k) ? s_kth - (double)key_score(last) - 4.0 * maxerr : INFINITY;
+            if (s_neartie) mg = -INFINITY;               // caller re-runs this query through the divide-first exact pass
+            out_margin[u] = mg;
         }
     }
 }
@@ -272,23 +287,28 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(PeerBufs peers, int
     }
 }
 
-int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
-                    int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st) {
+template <typename T, bool DIV>
+static int finalize_launch_t(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
+                             int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st) {
     const size_t smem = (size_t)cat->ld * sizeof(double);
-    const int threads = kFinalThreads;      // one candidate per warp at kc = 32: the DRAM latencies of the row reads overlap
-    if (cat->dtype == REBERT_F32) {
-        auto kern = finalize_topk_kernel<float>;
-        { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
-        kern<<<b, threads, smem, st>>>((const float*)cat->rows, cat->norm64, cat->row_base, cat->ld, q64, cand_keys, kc, k, out_rows,
-                                       out_scores, out_count, out_margin);
-    } else {
-        auto kern = finalize_topk_kernel<__nv_bfloat16>;
-        { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
-        kern<<<b, threads, smem, st>>>((const __nv_bfloat16*)cat->rows, cat->norm64, cat->row_base, cat->ld, q64, cand_keys, kc, k,
-                                       out_rows, out_scores, out_count, out_margin);
-    }
+    auto kern = finalize_topk_kernel<T, DIV>;
+    { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
+    kern<<<b, kFinalThreads, smem, st>>>((const T*)cat->rows, cat->norm64, cat->row_base, cat->ld, q64, cand_keys, kc, k, out_rows,
+                                         out_scores, out_count, out_margin);
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
+}
+
+// exact_order = true: sklearn's operation order (element-wise division first) — the single-request path.
+// exact_order = false: one division after the dot (within 1 ulp), near-ties flagged through the margin — the batched path.
+int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
+                    int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st,
+                    bool exact_order) {
+    if (cat->dtype == REBERT_F32)
+        return exact_order ? finalize_launch_t<float, true>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st)
+                           : finalize_launch_t<float, false>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st);
+    return exact_order ? finalize_launch_t<__nv_bfloat16, true>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st)
+                       : finalize_launch_t<__nv_bfloat16, false>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st);
 }
 
 }  // namespace rebert
@@ -304,7 +324,7 @@ REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* q
                    "finalize_topk: null argument");
     REBERT_REQUIRE(kc > 0 && kc <= kMaxKc && k > 0 && k <= kc, "finalize_topk: k=%d kc=%d", k, kc);
     return finalize_launch(cat, qn64, cand_keys, 1, kc, k, out_rows, out_scores, out_count, out_margin,
-                           (cudaStream_t)stream);
+                           (cudaStream_t)stream, /*exact_order=*/true);
 }
 
 REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, const int32_t* counts, int64_t rows_stride,

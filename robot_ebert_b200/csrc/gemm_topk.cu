@@ -30,7 +30,8 @@
 namespace rebert {
 
 int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
-                    int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st);
+                    int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st,
+                    bool exact_order);
 
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
 constexpr int GEMM_STAGES = 4;
@@ -879,7 +880,8 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
                                                     excl_col, w.tau, w.cand_keys, out_status);
     REBERT_CUDA(cudaGetLastError());
     // 5. exact pass
-    rc = finalize_launch(cat, q64, w.cand_keys, b, plan->kc, plan->k, out_rows, out_scores, out_count, w.margin, st);
+    rc = finalize_launch(cat, q64, w.cand_keys, b, plan->kc, plan->k, out_rows, out_scores, out_count, w.margin, st,
+                         /*exact_order=*/false);   // near-ties come back as margin = -inf and are re-run by the caller
     if (rc != REBERT_OK) return rc;
     // The margin already has 4 x (largest observed |fast - exact| over the kc candidates) subtracted (finalize.cu), which
     // calibrates the bf16 rounding of the query; on top require the model bound for that rounding, 3 sigma with

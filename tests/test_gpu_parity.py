@@ -228,3 +228,26 @@ def test_mass_ties_are_resolved_by_the_exact_sweep(n, d, k):
     assert info["proven_exact"]
     np.testing.assert_array_equal(rows, want_rows)
     np.testing.assert_allclose(scores, want_scores, rtol=1e-12)
+
+
+def test_exact_ties_follow_sklearn_operation_order():
+    """Found by hypothesis: d = 1 profile mode, and scaled one-hot rows in any d, tie EXACTLY in the float64 reference
+    (x/||x|| is exactly +-1).  The exact pass must divide element-wise first, like sklearn's normalize(), to keep the tie."""
+    m = synth.catalog_rows_f32(0, 0, 17, 1, scale_rows=True)
+    m[int(np.random.default_rng(0).integers(0, 17))] = 0.0
+    store = CatalogStore.from_host(synth.row_ids(17), m, "fp32")
+    liked = np.array([2, 5, 11])
+    rows, scores = store.recommend(liked_rows=liked, k=1)
+    want_rows, want_scores = ora.recommend_rows(m.astype(np.float64), liked, None, 1)
+    np.testing.assert_array_equal(rows, want_rows)
+    # scaled one-hot rows, d = 48: every row on axis j scores exactly q_hat[j] * sign
+    rng = np.random.default_rng(1)
+    n, d = 4000, 48
+    m = np.zeros((n, d), dtype=np.float32)
+    m[np.arange(n), rng.integers(0, d, size=n)] = rng.uniform(0.1, 9.0, size=n).astype(np.float32) * rng.choice([-1, 1], size=n)
+    store = CatalogStore.from_host(synth.row_ids(n), m, "fp32")
+    for liked in (rng.choice(n, size=7, replace=False), rng.choice(n, size=40, replace=False)):
+        rows, scores = store.recommend(liked_rows=np.sort(liked), exclude_rows=liked, k=25)
+        want_rows, want_scores = ora.recommend_rows(m.astype(np.float64), np.sort(liked), liked, 25)
+        np.testing.assert_allclose(scores, want_scores, rtol=1e-12, atol=1e-15)
+        np.testing.assert_array_equal(rows, want_rows)
