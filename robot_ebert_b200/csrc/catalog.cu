@@ -194,35 +194,88 @@ __global__ void query_normalize_kernel(const float* __restrict__ q, int d, int l
     }
 }
 
-// One CTA per user; thread c owns column c and walks the user's CSR entries in order, so the fp64 sum has a
-// fixed order (deterministic).  Entries outside this shard are skipped.
+// One CTA per user.  The user's entries (local row, weight, row norm) are staged in shared memory in blocks; each
+// thread owns one 16-byte chunk of the row (4 fp32 / 8 bf16 columns) with fp64 accumulators and walks the entries in
+// CSR order — a fixed summation order, so the profile is deterministic — with four row loads in flight.
+// Entries outside this shard are skipped (their partial sums come from the owning rank through the all-reduce).
+template <typename T> struct RowChunk;
+template <> struct RowChunk<float> {
+    static constexpr int EPC = 4;
+    __device__ static __forceinline__ void unpack(const uint4& v, double* x) {
+        x[0] = (double)__uint_as_float(v.x); x[1] = (double)__uint_as_float(v.y);
+        x[2] = (double)__uint_as_float(v.z); x[3] = (double)__uint_as_float(v.w);
+    }
+};
+template <> struct RowChunk<__nv_bfloat16> {
+    static constexpr int EPC = 8;
+    __device__ static __forceinline__ void unpack(const uint4& v, double* x) {
+        x[0] = (double)bf16lo(v.x); x[1] = (double)bf16hi(v.x); x[2] = (double)bf16lo(v.y); x[3] = (double)bf16hi(v.y);
+        x[4] = (double)bf16lo(v.z); x[5] = (double)bf16hi(v.z); x[6] = (double)bf16lo(v.w); x[7] = (double)bf16hi(v.w);
+    }
+};
+
+constexpr int kProfBlock = 512;     // entries staged per round
+
 template <typename T, bool DIV>
-__global__ void profile_accumulate_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n,
-                                          int64_t row_base, int ld, const int64_t* __restrict__ row_ptr,
-                                          const int32_t* __restrict__ col, const float* __restrict__ w,
-                                          double* __restrict__ sum64, double* __restrict__ wsum) {
-    int u = blockIdx.x;
-    int64_t e0 = row_ptr[u], e1 = row_ptr[u + 1];
-    for (int c0 = 0; c0 < ld; c0 += blockDim.x) {
-        int c = c0 + threadIdx.x;
-        double acc = 0.0;
-        for (int64_t e = e0; e < e1; ++e) {
-            int64_t r = (int64_t)col[e] - row_base;
-            if (r < 0 || r >= n) continue;
-            const double wt = w ? (double)w[e] : 1.0;
-            const double nrm = norm64[r];
-            if (c < ld) {
-                // DIV: sklearn's order (unit row element first, then weight) so +-1-type exact values stay exact
-                if (DIV) acc = fma(wt, elem_f64<T>(rows + r * ld, c) / nrm, acc);
-                else     acc = fma(elem_f64<T>(rows + r * ld, c), wt / nrm, acc);
+__global__ void __launch_bounds__(256) profile_accumulate_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n,
+                                                                 int64_t row_base, int ld, const int64_t* __restrict__ row_ptr,
+                                                                 const int32_t* __restrict__ col, const float* __restrict__ w,
+                                                                 double* __restrict__ sum64, double* __restrict__ wsum) {
+    constexpr int EPC = RowChunk<T>::EPC;
+    __shared__ int s_row[kProfBlock];
+    __shared__ double s_w[kProfBlock];      // weight (DIV) or weight / norm (!DIV)
+    __shared__ double s_n[kProfBlock];      // norm (DIV only)
+    const int u = blockIdx.x;
+    const int64_t e0 = row_ptr[u], e1 = row_ptr[u + 1];
+    const int chunks = ld / EPC;
+    for (int g0 = 0; g0 < chunks; g0 += blockDim.x) {
+        const int g = g0 + threadIdx.x;
+        double acc[EPC];
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) acc[i] = 0.0;
+        for (int64_t b0 = e0; b0 < e1; b0 += kProfBlock) {
+            const int nb = (int)((e1 - b0) < kProfBlock ? (e1 - b0) : kProfBlock);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+                const int64_t r = (int64_t)col[b0 + i] - row_base;
+                const bool mine = r >= 0 && r < n;
+                const double wt = w ? (double)w[b0 + i] : 1.0;
+                const double nrm = mine ? norm64[r] : 1.0;
+                s_row[i] = mine ? (int)r : -1;
+                s_w[i] = DIV ? wt : wt / nrm;
+                s_n[i] = nrm;
+            }
+            __syncthreads();
+            if (g < chunks) {
+                for (int i = 0; i < nb; i += 4) {
+                    uint4 v[4];
+                    int rr[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        rr[j] = (i + j < nb) ? s_row[i + j] : -1;
+                        if (rr[j] >= 0) v[j] = __ldg((const uint4*)(rows + (size_t)rr[j] * ld) + g);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (rr[j] < 0) continue;
+                        double x[EPC];
+                        RowChunk<T>::unpack(v[j], x);
+                        const double wt = s_w[i + j], nrm = s_n[i + j];
+#pragma unroll
+                        for (int t = 0; t < EPC; ++t) acc[t] = DIV ? fma(wt, x[t] / nrm, acc[t]) : fma(x[t], wt, acc[t]);
+                    }
+                }
             }
         }
-        if (c < ld) sum64[(int64_t)u * ld + c] = acc;
+        if (g < chunks) {
+#pragma unroll
+            for (int t = 0; t < EPC; ++t) sum64[(int64_t)u * ld + (int64_t)g * EPC + t] = acc[t];
+        }
     }
     if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int64_t e = e0; e < e1; ++e) s += w ? (double)w[e] : 1.0;
-        wsum[u] = s;
+        double sw = 0.0;
+        for (int64_t e = e0; e < e1; ++e) sw += w ? (double)w[e] : 1.0;
+        wsum[u] = sw;
     }
 }
 
