@@ -603,14 +603,19 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(float* sample, in
     if (threadIdx.x == 0) tau[q] = (s_rank == 0xFFFFFFFFu || s_prefix == 0) ? -INFINITY : orderable_f32(s_prefix);
 }
 
-// Per query: survivors of the filter -> drop excluded rows -> bitonic sort -> best kc keys (zero padded).
+// Per query: survivors of the filter -> drop excluded rows -> best kc keys, sorted (zero padded).
+// With many more survivors than kc a full sort is wasted work: the scores' range [lo, hi] is cut into 1024 linear
+// buckets, a histogram finds the bucket holding the kc-th best, and only the keys from that bucket upwards (kc + a
+// few) are sorted.  Small or degenerate inputs (few survivors, mass ties) take the plain bitonic sort.
 __global__ void __launch_bounds__(512) select_candidates_kernel(const uint64_t* __restrict__ cand, const unsigned* __restrict__ cand_count,
                                                                 int cand_cap, int kc, int64_t row_base,
                                                                 const int64_t* __restrict__ excl_ptr, const int32_t* __restrict__ excl_col,
                                                                 const float* __restrict__ tau, uint64_t* __restrict__ out_keys,
                                                                 int* __restrict__ status) {
-    extern __shared__ __align__(16) uint64_t buf[];        // [pow2 >= cand_cap]
-    __shared__ int s_valid;
+    extern __shared__ __align__(16) uint64_t buf[];        // [pow2 >= cand_cap] survivors, then [1024] top set
+    __shared__ unsigned hist[1024];
+    __shared__ int s_valid, s_m, s_bstar;
+    __shared__ unsigned s_lo, s_hi;
     const int q = blockIdx.x;
     const unsigned cnt_raw = cand_count[q];
     const int cnt = cnt_raw < (unsigned)cand_cap ? (int)cnt_raw : cand_cap;
@@ -619,23 +624,73 @@ __global__ void __launch_bounds__(512) select_candidates_kernel(const uint64_t* 
     if (excl_ptr) { ex = excl_col + excl_ptr[q]; nex = (int)(excl_ptr[q + 1] - excl_ptr[q]); }
     int p2 = 2;
     while (p2 < cnt || p2 < kc) p2 <<= 1;
-    if (threadIdx.x == 0) s_valid = 0;
+    if (threadIdx.x == 0) { s_valid = 0; s_m = 0; s_lo = 0xFFFFFFFFu; s_hi = 0; s_bstar = 0; }
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     int mine = 0;
+    unsigned lo = 0xFFFFFFFFu, hi = 0;
     for (int i = threadIdx.x; i < p2; i += blockDim.x) {
         uint64_t key = i < cnt ? cand[(size_t)q * cand_cap + i] : 0;
         if (key && nex && sorted_contains(ex, nex, (int32_t)(row_base + key_row(key)))) key = 0;
         buf[i] = key;
-        mine += key != 0;
+        if (key) {
+            ++mine;
+            const unsigned v = (unsigned)(key >> 32);
+            lo = min(lo, v);
+            hi = max(hi, v);
+        }
     }
-    if (mine) atomicAdd(&s_valid, mine);
+    if (mine) { atomicAdd(&s_valid, mine); atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
     __syncthreads();
-    block_bitonic_sort_desc(buf, p2);
-    for (int i = threadIdx.x; i < kc; i += blockDim.x) out_keys[(size_t)q * kc + i] = buf[i];
+    const int valid = s_valid;
+    bool sorted_in_place = true;
+    if (valid > 2 * kc && s_hi > s_lo) {
+        // ---- bucket select
+        const unsigned blo = s_lo;
+        const unsigned long long range = (unsigned long long)(s_hi - blo) + 1ull;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint64_t key = buf[i];
+            if (key) atomicAdd(&hist[(unsigned)(((unsigned long long)((unsigned)(key >> 32) - blo) * 1023ull) / range)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cum = 0, b = 1023;
+            for (; b > 0; --b) { cum += (int)hist[b]; if (cum >= kc) break; }
+            if (b == 0) cum += (int)hist[0];
+            s_bstar = b;
+            s_m = cum >= kc ? cum : -1;            // keys in buckets >= b*
+        }
+        __syncthreads();
+        const int m = s_m, bstar = s_bstar;
+        if (m >= kc && m <= 1024) {
+            uint64_t* top = buf + p2;              // second region of the dynamic smem
+            __syncthreads();
+            if (threadIdx.x == 0) s_m = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+                const uint64_t key = buf[i];
+                if (key && (int)(((unsigned long long)((unsigned)(key >> 32) - blo) * 1023ull) / range) >= bstar)
+                    top[atomicAdd(&s_m, 1)] = key;
+            }
+            __syncthreads();
+            int t2 = 2;
+            while (t2 < m) t2 <<= 1;
+            for (int i = m + threadIdx.x; i < t2; i += blockDim.x) top[i] = 0;
+            __syncthreads();
+            block_bitonic_sort_desc(top, t2);
+            for (int i = threadIdx.x; i < kc; i += blockDim.x) out_keys[(size_t)q * kc + i] = top[i];
+            sorted_in_place = false;
+        }
+    }
+    if (sorted_in_place) {
+        __syncthreads();
+        block_bitonic_sort_desc(buf, p2);
+        for (int i = threadIdx.x; i < kc; i += blockDim.x) out_keys[(size_t)q * kc + i] = buf[i];
+    }
     if (threadIdx.x == 0) {
         int st = status[q];
         if (cnt_raw > (unsigned)cand_cap) st |= 2;                         // buffer overflow: some survivors were dropped
-        if (s_valid < kc && tau[q] != -INFINITY) st |= 4;                  // threshold too optimistic: not enough candidates
+        if (valid < kc && tau[q] != -INFINITY) st |= 4;                    // threshold too optimistic: not enough candidates
         status[q] = st;
     }
 }
@@ -874,7 +929,7 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     // 4. per-query candidate selection
     int p2 = 2;
     while (p2 < plan->cand_cap) p2 <<= 1;
-    const size_t csmem = (size_t)p2 * 8;
+    const size_t csmem = (size_t)(p2 + 1024) * 8;        // survivors + the bucket-selected top set
     { int rc__ = raise_smem_limit(select_candidates_kernel); if (rc__ != REBERT_OK) return rc__; }
     select_candidates_kernel<<<b, 512, csmem, st>>>(w.cand, w.cand_count, plan->cand_cap, plan->kc, cat->row_base, excl_row_ptr,
                                                     excl_col, w.tau, w.cand_keys, out_status);
