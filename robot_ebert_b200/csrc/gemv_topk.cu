@@ -39,6 +39,7 @@ struct GemvParams {
     uint64_t*    cta_lists; // [grid, kc]
     uint64_t*    cand_keys; // [kc] final output
     unsigned*    counter;   // CTAs finished (zero before launch; the last CTA resets it)
+    unsigned*    ghint;     // grid-wide threshold hint, orderable fp32 bits (zero before launch; reset with the counter)
     int          merge_cap; // keys the final merge may hold in shared memory (power of two)
 };
 
@@ -231,6 +232,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
 
     WarpTopK<M> top;
     top.init();
+    // Threshold hints.  A warp whose list is full has kc rows scoring >= its threshold, so that value bounds the global
+    // kc-th best from below and every other warp may drop rows strictly below it (>= keeps equal scores, whose row
+    // order is decided later).  Best value per CTA in shared memory, and sparsely grid-wide through one global word.
+    __shared__ unsigned s_hint;
+    if (threadIdx.x == 0) s_hint = 0u;
+    __syncthreads();
 
     if (warp == kConsumerWarps) {
         // ===================== producer warp: one elected lane issues the bulk copies =====================
@@ -278,6 +285,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
             const uint4* tile = (const uint4*)st;
             const float* inv_s = (const float*)(st + tile_bytes);
 
+            // hint for this tile: CTA value, refreshed from / published to the grid-wide word every 8th tile by warp 0
+            unsigned hb = *(volatile unsigned*)&s_hint;
+            if ((it & 7) == 0) {
+                const unsigned g = __ldcg(p.ghint);
+                if (g > hb) { hb = g; if (lane == 0) atomicMax(&s_hint, g); }
+                else if (warp == 0 && lane == 0 && hb > g) atomicMax(p.ghint, hb);
+            }
+            const float hint = hb ? orderable_f32(hb) : -INFINITY;
+
             mbar_wait(&full_bar[s], round & 1u);
 
             // two row groups per step for ILP: rows rA and rB = rA + kConsumerWarps*RPW
@@ -324,21 +340,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
 
                 // rare path: some row of this step beats the warp threshold.  Row order A(sub 0..), then B(sub 0..)
                 // is ascending, which WarpTopK::insert relies on.
-                unsigned ma = __ballot_sync(0xffffffffu, vA && cl == 0 && sa > top.thr);
+                unsigned ma = __ballot_sync(0xffffffffu, vA && cl == 0 && sa > top.thr && sa >= hint);
                 while (ma) {
                     const int src = __ffs(ma) - 1;
                     ma &= ma - 1;
                     const float sc = __shfl_sync(0xffffffffu, sa, src);
                     const uint32_t lr = (uint32_t)(row0 + base + src / LANES);
-                    if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) top.insert(make_key(sc, lr), lane);
+                    if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) {
+                        top.insert(make_key(sc, lr), lane);
+                        if (lane == 0 && top.thr > -INFINITY) atomicMax(&s_hint, f32_orderable(top.thr));
+                    }
                 }
-                unsigned mb = __ballot_sync(0xffffffffu, vB && cl == 0 && sb > top.thr);
+                unsigned mb = __ballot_sync(0xffffffffu, vB && cl == 0 && sb > top.thr && sb >= hint);
                 while (mb) {
                     const int src = __ffs(mb) - 1;
                     mb &= mb - 1;
                     const float sc = __shfl_sync(0xffffffffu, sb, src);
                     const uint32_t lr = (uint32_t)(row0 + base + kConsumerWarps * RPW + src / LANES);
-                    if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) top.insert(make_key(sc, lr), lane);
+                    if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) {
+                        top.insert(make_key(sc, lr), lane);
+                        if (lane == 0 && top.thr > -INFINITY) atomicMax(&s_hint, f32_orderable(top.thr));
+                    }
                 }
             }
             __syncwarp();
@@ -388,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     if (!s_last) return;
     __threadfence();
     final_merge(p.cta_lists, (int)gridDim.x, kc, p.merge_cap, (uint64_t*)smem, p.cand_keys);
-    if (threadIdx.x == 0) *p.counter = 0;
+    if (threadIdx.x == 0) { *p.counter = 0; *p.ghint = 0u; }
 }
 
 // ---------------------------------------------------------------- host side ----------------------------------
@@ -547,6 +569,7 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.filter = make_filter(filter, cat->row_base);
     p.cta_lists = (uint64_t*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
     p.counter = (unsigned*)(p.cta_lists + (size_t)num_sms() * kc);
+    p.ghint = p.counter + 1;
     p.cand_keys = cand_keys;
     p.merge_cap = g.merge_cap;
 
