@@ -284,29 +284,39 @@ class CatalogStore:
     def _exact_sweep(self, lib, query, liked_rows, weights, exclude_rows, k, row_filter, kth_score):
         """Fallback for results no candidate list can prove: collect every allowed row with fast score >= k-th exact
         score - 2 eps (a superset of the true top-k), fp64 re-score them, order by (score desc, row asc)."""
-        s = self._scratch()
         with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream()
             kc = lib.rebert_candidates_for_k(k)
             excl_ptr, ne = self.stage_inputs(query, liked_rows, weights, exclude_rows, k, kc)   # refreshes qn32 / qn64
-            f = self._filter_struct(row_filter) or nat.Filter()
-            if ne:
-                f.exclude_rows, f.n_exclude = excl_ptr, ne
-            out_rows = torch.empty(self.SWEEP_CAP, dtype=torch.int32, device=self.device)
-            out_count = torch.zeros(1, dtype=torch.int32, device=self.device)
-            thr = kth_score - 2.0 * self.fast_eps
-            nat.check(lib.rebert_collect_above(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), C.c_float(thr), out_rows.data_ptr(),
-                                               self.SWEEP_CAP, out_count.data_ptr(), stream.cuda_stream))
-            cnt = int(out_count.item())
-            if cnt < k or cnt > self.SWEEP_CAP:
-                return None
-            sub = out_rows[:cnt].contiguous()
-            exact = torch.empty((1, cnt), dtype=torch.float64, device=self.device)
-            nat.check(lib.rebert_score_subset(C.byref(self._c), s.qn64.data_ptr(), 1, sub.data_ptr(), cnt, exact.data_ptr(),
-                                              stream.cuda_stream))
-            rr, sc = sub.cpu().numpy().astype(np.int64), exact[0].cpu().numpy()
+            res = self.sweep_above(kth_score - 2.0 * self.fast_eps, excl_ptr, ne, row_filter)
+        if res is None or len(res[0]) < k:
+            return None
+        rr, sc = res
         order = np.lexsort((rr, -sc))[:k]            # bookkeeping on the handful of survivors
         return rr[order], sc[order]
+
+    def sweep_above(self, threshold: float, excl_ptr=None, n_excl: int = 0, row_filter: Optional[RowFilter] = None):
+        """(global rows int64, exact fp64 scores) of every allowed row of this shard whose fast score >= threshold, for
+        the query / profile in this thread's scratch; None if more than SWEEP_CAP rows qualify."""
+        lib = nat.load()
+        s = self._scratch()
+        stream = torch.cuda.current_stream()
+        f = self._filter_struct(row_filter) or nat.Filter()
+        if n_excl:
+            f.exclude_rows, f.n_exclude = excl_ptr, n_excl
+        out_rows = torch.empty(self.SWEEP_CAP, dtype=torch.int32, device=self.device)
+        out_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nat.check(lib.rebert_collect_above(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), C.c_float(threshold), out_rows.data_ptr(),
+                                           self.SWEEP_CAP, out_count.data_ptr(), stream.cuda_stream))
+        cnt = int(out_count.item())
+        if cnt > self.SWEEP_CAP:
+            return None
+        if cnt == 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float64)
+        sub = out_rows[:cnt].contiguous()
+        exact = torch.empty((1, cnt), dtype=torch.float64, device=self.device)
+        nat.check(lib.rebert_score_subset(C.byref(self._c), s.qn64.data_ptr(), 1, sub.data_ptr(), cnt, exact.data_ptr(),
+                                          stream.cuda_stream))
+        return sub.cpu().numpy().astype(np.int64), exact[0].cpu().numpy()
 
     def _recommend_once(self, lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter):
         """One rebert_recommend_host call: host buffers in, host buffers out, copies + kernels + sync inside."""

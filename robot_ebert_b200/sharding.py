@@ -116,6 +116,10 @@ class CudaShardBackend:
         s.wsum.copy_(summed[st.ld:] / self._world)
         st.finalize_profile()
 
+    def sweep_local(self, threshold: float, row_filter: Optional[RowFilter]):
+        ptr, ne = self._excl
+        return self.store.sweep_above(threshold, ptr, ne, row_filter)
+
     def local_topk(self, k: int, kc: int, row_filter: Optional[RowFilter]) -> torch.Tensor:
         ptr, ne = self._excl
         return self.store.enqueue_topk(k, kc, ptr, ne, row_filter)
@@ -197,9 +201,39 @@ class ShardedCatalog:
             if margin > eps or kc >= 256:
                 break
             kc = min(256, kc * 4)
+        proven, swept = margin > eps, False
+        if not proven and len(rows) == k and hasattr(self.backend, "sweep_local"):
+            # mass ties (see CatalogStore._exact_sweep): every rank sweeps its shard against the global k-th score
+            res = self._exact_sweep(float(scores[k - 1]) - 2.0 * eps, k, row_filter)
+            if res is not None:
+                rows, scores = res
+                proven = swept = True
         if return_info:
-            return rows, scores, {"kc": kc, "margin": margin, "proven_exact": margin > eps}
+            return rows, scores, {"kc": kc, "margin": margin, "proven_exact": proven, "exact_sweep": swept}
         return rows, scores
+
+    def _exact_sweep(self, threshold: float, k: int, row_filter):
+        """Sharded form of the exact fallback: local sweeps, one all-gather of the (padded) survivors, same order on every rank."""
+        local = self.backend.sweep_local(threshold, row_filter)
+        dev = self.backend.device
+        n_loc = torch.tensor([-1 if local is None else len(local[0])], dtype=torch.int64, device=dev)
+        counts = torch.empty(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, n_loc, group=self.group)
+        counts = counts.cpu().numpy()
+        if (counts < 0).any() or counts.sum() < k:
+            return None
+        cap = int(counts.max())
+        mine = torch.zeros(2 * cap, dtype=torch.int64, device=dev)
+        if cap and len(local[0]):
+            mine[:len(local[0])] = torch.from_numpy(local[0]).to(dev)
+            mine[cap:cap + len(local[0])] = torch.from_numpy(local[1].view(np.int64)).to(dev)
+        allr = torch.empty((self.world, 2 * cap), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allr.view(-1), mine, group=self.group)
+        allr = allr.cpu().numpy()
+        rr = np.concatenate([allr[g, :counts[g]] for g in range(self.world)])
+        sc = np.concatenate([allr[g, cap:cap + counts[g]].view(np.float64) for g in range(self.world)])
+        order = np.lexsort((rr, -sc))[:k]
+        return rr[order], sc[order]
 
     # ------------------------------------------------------------------ batched (tensor-core) path ----------
     def batch_context(self, qbf: torch.Tensor, qn64: torch.Tensor, k: int, excl_ptr=None, excl_col=None, row_filter=None):

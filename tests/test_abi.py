@@ -77,3 +77,27 @@ def test_sorted_csr_validates_and_sorts():
     for bad in ([1, 3], [0, 4, 2], [0, 2]):
         with pytest.raises(ValueError):
             sorted_csr(bad, [1, 2, 3])
+
+
+def test_c_abi_argument_validation_without_a_gpu():
+    """Every entry point validates its arguments before touching CUDA: status codes + thread-local message."""
+    import ctypes as C
+    lib = nat.load()
+    cat = nat.Catalog(rows=0, inv_norm=0, norm64=0, n=10, row_base=0, d=32, ld=32, dtype=nat.F32, reserved=0)
+    f = nat.Filter()
+    assert lib.rebert_gemv_topk(C.byref(cat), None, C.byref(f), 32, None, 0, None, None) == nat.ERR_INVALID
+    assert b"null" in lib.rebert_last_error()
+    assert lib.rebert_finalize_topk(C.byref(cat), None, None, 32, 10, None, None, None, None, None) == nat.ERR_INVALID
+    assert lib.rebert_catalog_layout(10, 32, 7, None, None) == nat.ERR_INVALID and b"dtype" in lib.rebert_last_error()
+    assert lib.rebert_merge_topk(None, None, None, 1, 1, 1, 2, 1, 10, None, None, None, None) == nat.ERR_INVALID
+    assert lib.rebert_exchange_buffer_bytes(0, 10) == 0 and lib.rebert_exchange_buffer_bytes(17, 10) == 0
+    assert lib.rebert_exchange_buffer_bytes(8, 240) == (2 * 8 * 482 + 16) * 8
+    plan = nat.GemmPlan()
+    assert lib.rebert_gemm_plan(1000, 16, 10, C.byref(plan)) == nat.ERR_UNSUPPORTED and b"too small" in lib.rebert_last_error()
+    assert lib.rebert_gemm_plan(1_000_000, 4096, 100, C.byref(plan)) == nat.OK
+    assert (plan.kc, plan.sample_rank, plan.cand_cap) == (128, 16, 4096) and plan.sample_rows % 256 == 0
+    assert lib.rebert_gemm_plan(1_000_000, 4096, 5000, C.byref(plan)) == nat.ERR_UNSUPPORTED
+    with pytest.raises(ValueError):
+        nat.check(nat.ERR_INVALID)
+    with pytest.raises(nat.NativeError):
+        nat.check(nat.ERR_UNSUPPORTED)

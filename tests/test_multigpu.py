@@ -125,3 +125,52 @@ def test_sharded_batch_equals_single_gpu_batch():
     for rank, rows, scores, counts in results:
         assert rows == want[0].tolist() and counts == want[2].tolist(), rank
         np.testing.assert_allclose(scores, want[1], rtol=1e-12)
+
+
+def _tie_worker(rank, world, port, out_q):
+    import torch.distributed as dist
+    from robot_ebert_b200 import CatalogStore
+    from robot_ebert_b200.sharding import CudaShardBackend, ShardedCatalog, ShardPlan
+    from robot_ebert_b200 import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        n = 3000
+        m = synth.catalog_rows_f32(0, 0, n, 1, scale_rows=True)                    # d = 1: every cosine is exactly +-1
+        row0, cnt = ShardPlan(n, world).range(rank)
+        store = CatalogStore.from_host(None, m[row0:row0 + cnt], "fp32", device=torch.device("cuda", rank), row_base=row0)
+        backend = CudaShardBackend(store)
+        backend.setup_p2p()
+        sc = ShardedCatalog(backend, n)
+        rows, scores, info = sc.recommend(query=np.ones(1, dtype=np.float32), exclude_rows=np.arange(0, n, 7), k=10, return_info=True)
+        out_q.put((rank, rows.tolist(), scores.tolist(), bool(info["proven_exact"])))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_mass_ties_use_the_exact_sweep():
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import reference_scoring as ora
+    from robot_ebert_b200 import synth
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    procs = [ctx.Process(target=_tie_worker, args=(r, world, port, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out_q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    m = synth.catalog_rows_f32(0, 0, 3000, 1, scale_rows=True).astype(np.float64)
+    want_rows, want_scores = ora.query_rows(m, np.ones(1), np.arange(0, 3000, 7), 10)
+    for rank, rows, scores, proven in results:
+        assert proven and rows == want_rows.tolist(), rank
+        np.testing.assert_allclose(scores, want_scores, rtol=1e-12)
