@@ -173,7 +173,7 @@ def test_unsupported_and_invalid_arguments():
     with pytest.raises(ValueError):
         store.recommend(query=q, k=0)
     with pytest.raises(ValueError):
-        store.recommend(query=q, k=1000)
+        store.recommend(query=q, k=10**6)
     with pytest.raises(ValueError):
         store.recommend(query=q[:5], k=3)
     with pytest.raises(ValueError):
@@ -251,3 +251,21 @@ def test_exact_ties_follow_sklearn_operation_order():
         want_rows, want_scores = ora.recommend_rows(m.astype(np.float64), np.sort(liked), liked, 25)
         np.testing.assert_allclose(scores, want_scores, rtol=1e-12, atol=1e-15)
         np.testing.assert_array_equal(rows, want_rows)
+
+
+@pytest.mark.parametrize("n,d,k", [(30_000, 64, 241), (50_000, 256, 1000), (300, 32, 500)])
+def test_large_k_route(n, d, k):
+    """k beyond the register-list kernel (the reference takes any k: api/users.py:151) — bisection + sweep, still exact."""
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    m = _stored_f64(store)
+    q = synth.query_f32(1, d)
+    excl = np.random.default_rng(2).choice(n, size=min(n // 3, 133), replace=False)
+    rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True)
+    want_rows, want_scores = ora.query_rows(m, q.astype(np.float64), excl, k)
+    assert info["proven_exact"] and len(rows) == min(k, n - len(excl))
+    np.testing.assert_array_equal(rows, want_rows)
+    np.testing.assert_allclose(scores, want_scores, rtol=1e-9, atol=1e-15)
+    (rated, rts), = synth.user_ratings(2, n, 1, mean_rated=min(60, n // 4))
+    rows, scores = store.recommend(liked_rows=rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1], exclude_rows=rated, k=k)
+    want_rows, want_scores = ora.recommend_rows(m, rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1], rated, k)
+    np.testing.assert_array_equal(rows, want_rows)
