@@ -57,6 +57,7 @@ class CudaShardBackend:
         self.store = store
         self.device = store.device
         self._merged = {}
+        self._host = {}
         self.exchange = "nccl"       # becomes "p2p" once setup_p2p() has mapped the peers' buffers
         self._seq = 0
 
@@ -77,7 +78,6 @@ class CudaShardBackend:
             hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
             self._symm_buf, self._symm_hdl = buf, hdl
             self._peer_ptrs = (C.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
-            self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._p2p_out = {}
             self._p2p_world, self._p2p_rank = world, rank
             ok.fill_(1)
@@ -89,15 +89,15 @@ class CudaShardBackend:
         return self.exchange == "p2p"
 
     def exchange_merge(self, local: torch.Tensor, k: int) -> torch.Tensor:
-        """P2P exchange + merge of the packed local result (int64 [2k+2]) -> packed merged result."""
+        """P2P exchange + merge of the packed local result (int64 [2k+2]) -> packed merged result (+1 word: error flag)."""
         lib = nat.load()
         out = self._p2p_out.get(k)
         if out is None:
-            out = self._p2p_out[k] = torch.empty(2 * k + 2, dtype=torch.int64, device=self.device)
+            out = self._p2p_out[k] = torch.zeros(2 * k + 3, dtype=torch.int64, device=self.device)   # last word: peer-timeout flag
         self._seq += 1
         nat.check(lib.rebert_exchange_merge(self._peer_ptrs, self._p2p_world, self._p2p_rank, k, self.K_MAX,
                                             self._seq & 0xFFFFFFFF or 1, local.data_ptr(), out.data_ptr(),
-                                            self._err.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                            out.data_ptr() + 8 * (2 * k + 2), torch.cuda.current_stream().cuda_stream))
         return out
 
     def stage(self, query, liked_rows, weights, exclude_rows, k, kc):
@@ -139,10 +139,17 @@ class CudaShardBackend:
         return out
 
     def fetch(self, packed: torch.Tensor, k: int):
-        res = unpack_result(packed.cpu().numpy(), k)
-        if self.exchange == "p2p" and int(self._err.item()) != 0:
-            raise RuntimeError(f"peer {int(self._err.item()) - 1} did not deliver its result to the exchange kernel")
-        return res
+        """ONE pinned D2H copy of the packed result (and, on the P2P path, its trailing error word), then a stream sync."""
+        n = packed.numel()
+        host = self._host.get(n)
+        if host is None:
+            host = self._host[n] = torch.empty(n, dtype=torch.int64).pin_memory()
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        words = host.numpy()
+        if n == 2 * k + 3 and int(words[2 * k + 2:].view(np.int32)[0]) != 0:
+            raise RuntimeError(f"peer {int(words[2 * k + 2:].view(np.int32)[0]) - 1} did not deliver its result to the exchange kernel")
+        return unpack_result(words, k)
 
 
 class ShardedCatalog:
@@ -293,7 +300,15 @@ class ShardedCatalog:
                     raise ValueError("Found array with 0 sample(s): a user has no liked movies in the catalog")
                 qn32, qn64, qbf = store.build_profiles(
                     lp, liked_col, liked_w, reduce_fn=lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group))
-            ctx = self.batch_context(qbf, qn64, k, excl_ptr, excl_col, row_filter)
+            try:
+                ctx = self.batch_context(qbf, qn64, k, excl_ptr, excl_col, row_filter)
+            except nat.NativeError as e:
+                if e.code != nat.ERR_UNSUPPORTED:
+                    raise
+                ctx = None           # shard too small for the tensor-core scheme (same verdict on every rank: equal shard sizes)
+            if ctx is None:
+                return self._recommend_batch_loop(queries, liked_ptr, liked_col, liked_w, excl_ptr, excl_col, k, row_filter,
+                                                  return_info)
             self.batch_step(ctx)
             b, hb = ctx["b"], ctx["hb"]
             status = ctx["gathered"][:, 2 * b * k + hb:].contiguous().view(torch.int32)[:, :b].max(dim=0).values   # any rank unsure
@@ -314,4 +329,26 @@ class ShardedCatalog:
             rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
         if return_info:
             return rows, scores, counts, {"status": status}
+        return rows, scores, counts
+
+    def _recommend_batch_loop(self, queries, liked_ptr, liked_col, liked_w, excl_ptr, excl_col, k, row_filter, return_info):
+        """Small shards: every query of the batch goes through the sharded single-query path (identical on all ranks)."""
+        b = len(queries) if queries is not None else len(liked_ptr) - 1
+        rows = np.full((b, k), -1, dtype=np.int64)
+        scores = np.full((b, k), -np.inf, dtype=np.float64)
+        counts = np.zeros(b, dtype=np.int32)
+        ecp = None if excl_ptr is None else np.asarray(excl_ptr, dtype=np.int64)
+        eca = None if excl_col is None else np.asarray(excl_col)
+        lpn = None if liked_ptr is None else np.asarray(liked_ptr, dtype=np.int64)
+        for u in range(b):
+            ex = None if ecp is None else eca[ecp[u]:ecp[u + 1]]
+            if queries is not None:
+                r, sc = self.recommend(query=np.asarray(queries[u]), exclude_rows=ex, k=k, row_filter=row_filter)
+            else:
+                lw = None if liked_w is None else np.asarray(liked_w)[lpn[u]:lpn[u + 1]]
+                r, sc = self.recommend(liked_rows=np.asarray(liked_col)[lpn[u]:lpn[u + 1]], weights=lw, exclude_rows=ex, k=k,
+                                       row_filter=row_filter)
+            rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
+        if return_info:
+            return rows, scores, counts, {"status": np.zeros(b, dtype=np.int32), "plan": None}
         return rows, scores, counts

@@ -9,6 +9,33 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _run_guarded(name, rank, world, port, *args):
+    """Picklable worker entry (spawn): runs the named worker; an exception becomes a queue item, so the parent fails at
+    once instead of waiting for a timeout."""
+    import traceback
+    out_q = args[-1]
+    try:
+        globals()[name](rank, world, port, *args)
+    except BaseException:  # noqa: BLE001
+        out_q.put((rank, "ERROR", traceback.format_exc()))
+        raise
+
+
+def _collect(out_q, procs, world, timeout=300):
+    results = []
+    for _ in range(world):
+        item = out_q.get(timeout=timeout)
+        if len(item) >= 2 and item[1] == "ERROR":
+            for p in procs:
+                p.kill()
+            pytest.fail(f"worker {item[0]} raised:\n{item[2]}")
+        results.append(item)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return results
+
+
 def _worker(rank, world, port, n, d, dtype, out_q):
     import torch.distributed as dist
     from robot_ebert_b200 import synth
@@ -42,13 +69,10 @@ def test_sharded_equals_single_gpu(dtype):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     out_q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, d, dtype, out_q)) for r in range(world)]
+    procs = [ctx.Process(target=_run_guarded, args=("_worker", r, world, port, n, d, dtype, out_q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [out_q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    results = _collect(out_q, procs, world)
     store = CatalogStore.synthetic(0, n, d, dtype, scale_rows=True, device="cuda:0")
     q = synth.query_f32(1, d)
     excl = np.random.default_rng(3).choice(n, size=133, replace=False)
@@ -106,13 +130,10 @@ def test_sharded_batch_equals_single_gpu_batch():
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     out_q = ctx.Queue()
-    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, n, d, b, k, out_q)) for r in range(world)]
+    procs = [ctx.Process(target=_run_guarded, args=("_batch_worker", r, world, port, n, d, b, k, out_q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [out_q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    results = _collect(out_q, procs, world)
     store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True, device="cuda:0")
     lp, lc, ep, ec = _csr_users(n, b)
     from robot_ebert_b200 import RowFilter, synth
@@ -162,15 +183,40 @@ def test_sharded_mass_ties_use_the_exact_sweep():
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     out_q = ctx.Queue()
-    procs = [ctx.Process(target=_tie_worker, args=(r, world, port, out_q)) for r in range(world)]
+    procs = [ctx.Process(target=_run_guarded, args=("_tie_worker", r, world, port, out_q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [out_q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    results = _collect(out_q, procs, world)
     m = synth.catalog_rows_f32(0, 0, 3000, 1, scale_rows=True).astype(np.float64)
     want_rows, want_scores = ora.query_rows(m, np.ones(1), np.arange(0, 3000, 7), 10)
     for rank, rows, scores, proven in results:
         assert proven and rows == want_rows.tolist(), rank
         np.testing.assert_allclose(scores, want_scores, rtol=1e-12)
+
+
+def test_sharded_batch_small_shards_fall_back_to_single_query_path():
+    """Shards below the tensor-core path's minimum size: recommend_batch must still answer (per-query sharded path)."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    from robot_ebert_b200 import CatalogStore, RowFilter, synth
+    n, d, b, k = 9_000 * world, 128, 6, 10
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    procs = [ctx.Process(target=_run_guarded, args=("_batch_worker", r, world, port, n, d, b, k, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = _collect(out_q, procs, world)
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True, device="cuda:0")
+    lp, lc, ep, ec = _csr_users(n, b)
+    g, y = synth.movie_metadata(3, 0, n)
+    store.set_metadata(g, y)
+    want = store.recommend_batch(liked_ptr=lp, liked_col=lc, excl_ptr=ep, excl_col=ec, k=k,
+                                 row_filter=RowFilter(genre_any=0b1011, year_lo=1960, year_hi=2000))
+    for rank, rows, scores, counts in results:
+        assert rows == want[0].tolist() and counts == want[2].tolist(), rank
+        np.testing.assert_allclose(scores, want[1], rtol=1e-12)
