@@ -242,7 +242,7 @@ def run_b200(args):
 
     from robot_ebert_b200 import CatalogStore, synth
     from robot_ebert_b200 import _native as nat
-    from robot_ebert_b200.sharding import CudaShardBackend, ShardedCatalog
+    from robot_ebert_b200.sharding import ShardedCatalog
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

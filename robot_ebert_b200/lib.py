@@ -12,7 +12,7 @@ module globals (constants.py:26-56: SQL engine, chat engine, the embeddings Data
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Protocol, Sequence, Tuple
+from typing import List, Optional, Protocol, Sequence, Tuple
 
 import numpy as np
 
