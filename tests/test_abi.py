@@ -101,3 +101,13 @@ def test_c_abi_argument_validation_without_a_gpu():
         nat.check(nat.ERR_INVALID)
     with pytest.raises(nat.NativeError):
         nat.check(nat.ERR_UNSUPPORTED)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent CPU / PyTorch fallback: without the built .so the product import path raises."""
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", str(tmp_path / "librebert_b200.so"))
+    with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
+        nat.load()
+    monkeypatch.undo()
+    assert nat.load().rebert_abi_version() == 1
