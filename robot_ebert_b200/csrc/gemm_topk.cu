@@ -815,8 +815,12 @@ extern "C" {
 
 REBERT_API int rebert_gemm_plan(int64_t n, int32_t b, int32_t k, rebert_gemm_plan_t* plan) {
     REBERT_REQUIRE(plan && n > 0 && b > 0 && k > 0, "gemm_plan: bad arguments");
-    const int kc = rebert_candidates_for_k(k);
-    if (kc == 0) { set_error("gemm_plan: k=%d unsupported", k); return REBERT_ERR_UNSUPPORTED; }
+    // Candidates for the exact pass.  The proof margin here must absorb the bf16 rounding of the query (sigma ~ 3e-5 at
+    // d = 1536), so the list keeps >= 25 % more than k (the gap between the k-th and the 1.25k-th best of a large catalog
+    // is ~1e-3); k itself must stay within what the single-query re-run path can serve.
+    if (rebert_candidates_for_k(k) == 0) { set_error("gemm_plan: k=%d unsupported", k); return REBERT_ERR_UNSUPPORTED; }
+    int need = k + 16 > k + (k + 3) / 4 ? k + 16 : k + (k + 3) / 4;
+    const int kc = (need + 31) / 32 * 32;
     // Expected survivors per query E = rank * n / sample_rows.  Want E >= 8 kc (the kc best are then inside with
     // overwhelming probability: the survivor count is Gamma(rank)-distributed around E) plus headroom for excluded
     // rows, which tend to score high; and E <= n / 64 so a thread stages ~4 keys per tile on average (24 slots).

@@ -96,6 +96,8 @@ def test_c_abi_argument_validation_without_a_gpu():
     assert lib.rebert_gemm_plan(1000, 16, 10, C.byref(plan)) == nat.ERR_UNSUPPORTED and b"too small" in lib.rebert_last_error()
     assert lib.rebert_gemm_plan(1_000_000, 4096, 100, C.byref(plan)) == nat.OK
     assert (plan.kc, plan.sample_rank, plan.cand_cap) == (128, 16, 4096) and plan.sample_rows % 256 == 0
+    assert lib.rebert_gemm_plan(1_000_000, 64, 240, C.byref(plan)) == nat.OK and plan.kc == 320
+    assert lib.rebert_gemm_plan(1_000_000, 64, 50, C.byref(plan)) == nat.OK and plan.kc == 96
     assert lib.rebert_gemm_plan(1_000_000, 4096, 5000, C.byref(plan)) == nat.ERR_UNSUPPORTED
     with pytest.raises(ValueError):
         nat.check(nat.ERR_INVALID)
