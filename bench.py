@@ -362,8 +362,9 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16 storage, fp32 accumulate, fp64 re-score", "data": "synthetic",
+            "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(rows), "rows": rows, "dim": DIM, "k": K, "exclusions": N_EXCL,
+                       "arithmetic": "bf16 catalog, fp32 accumulate in the streaming kernel, fp64 exact pass over the candidates",
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                        "exchange": (("fused P2P store+flag+merge kernel over NVLink peer memory" if sharded.backend.exchange == "p2p"
                                      else "NCCL all-gather + merge kernel") if world > 1 else None),
