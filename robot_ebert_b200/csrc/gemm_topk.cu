@@ -5,23 +5,29 @@
 // rebert_gemm_topk (everything enqueued on the caller's stream):
 //
 //   1. gemm<STORE>  over a strided SAMPLE of row tiles  -> sample scores [B, S]            (~1.5 % of the flops)
-//   2. select_threshold: per query, mask excluded sample rows, radix-select the r-th largest -> tau[q]
-//      (a lower bound of the query's k-th best that leaves ~8*kc rows above it in expectation)
-//   3. gemm<FILTER> over ALL row tiles: epilogue scales by inv_norm, compares with tau[q] (one FSETP per score,
-//      predicated smem staging, one atomicAdd per thread per tile) and appends (score,row) keys to cand[q]
-//   4. select_candidates: per query, drop excluded rows, bitonic top-kc of the few hundred survivors
+//   2. select_threshold: per query, knock out excluded / predicate-filtered sample rows, take the 16-th largest
+//      (thread-maxima pruning, radix select as fallback) -> tau[q]: a lower bound of the query's k-th best that leaves
+//      ~max(8 kc, 1024) rows above it in expectation
+//   3. gemm<FILTER> over ALL row tiles: the epilogue scales by inv_norm (NaN for rows the batch predicate drops), compares
+//      a whole 32-column chunk with tau[q] through a max tree (one compare per chunk), stages the rare winners in smem
+//      and appends (score,row) keys to cand[q] with one atomicAdd per thread per tile
+//   4. select_candidates: per query, drop excluded rows, bucket-select + small bitonic sort -> best kc keys
 //   5. finalize_topk (csrc/finalize.cu): fp64 re-score, (score desc, row asc), best k, proof margin
-//   status[q] != 0 tells the caller to re-run that query through the single-query kernel (threshold too
-//   optimistic, buffer overflow or margin below eps) — exactness never depends on the sample being lucky.
+//   status[q] != 0 tells the caller to re-run that query through the single-query kernel (threshold too optimistic,
+//   staging / buffer overflow, margin below eps or a sub-4-ulp gap) — exactness never depends on the sample being lucky.
 //
-// GEMM kernel anatomy (one CTA per SM, persistent, 192 threads):
-//   warp 0  : TMA producer  - cp.async.bulk.tensor.2d (SWIZZLE_128B) of Q tile [128 x 64] and row tile [256 x 64]
-//             per k-block into a 4-stage smem ring (48 KB / stage), mbarrier complete_tx
-//   warp 1  : MMA issuer    - one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) x4 per
-//             k-block, tcgen05.commit frees the smem stage; accumulators double-buffered in TMEM (2 x 256 columns)
-//   warps 2-5: epilogue     - tcgen05.ld 32x32b.x32 (thread = query row, 32 catalog columns per load), scale, filter
-//   Tile order: row-tile-major over (row tile, query tile) so concurrently running CTAs share the same catalog tile
-//   in L2 and the catalog streams from HBM once; Q (12.6 MB at B=4096) stays L2-resident.
+// Two GEMM kernels share the epilogue (epilogue_tile):
+//   gemm2_kernel (B > 128, the normal case): cluster of 2 CTAs = one SM pair per 256-query x 256-row tile,
+//     tcgen05.mma.cta_group::2 M=256 N=256 K=16, each CTA stages its 128-query half of A and its 128-row half of B
+//     (32 KB / stage, 6 stages) with cp.async.bulk.tensor.2d.cta_group::2 completing on the leader's mbarrier; commits
+//     are multicast to both CTAs; the peer's epilogue releases the accumulator with a remote mbarrier.arrive.
+//   gemm_kernel (B <= 128): one CTA per SM, cta_group::1 M=128 N=256, 4 stages of 48 KB.
+//   Both: 192 threads = warp 0 TMA producer (one lane), warp 1 MMA issuer (one lane) + TMEM allocator, warps 2-5
+//   epilogue (thread = query row; tcgen05.ld 32x32b.x32 software-pipelined against the previous chunk's math);
+//   fp32 accumulators double-buffered in TMEM (2 x 256 columns); K-major SWIZZLE_128B smem descriptors.
+//   Tile order is row-tile-major so the CTAs of a wave share catalog tiles in L2 (the catalog streams from HBM about
+//   once) and Q (12.6 MB at B = 4096) stays L2-resident (evict_last).
+//   Measured (profiles/r01_gemm2_filter_1M_ncu_summary.md): tensor pipe 97 % active, 1607 TFLOP/s.
 #include <cuda.h>
 #include <stdlib.h>
 
