@@ -113,3 +113,21 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         nat.load()
     monkeypatch.undo()
     assert nat.load().rebert_abi_version() == 1
+
+
+def test_header_is_plain_c_and_library_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (-pedantic) and a C program must link and run against the
+    shared library without Python or C++ in the picture."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "c_embed")
+    libdir = os.path.dirname(nat.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"),
+           os.path.join(REPO, "examples", "c_embed.c"), "-o", exe, "-L", libdir, "-lrebert_b200", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "c_embed ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
