@@ -269,3 +269,31 @@ def test_large_k_route(n, d, k):
     rows, scores = store.recommend(liked_rows=rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1], exclude_rows=rated, k=k)
     want_rows, want_scores = ora.recommend_rows(m, rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1], rated, k)
     np.testing.assert_array_equal(rows, want_rows)
+
+
+def test_plain_c_program_serves_a_request(tmp_path):
+    """examples/c_embed.c built with -DWITH_CUDA: a C program (no Python, no torch) builds a catalog with the library's
+    kernels and serves one request with host buffers through rebert_recommend_host; same rows/scores as the Python path."""
+    import os
+    import shutil
+    import subprocess
+    from robot_ebert_b200 import _native as nat
+    gcc, cuda = shutil.which("gcc"), "/usr/local/cuda"
+    if gcc is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(nat.LIB_PATH)
+    exe = str(tmp_path / "c_embed")
+    cmd = [gcc, "-std=c99", "-Wall", "-DWITH_CUDA", "-I", os.path.join(repo, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(repo, "examples", "c_embed.c"), "-o", exe, "-L", libdir, "-lrebert_b200", "-L", os.path.join(cuda, "lib64"),
+           "-lcudart", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n, d, k = 200_000, 1536, 10
+    r = subprocess.run([exe, str(n), str(d), str(k)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    got = [(int(l.split()[1]), float(l.split()[3])) for l in r.stdout.splitlines() if l.startswith("row ")]
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    rows, scores = store.recommend(query=synth.query_f32(1, d), exclude_rows=np.arange(0, 700, 7), k=k)
+    assert [g[0] for g in got] == rows.tolist() and "margin_ok 1" in r.stdout
+    np.testing.assert_allclose([g[1] for g in got], scores, rtol=1e-15)
