@@ -114,6 +114,39 @@ def unpack_result(words: np.ndarray, k: int):
     return words[:cnt].copy(), words[k:k + cnt].view(np.float64).copy(), margin
 
 
+def large_k_search(count, sweep, k: int, eps: float):
+    """Exact top-k for k beyond the register-list kernel (k > 240), on one shard or across shards.
+
+    count(thr) -> number of allowed rows whose fast score >= thr;  sweep(thr) -> (global rows int64, exact fp64 scores) of
+    those rows, or None on overflow.  Bisection finds a threshold that at least k (and at most ~2k) rows reach; the
+    collected rows are ordered by (exact score desc, row asc) and the threshold is lowered until the k-th exact score
+    clears it by 2 eps (eps = bound on |fast - exact|) — then no row outside the collected set can belong to the top-k."""
+    total = count(-2.0)                                   # every allowed row (scores live in [-1, 1])
+    if total <= k:
+        thr = -2.0
+    else:
+        lo, hi = -2.0, 1.5                                # count(lo) >= k, count(hi) = 0
+        for _ in range(40):
+            mid = 0.5 * (lo + hi)
+            c = count(mid)
+            if c >= k:
+                lo = mid
+                if c <= 2 * k:
+                    break
+            else:
+                hi = mid
+        thr = lo
+    while True:
+        res = sweep(thr)
+        if res is None:
+            raise RuntimeError("large-k sweep overflow: more than SWEEP_CAP rows within the threshold band")
+        rr, sc = res
+        order = np.lexsort((rr, -sc))[:k]
+        if len(rr) >= total or len(order) < k or sc[order[-1]] - 2.0 * eps > thr:
+            return rr[order], sc[order]
+        thr = float(sc[order[-1]]) - 4.0 * eps - 1e-6     # k-th exact score too close to the cut: widen
+
+
 class CatalogStore:
     """One catalog shard in HBM: rows [n, ld] (fp32 or bf16), fp32 inv_norm[n], fp64 norm64[n].
 
@@ -301,51 +334,29 @@ class CatalogStore:
         return rr[order], sc[order]
 
     def _recommend_large_k(self, lib, query, liked_rows, weights, exclude_rows, k, row_filter):
-        """k > 240: find by bisection a fast-score threshold that at least k allowed rows reach (count-only sweeps), collect
-        those rows, re-score them in fp64 and keep lowering the threshold until the k-th exact score clears it by 2 eps —
-        then no row outside the collected set can belong to the top-k."""
+        """k > 240: see large_k_search — count-only sweeps for the bisection, then collect + fp64 re-score."""
         if liked_rows is not None and len(liked_rows) == 0:
             raise ValueError("Found array with 0 sample(s): user has no liked movies in the catalog")
         if k > self.SWEEP_CAP // 2:
             raise ValueError(f"k={k} is too large (limit {self.SWEEP_CAP // 2})")
         with torch.cuda.device(self.device):
             excl_ptr, ne = self.stage_inputs(query, liked_rows, weights, exclude_rows, 1, 32)
-            s = self._scratch()
-            f = self._filter_struct(row_filter) or nat.Filter()
-            if ne:
-                f.exclude_rows, f.n_exclude = excl_ptr, ne
-            dummy = torch.empty(1, dtype=torch.int32, device=self.device)
-            cnt_t = torch.zeros(1, dtype=torch.int32, device=self.device)
+            return large_k_search(lambda thr: self.count_above(thr, excl_ptr, ne, row_filter),
+                                  lambda thr: self.sweep_above(thr, excl_ptr, ne, row_filter), k, self.fast_eps)
 
-            def count(thr):
-                nat.check(lib.rebert_collect_above(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), C.c_float(thr), dummy.data_ptr(), 1,
-                                                   cnt_t.data_ptr(), torch.cuda.current_stream().cuda_stream))
-                return int(cnt_t.item())
-
-            total = count(-2.0)                                   # every allowed row (scores live in [-1, 1])
-            if total <= k:
-                thr = -2.0
-            else:
-                lo, hi = -2.0, 1.5                                # count(lo) >= k, count(hi) = 0
-                for _ in range(40):
-                    mid = 0.5 * (lo + hi)
-                    c = count(mid)
-                    if c >= k:
-                        lo = mid
-                        if c <= 2 * k:
-                            break
-                    else:
-                        hi = mid
-                thr = lo
-            while True:
-                res = self.sweep_above(thr, excl_ptr, ne, row_filter)
-                if res is None:
-                    raise RuntimeError("large-k sweep overflow: more than SWEEP_CAP rows within the threshold band")
-                rr, sc = res
-                order = np.lexsort((rr, -sc))[:k]
-                if len(rr) >= total or len(order) < k or sc[order[-1]] - 2.0 * self.fast_eps > thr:
-                    return rr[order], sc[order]
-                thr = float(sc[order[-1]]) - 4.0 * self.fast_eps - 1e-6   # k-th exact score too close to the cut: widen
+    def count_above(self, threshold: float, excl_ptr=None, n_excl: int = 0, row_filter: Optional[RowFilter] = None) -> int:
+        """Number of allowed rows of this shard whose fast score >= threshold (count-only sweep; query / profile from this
+        thread's scratch)."""
+        lib = nat.load()
+        s = self._scratch()
+        f = self._filter_struct(row_filter) or nat.Filter()
+        if n_excl:
+            f.exclude_rows, f.n_exclude = excl_ptr, n_excl
+        dummy = torch.empty(1, dtype=torch.int32, device=self.device)
+        cnt_t = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nat.check(lib.rebert_collect_above(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), C.c_float(threshold), dummy.data_ptr(), 1,
+                                           cnt_t.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return int(cnt_t.item())
 
     def sweep_above(self, threshold: float, excl_ptr=None, n_excl: int = 0, row_filter: Optional[RowFilter] = None):
         """(global rows int64, exact fp64 scores) of every allowed row of this shard whose fast score >= threshold, for

@@ -40,6 +40,7 @@ struct GemvParams {
     uint64_t*    cand_keys; // [kc] final output
     unsigned*    counter;   // CTAs finished (zero before launch; the last CTA resets it)
     unsigned*    ghint;     // grid-wide threshold hint, orderable fp32 bits (zero before launch; reset with the counter)
+    int          cta_hint;  // 1 = CTA-level quantile hint from the warps' (kc/8)-th best keys (default; 0 is a tuning knob)
     int          merge_cap; // keys the final merge may hold in shared memory (power of two)
 };
 
@@ -98,6 +99,24 @@ struct WarpTopK {
         thr = last ? key_score(last) : -INFINITY;
     }
 };
+
+// After an insert: publish the two lower bounds of the kc-th best score this warp can now vouch for (see the kernel).
+//   * its own threshold, once its list is full (kc rows of this warp reach it);
+//   * the CTA-wide quantile bound: min over the 8 warps of their (kc/8)-th best score (kc rows of this CTA reach it).
+// s_wq entries only grow, so a stale read only yields a smaller, still valid bound.
+template <int QLANE>
+__device__ __forceinline__ void publish_hints(uint64_t key0, float thr, int warp, int lane, int cta_hint, unsigned* s_hint,
+                                              unsigned* s_wq) {
+    if (lane == 0 && thr > -INFINITY) atomicMax(s_hint, f32_orderable(thr));
+    if (cta_hint && lane == QLANE && key0 != 0) {
+        const unsigned mine = (unsigned)(key0 >> 32);
+        ((volatile unsigned*)s_wq)[warp] = mine;
+        unsigned mn = mine;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) mn = min(mn, ((volatile unsigned*)s_wq)[w]);
+        if (mn) atomicMax(s_hint, mn);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Final merge, run by the LAST CTA to finish (no second launch): `lists` sorted lists of kc keys -> best kc.
@@ -199,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     constexpr int RPW = 32 / LANES;              // rows a warp scores at once
     constexpr bool kRegQ = CPL > 0;              // query chunks live in registers
     constexpr int QREGS = kRegQ ? CPL * EPC : 1;
+    constexpr int kQuantLane = 4 * M - 1;        // list entry kc/8 - 1 lives in keys[0] of this lane (kc = 32 M)
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int row_bytes = p.ld * (int)sizeof(T);
@@ -235,8 +255,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     // Threshold hints.  A warp whose list is full has kc rows scoring >= its threshold, so that value bounds the global
     // kc-th best from below and every other warp may drop rows strictly below it (>= keeps equal scores, whose row
     // order is decided later).  Best value per CTA in shared memory, and sparsely grid-wide through one global word.
+    // A second, much tighter bound feeds the same word: once every consumer warp holds kc/8 keys, the smallest of the
+    // warps' (kc/8)-th best scores is reached by 8 * kc/8 = kc distinct allowed rows of this CTA, so it too bounds the
+    // kc-th best from below — and it tracks the kc-th best of ALL rows the CTA has seen, not of one warp's eighth of them.
+    // It is recomputed only by a warp that has just inserted (the rare path); the per-tile cost stays one shared load.
     __shared__ unsigned s_hint;
+    __shared__ unsigned s_wq[kConsumerWarps];   // orderable score of warp w's (kc/8)-th best key, 0 = not there yet
     if (threadIdx.x == 0) s_hint = 0u;
+    if (threadIdx.x < kConsumerWarps) s_wq[threadIdx.x] = 0u;
     __syncthreads();
 
     if (warp == kConsumerWarps) {
@@ -348,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                     const uint32_t lr = (uint32_t)(row0 + base + src / LANES);
                     if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) {
                         top.insert(make_key(sc, lr), lane);
-                        if (lane == 0 && top.thr > -INFINITY) atomicMax(&s_hint, f32_orderable(top.thr));
+                        publish_hints<kQuantLane>(top.keys[0], top.thr, warp, lane, p.cta_hint, &s_hint, s_wq);
                     }
                 }
                 unsigned mb = __ballot_sync(0xffffffffu, vB && cl == 0 && sb > top.thr && sb >= hint);
@@ -359,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                     const uint32_t lr = (uint32_t)(row0 + base + kConsumerWarps * RPW + src / LANES);
                     if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) {
                         top.insert(make_key(sc, lr), lane);
-                        if (lane == 0 && top.thr > -INFINITY) atomicMax(&s_hint, f32_orderable(top.thr));
+                        publish_hints<kQuantLane>(top.keys[0], top.thr, warp, lane, p.cta_hint, &s_hint, s_wq);
                     }
                 }
             }
@@ -570,6 +596,8 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.cta_lists = (uint64_t*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
     p.counter = (unsigned*)(p.cta_lists + (size_t)num_sms() * kc);
     p.ghint = p.counter + 1;
+    p.cta_hint = 1;
+    if (const char* e = getenv("REBERT_GEMV_CTA_HINT")) p.cta_hint = atoi(e) != 0;                                                    // tools/tune_gemv.py
     p.cand_keys = cand_keys;
     p.merge_cap = g.merge_cap;
 

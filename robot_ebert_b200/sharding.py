@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import _native as nat
-from .catalog import CatalogStore, RowFilter, sorted_csr, unpack_result
+from .catalog import CatalogStore, RowFilter, large_k_search, sorted_csr, unpack_result
 
 
 class ShardPlan:
@@ -120,6 +120,10 @@ class CudaShardBackend:
         ptr, ne = self._excl
         return self.store.sweep_above(threshold, ptr, ne, row_filter)
 
+    def count_local(self, threshold: float, row_filter: Optional[RowFilter]) -> int:
+        ptr, ne = self._excl
+        return self.store.count_above(threshold, ptr, ne, row_filter)
+
     def local_topk(self, k: int, kc: int, row_filter: Optional[RowFilter]) -> torch.Tensor:
         ptr, ne = self._excl
         return self.store.enqueue_topk(k, kc, ptr, ne, row_filter)
@@ -195,9 +199,13 @@ class ShardedCatalog:
             raise ValueError("pass exactly one of query / liked_rows")
         lib = nat.load()
         kc = lib.rebert_candidates_for_k(k)
-        if kc == 0:
-            raise ValueError(f"k={k} is outside the supported range (1..240)")
         eps = getattr(getattr(self.backend, "store", None), "fast_eps", 0.0)
+        if kc == 0:
+            # k beyond the register-list kernel (k > 240): sharded threshold bisection + sweep, still exact (slower route)
+            rows, scores = self._recommend_large_k(query, liked_rows, weights, exclude_rows, k, row_filter, eps)
+            if return_info:
+                return rows, scores, {"kc": 0, "margin": float("inf"), "proven_exact": True, "exact_sweep": True}
+            return rows, scores
         while True:
             partial = self.backend.stage(query, liked_rows, weights, exclude_rows, k, kc)
             if partial is not None:
@@ -219,28 +227,59 @@ class ShardedCatalog:
             return rows, scores, {"kc": kc, "margin": margin, "proven_exact": proven, "exact_sweep": swept}
         return rows, scores
 
+    def _recommend_large_k(self, query, liked_rows, weights, exclude_rows, k, row_filter, eps):
+        """Sharded form of CatalogStore._recommend_large_k.  The bisection runs on the all-reduced count, so every rank
+        takes the same branches and the collectives stay aligned; the survivors are all-gathered and ordered alike."""
+        if liked_rows is not None and len(liked_rows) == 0:
+            raise ValueError("Found array with 0 sample(s): user has no liked movies in the catalog")
+        if k > CatalogStore.SWEEP_CAP // 2:
+            raise ValueError(f"k={k} is too large (limit {CatalogStore.SWEEP_CAP // 2})")
+        partial = self.backend.stage(query, liked_rows, weights, exclude_rows, 1, 32)
+        if partial is not None:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
+            self.backend.set_profile(partial)
+        dev = self.backend.device
+
+        def count(thr):
+            c = torch.tensor([self.backend.count_local(thr, row_filter)], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM, group=self.group)
+            return int(c.item())
+
+        return large_k_search(count, lambda thr: self._sweep_gather(thr, row_filter), k, eps)
+
     def _exact_sweep(self, threshold: float, k: int, row_filter):
         """Sharded form of the exact fallback: local sweeps, one all-gather of the (padded) survivors, same order on every rank."""
+        res = self._sweep_gather(threshold, row_filter)
+        if res is None or len(res[0]) < k:
+            return None
+        rr, sc = res
+        order = np.lexsort((rr, -sc))[:k]
+        return rr[order], sc[order]
+
+    def _sweep_gather(self, threshold: float, row_filter):
+        """(global rows, exact fp64 scores) of every allowed row of ANY shard whose fast score >= threshold, identical on
+        every rank; None if some shard overflowed its sweep buffer."""
         local = self.backend.sweep_local(threshold, row_filter)
         dev = self.backend.device
         n_loc = torch.tensor([-1 if local is None else len(local[0])], dtype=torch.int64, device=dev)
         counts = torch.empty(self.world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(counts, n_loc, group=self.group)
         counts = counts.cpu().numpy()
-        if (counts < 0).any() or counts.sum() < k:
+        if (counts < 0).any():
             return None
         cap = int(counts.max())
+        if cap == 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float64)
         mine = torch.zeros(2 * cap, dtype=torch.int64, device=dev)
-        if cap and len(local[0]):
-            mine[:len(local[0])] = torch.from_numpy(local[0]).to(dev)
-            mine[cap:cap + len(local[0])] = torch.from_numpy(local[1].view(np.int64)).to(dev)
+        if len(local[0]):
+            mine[:len(local[0])] = torch.from_numpy(np.ascontiguousarray(local[0], dtype=np.int64)).to(dev)
+            mine[cap:cap + len(local[0])] = torch.from_numpy(np.ascontiguousarray(local[1], dtype=np.float64).view(np.int64)).to(dev)
         allr = torch.empty((self.world, 2 * cap), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allr.view(-1), mine, group=self.group)
         allr = allr.cpu().numpy()
         rr = np.concatenate([allr[g, :counts[g]] for g in range(self.world)])
         sc = np.concatenate([allr[g, cap:cap + counts[g]].view(np.float64) for g in range(self.world)])
-        order = np.lexsort((rr, -sc))[:k]
-        return rr[order], sc[order]
+        return rr, sc
 
     # ------------------------------------------------------------------ batched (tensor-core) path ----------
     def batch_context(self, qbf: torch.Tensor, qn64: torch.Tensor, k: int, excl_ptr=None, excl_col=None, row_filter=None):

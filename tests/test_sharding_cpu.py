@@ -36,6 +36,7 @@ class OracleShardBackend:
         from oracle.reference_scoring import _normalize_rows
         self.unit = _normalize_rows(m_local)
         self.row0, self.n, self.d = row0, m_local.shape[0], m_local.shape[1]
+        self.device = torch.device("cpu")
 
     def stage(self, query, liked_rows, weights, exclude_rows, k, kc):
         self.excl = None if exclude_rows is None else np.asarray(exclude_rows, dtype=np.int64)
@@ -53,6 +54,22 @@ class OracleShardBackend:
     def set_profile(self, summed):
         s = summed.numpy()
         self.vec = s[:self.d] / (s[self.d] / self._world)
+
+    def _allowed_scores(self):
+        scores = self.unit @ self.vec
+        ok = np.ones(self.n, dtype=bool)
+        if self.excl is not None:
+            ok[self.excl[(self.excl >= self.row0) & (self.excl < self.row0 + self.n)] - self.row0] = False
+        return scores, ok
+
+    def count_local(self, threshold, row_filter):
+        scores, ok = self._allowed_scores()
+        return int(np.count_nonzero(ok & (scores >= threshold)))
+
+    def sweep_local(self, threshold, row_filter):
+        scores, ok = self._allowed_scores()
+        rows = np.nonzero(ok & (scores >= threshold))[0]
+        return rows.astype(np.int64) + self.row0, scores[rows]
 
     def local_topk(self, k, kc, row_filter):
         from oracle.reference_scoring import topk_rows
@@ -103,7 +120,12 @@ def _worker(rank, world, port, n, d, out_q):
         (rated, rts), = synth.user_ratings(2, n, 1, mean_rated=60)
         liked = rated[rts >= 3.5]
         r2 = sc.recommend(liked_rows=liked, exclude_rows=rated, k=25)
-        out_q.put((rank, r1[0].tolist(), r1[1].tolist(), r2[0].tolist(), r2[1].tolist()))
+        # k beyond the register-list kernel: sharded threshold bisection + sweep (query form, then profile form with
+        # fewer allowed rows than k)
+        r3 = sc.recommend(query=q, exclude_rows=excl, k=300)
+        r4 = sc.recommend(liked_rows=liked, exclude_rows=np.setdiff1d(np.arange(n), np.arange(0, n, 11)), k=400)
+        out_q.put((rank, r1[0].tolist(), r1[1].tolist(), r2[0].tolist(), r2[1].tolist(), r3[0].tolist(), r3[1].tolist(),
+                   r4[0].tolist(), r4[1].tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -129,7 +151,15 @@ def test_two_rank_gloo_matches_unsharded_oracle():
     want1 = ora.query_rows(m, q, excl, 10)
     (rated, rts), = synth.user_ratings(2, n, 1, mean_rated=60)
     want2 = ora.recommend_rows(m, rated[rts >= 3.5], rated, 25)
-    for rank, r1_rows, r1_scores, r2_rows, r2_scores in results:
+    want3 = ora.query_rows(m, q, excl, 300)
+    allowed4 = np.arange(0, n, 11)
+    want4 = ora.recommend_rows(m, rated[rts >= 3.5], np.setdiff1d(np.arange(n), allowed4), 400)
+    assert len(want3[0]) == 300 and len(want4[0]) == len(allowed4) < 400
+    for rank, r1_rows, r1_scores, r2_rows, r2_scores, r3_rows, r3_scores, r4_rows, r4_scores in results:
+        assert r3_rows == want3[0].tolist(), rank
+        np.testing.assert_allclose(r3_scores, want3[1], rtol=1e-12)
+        assert r4_rows == want4[0].tolist(), rank
+        np.testing.assert_allclose(r4_scores, want4[1], rtol=1e-12)
         assert r1_rows == want1[0].tolist(), rank
         np.testing.assert_allclose(r1_scores, want1[1], rtol=1e-12)
         assert r2_rows == want2[0].tolist(), rank
