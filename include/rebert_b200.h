@@ -121,8 +121,9 @@ REBERT_API int rebert_profile_finalize(const double* sum64, const double* wsum, 
 /* ---- single query: fused score + mask + top-k (lib.py:51-55, L = 1 or a prebuilt profile) -- */
 /* Candidate count the fast pass keeps for a request of k: a multiple of 32 >= k + margin; 0 if k is unsupported. */
 REBERT_API int32_t rebert_candidates_for_k(int32_t k);
-/* The workspace must be ZERO-FILLED once before its first use (it holds a ticket counter that every launch leaves at
- * zero again); after that it can be reused by consecutive calls on the same stream without further clearing. */
+/* The workspace must be ZERO-FILLED once before its first use (it holds a ticket counter, a tile-claim counter and a
+ * threshold word that every launch leaves at zero again); after that it can be reused by consecutive calls on the
+ * same stream without further clearing. */
 REBERT_API size_t  rebert_gemv_workspace_bytes(int64_t n, int32_t kc);
 /* Fast pass.  score(r) = <qn32, row r> * inv_norm[r] in fp32; keeps the kc best allowed rows of the shard.
  * Output: cand_keys[kc] sorted best-first (packed (score, local row) keys; unused slots are 0). */

@@ -40,6 +40,9 @@ struct GemvParams {
     uint64_t*    cand_keys; // [kc] final output
     unsigned*    counter;   // CTAs finished (zero before launch; the last CTA resets it)
     unsigned*    ghint;     // grid-wide threshold hint, orderable fp32 bits (zero before launch; reset with the counter)
+    unsigned*    tile_ctr;  // tail tiles claimed so far (zero before launch; reset with the counter)
+    int64_t      static_rounds;  // every CTA takes tiles blockIdx.x + i * grid for i < static_rounds, the rest are claimed
+    unsigned long long* trace;  // tuning only (REBERT_GEMV_TRACE): [grid + 1][8] %globaltimer stamps, or nullptr
     int          cta_hint;  // 1 = CTA-level quantile hint from the warps' (kc/8)-th best keys (default; 0 is a tuning knob)
     int          merge_cap; // keys the final merge may hold in shared memory (power of two)
 };
@@ -127,6 +130,13 @@ __device__ __forceinline__ void publish_hints(uint64_t key0, float thr, int warp
 // input (mass ties) overflows the buffer, a chunked full sort over all keys is used instead.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t ldcg_u64(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define REBERT_TRACE(slot) do { if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 8 + (slot)] = globaltimer_ns(); } while (0)
 
 __device__ void chunked_merge(const uint64_t* __restrict__ in, int total, int kc, int cap, uint64_t* buf,
                               uint64_t* __restrict__ out) {
@@ -234,6 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     const int32_t* excl_s = excl_staged ? excl_smem : nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    REBERT_TRACE(0);                                   // kernel entry
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -261,19 +272,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     // It is recomputed only by a warp that has just inserted (the rare path); the per-tile cost stays one shared load.
     __shared__ unsigned s_hint;
     __shared__ unsigned s_wq[kConsumerWarps];   // orderable score of warp w's (kc/8)-th best key, 0 = not there yet
+    __shared__ int s_tile[kMaxStages];          // tile held by each stage, written by the producer before it arms the barrier
     if (threadIdx.x == 0) s_hint = 0u;
     if (threadIdx.x < kConsumerWarps) s_wq[threadIdx.x] = 0u;
     __syncthreads();
+    REBERT_TRACE(1);                                   // prologue done
 
     if (warp == kConsumerWarps) {
         // ===================== producer warp: one elected lane issues the bulk copies =====================
         if (lane == 0) {
             const uint64_t policy = p.l2_policy == 0 ? l2_policy_evict_first() : (p.l2_policy == 2 ? l2_policy_evict_last() : l2_policy_evict_normal());
+            // SMs do not stream at the same speed (measured: equal shares finish up to 10 % apart), so only the first
+            // `static_rounds` rounds are dealt out statically (tile = blockIdx.x + i * grid); the tail tiles are claimed
+            // one by one from a grid-wide counter.  Four claims are kept in flight — the first four issued right here —
+            // so a claim's L2 round trip is never waited for.  A CTA's tiles still ascend (WarpTopK::insert relies on it).
+            const int64_t tail0 = p.static_rounds * (int64_t)gridDim.x;      // first dynamically claimed tile
+            const bool has_tail = tail0 < p.num_tiles;
+            unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            if (has_tail) {
+                c0 = atomicAdd(p.tile_ctr, 1u); c1 = atomicAdd(p.tile_ctr, 1u);
+                c2 = atomicAdd(p.tile_ctr, 1u); c3 = atomicAdd(p.tile_ctr, 1u);
+            }
             int it = 0;
-            for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            auto issue = [&](int64_t t) {
                 const int s = it % p.stages;
                 const uint32_t round = (uint32_t)(it / p.stages);
                 mbar_wait(&empty_bar[s], (round & 1u) ^ 1u);
+                ++it;
+                if (t >= p.num_tiles) {                                      // tell the consumers there is nothing more
+                    s_tile[s] = -1;
+                    mbar_arrive(&full_bar[s]);
+                    return false;
+                }
+                s_tile[s] = (int)t;
                 const int64_t row0 = t * p.tile_rows;
                 const int64_t left = p.n - row0;
                 const int nrows = left < p.tile_rows ? (int)left : p.tile_rows;
@@ -283,6 +314,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                 mbar_arrive_expect_tx(&full_bar[s], bytes + ibytes);
                 bulk_g2s(dst, (const unsigned char*)p.rows + row0 * row_bytes, bytes, &full_bar[s], policy);
                 if (ibytes) bulk_g2s(dst + tile_bytes, p.inv_norm + row0, ibytes, &full_bar[s], policy);
+                return true;
+            };
+            bool more = true;
+            for (int64_t i = 0; i < p.static_rounds && more; ++i) more = issue(blockIdx.x + i * (int64_t)gridDim.x);
+            if (more && !has_tail) more = issue(p.num_tiles);                // static only: post the end marker
+            while (more) {
+                if (!(more = issue(tail0 + c0))) break;
+                c0 = atomicAdd(p.tile_ctr, 1u);
+                if (!(more = issue(tail0 + c1))) break;
+                c1 = atomicAdd(p.tile_ctr, 1u);
+                if (!(more = issue(tail0 + c2))) break;
+                c2 = atomicAdd(p.tile_ctr, 1u);
+                if (!(more = issue(tail0 + c3))) break;
+                c3 = atomicAdd(p.tile_ctr, 1u);
             }
         }
     } else {
@@ -299,14 +344,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
         const int cpl = kRegQ ? CPL : p.cpl;
         const int row_chunks = cpl * LANES;
 
-        int it = 0;
-        for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        for (int it = 0;; ++it) {
             const int s = it % p.stages;
             const uint32_t round = (uint32_t)(it / p.stages);
-            const int64_t row0 = t * p.tile_rows;
-            const int64_t left = p.n - row0;
-            const int nrows = left < p.tile_rows ? (int)left : p.tile_rows;
-            const int nrows4 = nrows & ~3;
             const unsigned char* st = stage_base + (size_t)s * stage_stride;
             const uint4* tile = (const uint4*)st;
             const float* inv_s = (const float*)(st + tile_bytes);
@@ -321,6 +361,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
             const float hint = hb ? orderable_f32(hb) : -INFINITY;
 
             mbar_wait(&full_bar[s], round & 1u);
+            if (it == 0) REBERT_TRACE(2);              // first tile landed
+            const int64_t t = s_tile[s];               // which tile the producer put into this stage (-1: none left)
+            if (t < 0) break;
+            const int64_t row0 = t * p.tile_rows;
+            const int64_t left = p.n - row0;
+            const int nrows = left < p.tile_rows ? (int)left : p.tile_rows;
+            const int nrows4 = nrows & ~3;
 
             // two row groups per step for ILP: rows rA and rB = rA + kConsumerWarps*RPW
             for (int base = warp * RPW; base < nrows; base += 2 * kConsumerWarps * RPW) {
@@ -395,7 +442,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     }
 
     // ===================== CTA merge: 8 sorted warp lists -> one sorted list of kc keys =====================
+    if (warp == 0) REBERT_TRACE(3);                    // warp 0 finished its last tile
     __syncthreads();   // every stage has been consumed; the pipeline memory is free to reuse
+    REBERT_TRACE(4);                                   // all warps finished
     uint64_t* lists = (uint64_t*)smem;           // [kConsumerWarps][kc]
     const int kc = p.kc;
     if (warp < kConsumerWarps) {
@@ -431,12 +480,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
+    REBERT_TRACE(5);                                   // CTA list written
     if (threadIdx.x == 0) s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     final_merge(p.cta_lists, (int)gridDim.x, kc, p.merge_cap, (uint64_t*)smem, p.cand_keys);
-    if (threadIdx.x == 0) { *p.counter = 0; *p.ghint = 0u; }
+    if (p.trace && threadIdx.x == 0) { p.trace[(size_t)gridDim.x * 8] = globaltimer_ns(); p.trace[(size_t)gridDim.x * 8 + 1] = blockIdx.x; }
+    if (threadIdx.x == 0) { *p.counter = 0; *p.ghint = 0u; *p.tile_ctr = 0u; }
 }
 
 // ---------------------------------------------------------------- host side ----------------------------------
@@ -596,6 +647,19 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.cta_lists = (uint64_t*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
     p.counter = (unsigned*)(p.cta_lists + (size_t)num_sms() * kc);
     p.ghint = p.counter + 1;
+    p.tile_ctr = p.counter + 2;
+    {
+        // share of the tiles claimed dynamically at the end (balances SMs of unequal speed); 0 = all static
+        int dyn_pct = 12;
+        if (const char* e = getenv("REBERT_GEMV_DYN_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) dyn_pct = v; }                  // tools/probe_knobs.py
+        const int64_t rounds = (p.num_tiles + g.grid - 1) / g.grid;       // static schedule would need this many
+        int64_t sr = rounds - (rounds * dyn_pct + 99) / 100;
+        if (dyn_pct == 0) sr = rounds;
+        if (sr < 1) sr = 1;                                               // the first tile is always blockIdx.x
+        p.static_rounds = sr;
+    }
+    p.trace = nullptr;
+    if (const char* e = getenv("REBERT_GEMV_TRACE")) p.trace = (unsigned long long*)strtoull(e, nullptr, 0);                          // tools/trace_gemv.py
     p.cta_hint = 1;
     if (const char* e = getenv("REBERT_GEMV_CTA_HINT")) p.cta_hint = atoi(e) != 0;                                                    // tools/tune_gemv.py
     p.cand_keys = cand_keys;

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B probe of the GEMV hint knob (REBERT_GEMV_CTA_HINT).
+"""A/B probe of the GEMV knobs (REBERT_GEMV_CTA_HINT, REBERT_GEMV_DYN_PCT).
 
 For every (rows, k) case: times rebert_gemv_topk by CUDA events under each knob combination, interleaved in rounds so
 that clock drift hits all combinations alike, and checks that the candidate keys are identical under all of them
@@ -16,7 +16,14 @@ cases = [(1_250_000, "bf16", 10), (1_000_000, "bf16", 10), (1_000_000, "bf16", 1
          (1_250_000, "bf16", 50), (10_000_000, "bf16", 10), (10_000_000, "bf16", 100)]
 if len(sys.argv) > 1:
     cases = [c for c in cases if c[0] <= int(sys.argv[1])]
-combos = [0, 1]
+combos = ["hint0_dyn12", "hint1_dyn0", "hint1_dyn6", "hint1_dyn12", "hint1_dyn25", "hint1_dyn100"]
+
+
+def apply(combo):
+    h, d = combo.split("_")
+    os.environ["REBERT_GEMV_CTA_HINT"] = h[4:]
+    os.environ["REBERT_GEMV_DYN_PCT"] = d[3:]
+
 out = []
 stores = {}
 for n, dtype, K in cases:
@@ -37,12 +44,12 @@ for n, dtype, K in cases:
         nat.check(lib.rebert_gemv_topk(C.byref(store._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(), s.ws.numel(),
                                        s.cand.data_ptr(), st))
 
-    iters = 30 if n >= 5_000_000 else 200
+    iters = 25 if n >= 5_000_000 else 150
     times = {c: [] for c in combos}
     keys = {}
-    for rnd in range(6):
+    for rnd in range(4):
         for hint in (combos if rnd % 2 == 0 else combos[::-1]):     # alternate the order: no combination always runs first
-            os.environ["REBERT_GEMV_CTA_HINT"] = str(hint)
+            apply(hint)
             for _ in range(5):
                 gemv()
             torch.cuda.synchronize()
@@ -59,10 +66,10 @@ for n, dtype, K in cases:
     res = {"rows": n, "dtype": dtype, "k": K, "kc": kc, "identical_candidates": bool(same),
            "ideal_us_at_7TBs": round(n * 1536 * esz / 7.0e12 * 1e6, 1)}
     for c in combos:
-        res[f"us_ctahint{c}_min"] = round(min(times[c]), 2)
-        res[f"us_ctahint{c}_median"] = round(float(np.median(times[c])), 2)
+        res[f"us_{c}"] = [round(min(times[c]), 2), round(float(np.median(times[c])), 2)]      # [min, median] over the rounds
     out.append(res)
     print(json.dumps(res), flush=True)
 os.environ.pop("REBERT_GEMV_CTA_HINT", None)
+os.environ.pop("REBERT_GEMV_DYN_PCT", None)
 with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "knobs.json"), "w") as fh:
     json.dump(out, fh, indent=1)

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Where does a GEMV launch spend its time?  Per-CTA %globaltimer stamps (REBERT_GEMV_TRACE = device buffer address):
+0 kernel entry, 1 prologue done, 2 first tile landed, 3 warp 0 finished its last tile, 4 all warps finished,
+5 CTA list written; extra row: end of the last CTA's final merge.  Prints the spread of every stamp relative to the
+earliest kernel entry, for a few launches back to back, beside the CUDA-event time of the same launches."""
+import ctypes as C, json, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from robot_ebert_b200 import CatalogStore, synth, _native as nat
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_250_000
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+lib = nat.load(); dev = torch.device("cuda:0")
+store = CatalogStore.synthetic(0, n, 1536, "bf16", device=dev)
+q = synth.query_f32(1, 1536); excl = np.random.default_rng(1).choice(n, size=133, replace=False)
+kc = lib.rebert_candidates_for_k(K)
+ptr, ne = store.stage_inputs(q, None, None, excl, K, kc)
+s = store._scratch(); f = nat.Filter(); f.exclude_rows, f.n_exclude = ptr, ne
+st = torch.cuda.current_stream().cuda_stream
+def gemv(): nat.check(lib.rebert_gemv_topk(C.byref(store._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(), s.ws.numel(), s.cand.data_ptr(), st))
+sms = torch.cuda.get_device_properties(dev).multi_processor_count
+L = 6
+bufs = [torch.zeros((sms + 1) * 8, dtype=torch.int64, device=dev) for _ in range(L)]
+for _ in range(20): gemv()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for i in range(L):
+    os.environ["REBERT_GEMV_TRACE"] = hex(bufs[i].data_ptr())
+    gemv()
+b.record(); torch.cuda.synchronize()
+os.environ.pop("REBERT_GEMV_TRACE")
+print(json.dumps({"rows": n, "k": K, "event_us_per_launch": round(a.elapsed_time(b) / L * 1e3, 2)}))
+names = ["entry", "prologue_done", "first_tile", "warp0_done", "all_warps_done", "list_written"]
+prev_end = None
+for i in range(L):
+    t = bufs[i].cpu().numpy().reshape(sms + 1, 8)
+    t0 = t[:sms, 0].min()
+    row = {"launch": i}
+    if prev_end is not None:
+        row["gap_from_prev_end_us"] = round((t0 - prev_end) / 1e3, 2)
+    for j, nm in enumerate(names):
+        v = (t[:sms, j] - t0) / 1e3
+        row[nm] = [round(float(v.min()), 2), round(float(np.median(v)), 2), round(float(v.max()), 2)]
+    row["final_merge_end"] = round(float(t[sms, 0] - t0) / 1e3, 2)
+    prev_end = t[sms, 0]
+    print(json.dumps(row))
