@@ -165,11 +165,21 @@ __device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int
     const int total = lists * kc;
     if (threadIdx.x == 0) { s_t0 = 0; s_t1 = 0; s_cnt = 0; }
     __syncthreads();
-    // T0
+    // T0 and the prefix set of T1 come from the same round of loads (every L2 round trip here is on the critical path
+    // of the whole launch: the other CTAs have already gone)
+    const int P = (kc + lists - 1) / lists;
+    const int S = P * lists;                       // kc <= S < kc + lists <= cap
     unsigned long long t0 = 0;
     for (int l = threadIdx.x; l < lists; l += blockDim.x) {
         const unsigned long long v = ldcg_u64(lists_g + (size_t)l * kc + kc - 1);
         t0 = v > t0 ? v : t0;
+    }
+    for (int e0 = threadIdx.x; e0 < S; e0 += 2 * blockDim.x) {
+        const int e1 = e0 + blockDim.x;
+        const uint64_t v0 = ldcg_u64(lists_g + (size_t)(e0 / P) * kc + (e0 % P));
+        const uint64_t v1 = e1 < S ? ldcg_u64(lists_g + (size_t)(e1 / P) * kc + (e1 % P)) : 0;
+        buf[e0] = v0;
+        if (e1 < S) buf[e1] = v1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -177,11 +187,8 @@ __device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int
         t0 = v > t0 ? v : t0;
     }
     if ((threadIdx.x & 31) == 0 && t0) atomicMax(&s_t0, t0);
-    // T1: prefix set of P keys per list, rank-count for the kc-th largest
-    const int P = (kc + lists - 1) / lists;
-    const int S = P * lists;                       // kc <= S < kc + lists <= cap
-    for (int e = threadIdx.x; e < S; e += blockDim.x) buf[e] = ldcg_u64(lists_g + (size_t)(e / P) * kc + (e % P));
     __syncthreads();
+    // T1: rank-count for the kc-th largest of the prefix set
     for (int e = threadIdx.x; e < S; e += blockDim.x) {
         const uint64_t key = buf[e];
         if (key == 0) continue;
@@ -191,16 +198,17 @@ __device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int
     }
     __syncthreads();
     const uint64_t T = s_t0 > s_t1 ? s_t0 : s_t1;
-    // gather survivors (loads issued four at a time so their L2 latencies overlap)
-    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
-        uint64_t kk[4];
+    // gather survivors (loads issued sixteen at a time so their L2 latencies overlap: 148 lists of 32 keys = one round)
+    constexpr int kInFlight = 16;
+    for (int i0 = threadIdx.x; i0 < total; i0 += kInFlight * blockDim.x) {
+        uint64_t kk[kInFlight];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kInFlight; ++j) {
             const int i = i0 + j * blockDim.x;
             kk[j] = i < total ? ldcg_u64(lists_g + i) : 0;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kInFlight; ++j) {
             if (kk[j] != 0 && kk[j] >= T) {
                 const int idx = atomicAdd(&s_cnt, 1);
                 if (idx < cap) buf[idx] = kk[j];
@@ -447,19 +455,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     REBERT_TRACE(4);                                   // all warps finished
     uint64_t* lists = (uint64_t*)smem;           // [kConsumerWarps][kc]
     const int kc = p.kc;
+    __shared__ int s_kept[kConsumerWarps];       // non-empty entries of each warp list
     if (warp < kConsumerWarps) {
+        int kept = 0;
 #pragma unroll
-        for (int m = 0; m < M; ++m) lists[warp * kc + m * 32 + lane] = top.keys[m];
+        for (int m = 0; m < M; ++m) {
+            lists[warp * kc + m * 32 + lane] = top.keys[m];
+            kept += __popc(__ballot_sync(0xffffffffu, top.keys[m] != 0));
+        }
+        if (lane == 0) s_kept[warp] = kept;
     }
     __syncthreads();
     uint64_t* out = p.cta_lists + (size_t)blockIdx.x * kc;
     int total = 0;
-    for (int w = 0; w < kConsumerWarps; ++w) {   // non-empty entries per list (lists are sorted, zeros last)
-        const uint64_t* L = lists + w * kc;
-        int lo = 0, hi = kc;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (L[mid] != 0) lo = mid + 1; else hi = mid; }
-        total += lo;
-    }
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) total += s_kept[w];
     for (int i = threadIdx.x; i < kConsumerWarps * kc; i += blockDim.x) {
         const uint64_t key = lists[i];
         if (key == 0) continue;
@@ -491,17 +501,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
 }
 
 // ---------------------------------------------------------------- host side ----------------------------------
+// Tuning knobs (tools/tune_gemv.py, tools/probe_knobs.py, tools/trace_gemv.py).  The environment is read ONCE, at the
+// first launch — getenv is a linear scan and this sits on the per-request path — unless REBERT_GEMV_TUNE is set at that
+// moment, in which case every launch re-reads it (what the tools do to sweep values inside one process).
+struct GemvKnobs {
+    int stage_bytes = kStageBytes;
+    int stages = 4;
+    int l2_policy = 0;
+    int cta_hint = 1;
+    int dyn_pct = 12;          // share of the tiles claimed dynamically at the end; 0 = all static
+    unsigned long long* trace = nullptr;
+};
+static GemvKnobs read_knobs() {
+    GemvKnobs k;
+    if (const char* e = getenv("REBERT_GEMV_STAGE_BYTES")) { int v = atoi(e); if (v >= 4096 && v <= 96 * 1024) k.stage_bytes = v; }
+    if (const char* e = getenv("REBERT_GEMV_STAGES")) { int v = atoi(e); if (v >= 1 && v <= kMaxStages) k.stages = v; }
+    if (const char* e = getenv("REBERT_GEMV_L2_POLICY")) k.l2_policy = atoi(e);
+    if (const char* e = getenv("REBERT_GEMV_CTA_HINT")) k.cta_hint = atoi(e) != 0;
+    if (const char* e = getenv("REBERT_GEMV_DYN_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) k.dyn_pct = v; }
+    if (const char* e = getenv("REBERT_GEMV_TRACE")) k.trace = (unsigned long long*)strtoull(e, nullptr, 0);
+    return k;
+}
+static GemvKnobs gemv_knobs() {
+    static const bool tuning = getenv("REBERT_GEMV_TUNE") != nullptr;
+    static const GemvKnobs cached = read_knobs();
+    return tuning ? read_knobs() : cached;
+}
+
 struct GemvLaunch {
     int grid, stages, tile_rows, merge_cap;
     size_t smem;
 };
 
-static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic, int n_exclude) {
+static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic, int n_exclude, const GemvKnobs& knobs) {
     GemvLaunch g;
     const int row_bytes = L.ld * L.esize;
     const int rpw = 32 / L.lanes;
-    int stage_bytes = kStageBytes;
-    if (const char* e = getenv("REBERT_GEMV_STAGE_BYTES")) { int v = atoi(e); if (v >= 4096 && v <= 96 * 1024) stage_bytes = v; }   // tools/tune_gemv.py
+    const int stage_bytes = knobs.stage_bytes;
     int tr = stage_bytes / row_bytes;
     const int unit = kConsumerWarps * rpw;           // rows one step of all warps covers
     if (tr >= 2 * unit) tr = (tr / (2 * unit)) * (2 * unit);
@@ -516,8 +552,7 @@ static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic,
     const int stage_stride = tile_bytes + ((tr * 4 + 127) & ~127);
     const size_t excl_bytes = (n_exclude > 0 && n_exclude <= kMaxExclSmem) ? (size_t)n_exclude * 4 : 0;
     const size_t fixed = 2 * kMaxStages * sizeof(uint64_t) + (generic ? (size_t)L.ld * 4 : 0) + excl_bytes + 128;
-    int stages = 4;
-    if (const char* e = getenv("REBERT_GEMV_STAGES")) { int v = atoi(e); if (v >= 1 && v <= kMaxStages) stages = v; }                  // tools/tune_gemv.py
+    int stages = knobs.stages;
     while (stages > 1 && (size_t)stages * stage_stride + fixed > 220 * 1024) --stages;
     g.stages = stages;
     g.smem = (size_t)stages * stage_stride + fixed;
@@ -629,7 +664,8 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     }
     const bool generic = use_generic(L);
     const int n_excl = (filter && filter->exclude_rows && filter->n_exclude > 0) ? filter->n_exclude : 0;
-    GemvLaunch g = plan_gemv(L, cat->n, kc, generic, n_excl);
+    const GemvKnobs knobs = gemv_knobs();
+    GemvLaunch g = plan_gemv(L, cat->n, kc, generic, n_excl, knobs);
     GemvParams p;
     p.rows = cat->rows;
     p.inv_norm = cat->inv_norm;
@@ -641,8 +677,7 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.num_tiles = (cat->n + g.tile_rows - 1) / g.tile_rows;
     p.stages = g.stages;
     p.kc = kc;
-    p.l2_policy = 0;
-    if (const char* e = getenv("REBERT_GEMV_L2_POLICY")) p.l2_policy = atoi(e);                                                       // tools/tune_gemv.py
+    p.l2_policy = knobs.l2_policy;
     p.filter = make_filter(filter, cat->row_base);
     p.cta_lists = (uint64_t*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
     p.counter = (unsigned*)(p.cta_lists + (size_t)num_sms() * kc);
@@ -650,18 +685,15 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.tile_ctr = p.counter + 2;
     {
         // share of the tiles claimed dynamically at the end (balances SMs of unequal speed); 0 = all static
-        int dyn_pct = 12;
-        if (const char* e = getenv("REBERT_GEMV_DYN_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) dyn_pct = v; }                  // tools/probe_knobs.py
+        const int dyn_pct = knobs.dyn_pct;
         const int64_t rounds = (p.num_tiles + g.grid - 1) / g.grid;       // static schedule would need this many
         int64_t sr = rounds - (rounds * dyn_pct + 99) / 100;
         if (dyn_pct == 0) sr = rounds;
         if (sr < 1) sr = 1;                                               // the first tile is always blockIdx.x
         p.static_rounds = sr;
     }
-    p.trace = nullptr;
-    if (const char* e = getenv("REBERT_GEMV_TRACE")) p.trace = (unsigned long long*)strtoull(e, nullptr, 0);                          // tools/trace_gemv.py
-    p.cta_hint = 1;
-    if (const char* e = getenv("REBERT_GEMV_CTA_HINT")) p.cta_hint = atoi(e) != 0;                                                    // tools/tune_gemv.py
+    p.trace = knobs.trace;
+    p.cta_hint = knobs.cta_hint;
     p.cand_keys = cand_keys;
     p.merge_cap = g.merge_cap;
 

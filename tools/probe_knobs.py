@@ -5,6 +5,7 @@ For every (rows, k) case: times rebert_gemv_topk by CUDA events under each knob 
 that clock drift hits all combinations alike, and checks that the candidate keys are identical under all of them
 (the knob may only change speed, never the result).  Prints one JSON document."""
 import ctypes as C, json, os, sys
+os.environ["REBERT_GEMV_TUNE"] = "1"          # make the library re-read its knobs at every launch
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

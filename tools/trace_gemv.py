@@ -4,6 +4,7 @@
 5 CTA list written; extra row: end of the last CTA's final merge.  Prints the spread of every stamp relative to the
 earliest kernel entry, for a few launches back to back, beside the CUDA-event time of the same launches."""
 import ctypes as C, json, os, sys
+os.environ["REBERT_GEMV_TUNE"] = "1"          # make the library re-read its knobs at every launch
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Tuning sweep of the GEMV streaming knobs (stage bytes / stages / L2 policy) on one catalog size."""
 import ctypes as C, json, os, sys
+os.environ["REBERT_GEMV_TUNE"] = "1"          # make the library re-read its knobs at every launch
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
