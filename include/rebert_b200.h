@@ -144,8 +144,11 @@ REBERT_API int rebert_recommend_host_scratch(const rebert_catalog_t* cat, int32_
                                              size_t* pinned_bytes, size_t* device_bytes);
 /* lib.py:43-55 for one request with HOST buffers: pass `query` [d] fp32 (not normalised) OR `liked_rows` (+ optional
  * weights), plus the sorted unique GLOBAL `exclude_rows`; device_filter may add device-resident bitmap / genre / year
- * tests.  Packs the request, ONE H2D copy, normalise or build the profile, fused score+mask+top-k, fp64 exact pass, ONE
- * D2H copy, and synchronises the stream.  out_rows / out_scores are host [k] (-1 / -inf padded), *out_count <= k.
+ * tests.  Packs the request into the pinned block; a raw query is read from there by the first kernel (zero-copy), a
+ * liked-rows request takes ONE H2D copy; then normalise or build the profile, fused score+mask+top-k, fp64 exact pass
+ * whose packed result the kernel writes straight into the pinned block (no D2H copy operation), and a stream
+ * synchronisation.  `pinned` must therefore be page-locked memory the device can address (cudaHostAlloc /
+ * cudaMallocHost / a pinned torch tensor).  out_rows / out_scores are host [k] (-1 / -inf padded), *out_count <= k.
  * Returns REBERT_ERR_INVALID with "Found array with 0 sample(s)" when liked_rows is given but empty (the reference's
  * own failure for a user without liked movies). */
 REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* query, const int32_t* liked_rows,
@@ -154,6 +157,17 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
                                      int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
                                      size_t device_bytes, int64_t* out_rows, double* out_scores, int32_t* out_count,
                                      double* out_margin, rebert_stream stream);
+
+/* The same call for ONE RANK of a row-sharded catalog (query requests): local fast + exact pass over this rank's shard,
+ * then the fused NVLink exchange + merge (rebert_exchange_merge, arguments as there: peer_buffers / world / rank / k_max /
+ * seq), whose merged result lands in the pinned block.  Every rank calls it with the same query, exclusions and seq and
+ * gets the same answer a single GPU would return; *out_margin is the smallest proof margin over the ranks. */
+REBERT_API int rebert_recommend_host_sharded(const rebert_catalog_t* cat, const float* query, const int32_t* exclude_rows,
+                                             int32_t n_exclude, const rebert_filter_t* device_filter, int32_t k, int32_t kc,
+                                             int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
+                                             size_t device_bytes, const uint64_t* peer_buffers, int32_t world, int32_t rank,
+                                             int32_t k_max, uint32_t seq, int64_t* out_rows, double* out_scores,
+                                             int32_t* out_count, double* out_margin, rebert_stream stream);
 
 /* ---- merge of per-shard results (lib.py:55 across shards) --------------------------------- */
 /* For each of b queries merge `lists` sorted result lists into the best k.  List l of query u is at
@@ -171,7 +185,8 @@ REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, cons
  * 2k+2 64-bit words: rows[k] | fp64 scores[k] | count | margin (what rebert_finalize_topk writes when its four outputs
  * point into one block).  seq is the call number, starting at 1 and incremented by every rank on every call.
  * The kernel stores the local block into every peer, publishes a flag, waits for all peers' flags and merges under
- * (score desc, row asc); *err_flag (device int32) becomes non-zero if a peer did not deliver within ~10 s. */
+ * (score desc, row asc); *err_flag (int32 in device or device-addressable pinned memory) becomes non-zero if a peer did
+ * not deliver within ~10 s.  out_packed may likewise point into pinned host memory. */
 REBERT_API size_t rebert_exchange_buffer_bytes(int32_t world, int32_t k_max);
 REBERT_API int rebert_exchange_merge(const uint64_t* peer_buffers, int32_t world, int32_t rank, int32_t k, int32_t k_max,
                                      uint32_t seq, const int64_t* local_packed, int64_t* out_packed, int32_t* err_flag,

@@ -54,6 +54,9 @@ _SIGS = {
     "rebert_recommend_host_scratch": (C.c_int, [C.POINTER(Catalog), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "rebert_recommend_host": (C.c_int, [C.POINTER(Catalog), _P, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(Filter), C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, _P, C.c_size_t, _P, C.c_size_t, _P, _P, _P, _P, _P]),
+    "rebert_recommend_host_sharded": (C.c_int, [C.POINTER(Catalog), _P, _P, C.c_int32, C.POINTER(Filter), C.c_int32, C.c_int32, C.c_int32,
+                                                _P, C.c_size_t, _P, C.c_size_t, _P, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
+                                                _P, _P, _P, _P, _P]),
     "rebert_merge_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "rebert_exchange_buffer_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rebert_exchange_merge": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P]),

@@ -6,6 +6,8 @@
 #include <mutex>
 #include <unordered_set>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rebert {
@@ -45,6 +47,10 @@ int raise_smem_limit_impl(const void* kern) {
     REBERT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem() - (int)a.sharedSizeBytes));
     done.insert(kern);
     return REBERT_OK;
+}
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("REBERT_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 int num_sms() {
     static int cached = 0;
@@ -169,6 +175,7 @@ __global__ void norms_kernel(const T* __restrict__ rows, int64_t n, int ld, floa
 __global__ void query_normalize_kernel(const float* __restrict__ q, int d, int ld, float* __restrict__ qn32,
                                        double* __restrict__ qn64, __nv_bfloat16* __restrict__ qnbf16) {
     __shared__ double red[32];
+    pdl_trigger();                                   // the scoring kernel may place its CTAs; it waits for our results
     const float* src = q + (int64_t)blockIdx.x * d;
     double acc = 0.0;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -192,6 +199,50 @@ __global__ void query_normalize_kernel(const float* __restrict__ q, int d, int l
         if (qn32) qn32[(int64_t)blockIdx.x * ld + c] = (float)v;
         if (qnbf16) qnbf16[(int64_t)blockIdx.x * ld + c] = __ushort_as_bfloat16(f32_to_bf16_rne((float)v));
     }
+}
+
+// Request staging for the host-buffer entry point: ONE CTA reads the raw query and the exclusion list straight from
+// the caller's pinned host block (zero-copy over PCIe, no copy-engine operation in front of the kernels), normalises the
+// query exactly as query_normalize_kernel does (same per-thread and reduction order => same bits) and drops the
+// exclusion list into device scratch for the scoring kernel.
+__global__ void __launch_bounds__(256) stage_query_kernel(const float* __restrict__ q_host, int d, int ld, float* __restrict__ qn32,
+                                                          double* __restrict__ qn64, const int32_t* __restrict__ excl_host,
+                                                          int n_excl, int32_t* __restrict__ excl_dev) {
+    extern __shared__ float s_src[];                 // [d]
+    __shared__ double red[32];
+    pdl_trigger();
+    pdl_wait();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) s_src[c] = q_host[c];
+    for (int c = threadIdx.x; c < n_excl; c += blockDim.x) excl_dev[c] = excl_host[c];
+    __syncthreads();
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        double x = (double)s_src[c];
+        acc = fma(x, x, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    double nrm = sqrt(red[0]);
+    if (nrm == 0.0) nrm = 1.0;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        double v = c < d ? (double)s_src[c] / nrm : 0.0;
+        qn64[c] = v;
+        qn32[c] = (float)v;
+    }
+}
+
+int stage_query_launch(const float* q_host, int d, int ld, float* qn32, double* qn64, const int32_t* excl_host, int n_excl,
+                       int32_t* excl_dev, cudaStream_t st) {
+    REBERT_CUDA(launch_pdl(stage_query_kernel, dim3(1), dim3(256), (size_t)d * sizeof(float), st, q_host, d, ld, qn32, qn64,
+                           excl_host, n_excl, excl_dev));
+    return REBERT_OK;
 }
 
 // One CTA per user.  The user's entries (local row, weight, row norm) are staged in shared memory in blocks; each

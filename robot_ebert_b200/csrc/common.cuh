@@ -32,6 +32,10 @@ int max_optin_smem();
 // memory), once per kernel.  Always the same constant, so concurrent callers cannot race each other's launches.
 int raise_smem_limit_impl(const void* kern);
 template <typename K> static inline int raise_smem_limit(K kern) { return raise_smem_limit_impl((const void*)kern); }
+bool pdl_enabled();
+// host_api.cu -> catalog.cu / finalize.cu (internal launchers)
+int stage_query_launch(const float* q_host, int d, int ld, float* qn32, double* qn64, const int32_t* excl_host, int n_excl,
+                       int32_t* excl_dev, cudaStream_t st);   // REBERT_PDL=0 switches programmatic dependent launch off (read once)
 
 // ---------------------------------------------------------------- layout --------------------
 // A stored row is LANES * CPL chunks of 16 bytes: LANES lanes of a warp each own CPL chunks.
@@ -145,6 +149,14 @@ template <> __device__ __forceinline__ double elem_f64<__nv_bfloat16>(const __nv
     return (double)__bfloat162float(row[c]);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The kernels of one request (normalize -> gemv_topk -> finalize -> exchange) run back to back on one stream.  Launched
+// with the programmatic-serialization attribute, a kernel's CTAs are placed and run their global-memory-free preamble
+// while the previous kernel drains; pdl_wait() then blocks until that kernel has completed and its writes are visible.
+// Rule kept by every kernel here: NO global memory access before pdl_wait().  pdl_trigger() lets the next kernel in.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- device: mbarrier / bulk copy
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -210,5 +222,24 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* a, int n) {
     }
 }
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// Launch `kern` so that it may start while the previous kernel of the stream is still draining (see pdl_wait above).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 
 }  // namespace rebert

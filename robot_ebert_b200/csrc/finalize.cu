@@ -72,6 +72,8 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
     __shared__ int s_neartie;
     const int u = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    pdl_trigger();
+    pdl_wait();                                      // the candidates come from the kernel launched just before
     const uint64_t* keys = cand_keys + (size_t)u * kc;
     const double* q = q64 + (size_t)u * ld;
     const int chunks = ld / EPC;
@@ -222,6 +224,8 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(PeerBufs peers, int
                                                              long long timeout_cycles) {
     const int words = 2 * k + 2;
     const int parity = (int)(seq & 1u);
+    pdl_trigger();
+    pdl_wait();                                      // `local` is written by the exact pass launched just before
     unsigned long long* mine = peers.p[my_rank];
     // (1) deliver my result to every rank (myself included)
     for (int i = threadIdx.x; i < world * words; i += blockDim.x) {
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(PeerBufs peers, int
         while (true) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
             if (v == (unsigned long long)seq) break;
-            if (clock64() - t0 > timeout_cycles) { atomicExch(err, 1 + threadIdx.x); break; }
+            if (clock64() - t0 > timeout_cycles) { *(volatile int*)err = 1 + threadIdx.x; break; }   // plain store: err may live in pinned host memory
             __nanosleep(64);
         }
     }
@@ -293,8 +297,8 @@ static int finalize_launch_t(const rebert_catalog_t* cat, const double* q64, con
     const size_t smem = (size_t)cat->ld * sizeof(double);
     auto kern = finalize_topk_kernel<T, DIV>;
     { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
-    kern<<<b, kFinalThreads, smem, st>>>((const T*)cat->rows, cat->norm64, cat->row_base, cat->ld, q64, cand_keys, kc, k, out_rows,
-                                         out_scores, out_count, out_margin);
+    REBERT_CUDA(launch_pdl(kern, dim3(b), dim3(kFinalThreads), smem, st, (const T*)cat->rows, cat->norm64, cat->row_base, cat->ld, q64,
+                           cand_keys, kc, k, out_rows, out_scores, out_count, out_margin));
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }
@@ -356,9 +360,8 @@ REBERT_API int rebert_exchange_merge(const uint64_t* peer_buffers, int32_t world
     // ~10 s of SM clocks at 2 GHz: only a dead peer gets here.  (A constant: querying the clock rate is a slow driver
     // call and this function sits on the per-request path.)
     const long long timeout_cycles = 20000000000ll;
-    exchange_merge_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pb, world, rank, k, 2 * k_max + 2, seq,
-                                                               (const unsigned long long*)local_packed,
-                                                               (unsigned long long*)out_packed, err_flag, timeout_cycles);
+    REBERT_CUDA(launch_pdl(exchange_merge_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, pb, world, rank, k, 2 * k_max + 2, seq,
+                           (const unsigned long long*)local_packed, (unsigned long long*)out_packed, err_flag, timeout_cycles));
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }

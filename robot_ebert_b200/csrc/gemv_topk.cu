@@ -261,6 +261,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
         }
         fence_mbar_init();
     }
+    // Programmatic dependent launch: everything above touched shared memory only.  Let the next kernel of the stream
+    // place its CTAs as ours retire, then wait until the previous kernel (query normalisation / profile build / the
+    // previous request) has completed before the first global access.
+    pdl_trigger();
+    pdl_wait();
     if (!kRegQ) {
         for (int c = threadIdx.x; c < p.ld; c += blockDim.x) q_smem[c] = p.q[c];
     }
@@ -578,7 +583,7 @@ static int launch_gemv_m(const GemvParams& p, const GemvLaunch& g, int kc, cudaS
     {                                                                                                            \
         auto kern = gemv_topk_kernel<T, CPL, LANES, MM>;                                                         \
         { int rc__ = raise_smem_limit(kern); if (rc__ != REBERT_OK) return rc__; }       \
-        kern<<<g.grid, kThreads, g.smem, st>>>(p);                                                               \
+        REBERT_CUDA(launch_pdl(kern, dim3(g.grid), dim3(kThreads), g.smem, st, p));                             \
     }
     switch (kc) {
         case 32: REBERT_LAUNCH_M(1); break;

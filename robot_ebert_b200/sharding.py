@@ -100,6 +100,35 @@ class CudaShardBackend:
                                             out.data_ptr() + 8 * (2 * k + 2), torch.cuda.current_stream().cuda_stream))
         return out
 
+    def recommend_query_host(self, query, exclude_rows, k: int, kc: int, row_filter: Optional[RowFilter]):
+        """One C call for a query request on the P2P path (rebert_recommend_host_sharded): zero-copy request, local fast +
+        exact pass, fused exchange + merge, result written into pinned memory, one stream sync.  Collective in effect:
+        every rank must call it with the same arguments.  Returns (rows, scores, margin)."""
+        lib = nat.load()
+        st = self.store
+        s = st._scratch()
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        if q.shape != (st.d,):
+            raise ValueError(f"query must have shape ({st.d},)")
+        ex, ne = None, 0
+        if exclude_rows is not None and len(exclude_rows):
+            ex = np.unique(np.asarray(exclude_rows, dtype=np.int32))
+            ne = int(ex.shape[0])
+        s.ensure_host(0, ne, k)
+        f = st._filter_struct(row_filter)
+        cnt, margin = C.c_int32(0), C.c_double(0.0)
+        self._seq += 1
+        with torch.cuda.device(self.device):
+            rc = lib.rebert_recommend_host_sharded(
+                C.byref(st._c), q.ctypes.data, None if ex is None else ex.ctypes.data, ne, None if f is None else C.byref(f), k, kc,
+                s.ne_cap, s.hpin.data_ptr(), s.hpin.numel(), s.hdev.data_ptr(), s.hdev.numel(), self._peer_ptrs, self._p2p_world,
+                self._p2p_rank, self.K_MAX, self._seq & 0xFFFFFFFF or 1, s.h_rows.ctypes.data, s.h_scores.ctypes.data,
+                C.byref(cnt), C.byref(margin), torch.cuda.current_stream().cuda_stream)
+        nat.check(rc)
+        st.last_h2d_bytes = 4 * st.d + 4 * ne            # read by the staging kernel straight from the pinned block
+        n = cnt.value
+        return s.h_rows[:n].copy(), s.h_scores[:n].copy(), margin.value
+
     def stage(self, query, liked_rows, weights, exclude_rows, k, kc):
         st = self.store
         self._excl = st.stage_inputs(query, liked_rows, weights, exclude_rows, k, kc, profile_partial_only=True)
@@ -206,19 +235,26 @@ class ShardedCatalog:
             if return_info:
                 return rows, scores, {"kc": 0, "margin": float("inf"), "proven_exact": True, "exact_sweep": True}
             return rows, scores
+        fast_host = query is not None and getattr(self.backend, "exchange", "nccl") == "p2p"
         while True:
-            partial = self.backend.stage(query, liked_rows, weights, exclude_rows, k, kc)
-            if partial is not None:
-                dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
-                self.backend.set_profile(partial)
-            packed = self.enqueue(k, kc, row_filter)
-            rows, scores, margin = self.backend.fetch(packed, k)
+            if fast_host:
+                # query request on the P2P path: the whole step is ONE C call per rank (no torch ops, no NCCL)
+                rows, scores, margin = self.backend.recommend_query_host(query, exclude_rows, k, kc, row_filter)
+            else:
+                partial = self.backend.stage(query, liked_rows, weights, exclude_rows, k, kc)
+                if partial is not None:
+                    dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
+                    self.backend.set_profile(partial)
+                packed = self.enqueue(k, kc, row_filter)
+                rows, scores, margin = self.backend.fetch(packed, k)
             if margin > eps or kc >= 256:
                 break
             kc = min(256, kc * 4)
         proven, swept = margin > eps, False
         if not proven and len(rows) == k and hasattr(self.backend, "sweep_local"):
             # mass ties (see CatalogStore._exact_sweep): every rank sweeps its shard against the global k-th score
+            if fast_host:
+                self.backend.stage(query, None, None, exclude_rows, k, kc)     # the sweep reads the query from torch scratch
             res = self._exact_sweep(float(scores[k - 1]) - 2.0 * eps, k, row_filter)
             if res is not None:
                 rows, scores = res

@@ -50,7 +50,10 @@ def _worker(rank, world, port, n, d, dtype, out_q):
         r1 = sc.recommend(query=q, exclude_rows=excl, k=10)
         (rated, rts), = synth.user_ratings(2, n, 1)
         r2 = sc.recommend(liked_rows=rated[rts >= 3.5], exclude_rows=rated, k=50)
-        out_q.put((rank, r1[0].tolist(), r1[1].tolist(), r2[0].tolist(), r2[1].tolist()))
+        r3 = sc.recommend(query=q, exclude_rows=excl, k=300)                 # k > 240: sharded bisection + sweep route
+        r4 = sc.recommend(liked_rows=rated[rts >= 3.5], exclude_rows=rated, k=1000)
+        out_q.put((rank, r1[0].tolist(), r1[1].tolist(), r2[0].tolist(), r2[1].tolist(), r3[0].tolist(), r3[1].tolist(),
+                   r4[0].tolist(), r4[1].tolist()))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -79,10 +82,16 @@ def test_sharded_equals_single_gpu(dtype):
     w1 = store.recommend(query=q, exclude_rows=excl, k=10)
     (rated, rts), = synth.user_ratings(2, n, 1)
     w2 = store.recommend(liked_rows=rated[rts >= 3.5], exclude_rows=rated, k=50)
-    for rank, r1r, r1s, r2r, r2s in results:
+    w3 = store.recommend(query=q, exclude_rows=excl, k=300)
+    w4 = store.recommend(liked_rows=rated[rts >= 3.5], exclude_rows=rated, k=1000)
+    assert len(w3[0]) == 300 and len(w4[0]) == 1000
+    for rank, r1r, r1s, r2r, r2s, r3r, r3s, r4r, r4s in results:
         assert r1r == w1[0].tolist() and r2r == w2[0].tolist(), rank
         np.testing.assert_allclose(r1s, w1[1], rtol=1e-12)
         np.testing.assert_allclose(r2s, w2[1], rtol=1e-12)
+        assert r3r == w3[0].tolist() and r4r == w4[0].tolist(), rank
+        np.testing.assert_allclose(r3s, w3[1], rtol=1e-12)
+        np.testing.assert_allclose(r4s, w4[1], rtol=1e-12)
 
 
 def _batch_worker(rank, world, port, n, d, b, k, out_q):
