@@ -8,9 +8,15 @@
 //     registers, so the inner loop is conflict-free LDS.128 + FFMA and never touches global memory;
 //   * every warp keeps its running top-kc as packed 64-bit keys in registers (kc/32 per lane); a row is looked at
 //     again only if it beats the warp's threshold (one FSETP per row), and only then is the filter evaluated;
+//   * lower bounds of the kc-th best score ("hints") are shared inside the CTA and, sparsely, across the grid, so rows
+//     that cannot make the final list are dropped before the insert path: a full warp list's threshold, and the much
+//     tighter CTA-wide bound min over the 8 warps of their (kc/8)-th best score;
+//   * tiles: static rounds for the first 88 %, then the tail is claimed from a grid-wide counter (four claims in
+//     flight per producer), because SMs stream at unequal speeds and equal static shares finish up to 10 % apart;
 //   * at the end the 8 warp lists are rank-merged through shared memory into one sorted list per CTA, and the last
 //     CTA to finish (atomic ticket) merges the per-CTA lists behind two pruning thresholds — one launch per query.
-//     The N-long score vector never exists.
+//     The N-long score vector never exists;
+//   * launched with programmatic stream serialization: no global access before griddepcontrol.wait.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import _native as nat
-from .catalog import CatalogStore, RowFilter, large_k_search, sorted_csr, unpack_result
+from .catalog import CatalogStore, RowFilter, _on_device, large_k_search, sorted_csr, sorted_unique_i32, unpack_result
 
 
 class ShardPlan:
@@ -112,13 +112,13 @@ class CudaShardBackend:
             raise ValueError(f"query must have shape ({st.d},)")
         ex, ne = None, 0
         if exclude_rows is not None and len(exclude_rows):
-            ex = np.unique(np.asarray(exclude_rows, dtype=np.int32))
+            ex = sorted_unique_i32(exclude_rows)
             ne = int(ex.shape[0])
         s.ensure_host(0, ne, k)
         f = st._filter_struct(row_filter)
         cnt, margin = C.c_int32(0), C.c_double(0.0)
         self._seq += 1
-        with torch.cuda.device(self.device):
+        with _on_device(self.device):
             rc = lib.rebert_recommend_host_sharded(
                 C.byref(st._c), q.ctypes.data, None if ex is None else ex.ctypes.data, ne, None if f is None else C.byref(f), k, kc,
                 s.ne_cap, s.hpin.data_ptr(), s.hpin.numel(), s.hdev.data_ptr(), s.hdev.numel(), self._peer_ptrs, self._p2p_world,
