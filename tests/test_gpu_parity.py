@@ -297,3 +297,59 @@ def test_plain_c_program_serves_a_request(tmp_path):
     rows, scores = store.recommend(query=synth.query_f32(1, d), exclude_rows=np.arange(0, 700, 7), k=k)
     assert [g[0] for g in got] == rows.tolist() and "margin_ok 1" in r.stdout
     np.testing.assert_allclose([g[1] for g in got], scores, rtol=1e-15)
+
+
+_KNOB_SCRIPT = r"""
+import ctypes as C, json, os, sys
+os.environ["REBERT_GEMV_TUNE"] = "1"                      # the library re-reads its knobs at every launch
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch
+from robot_ebert_b200 import CatalogStore, synth, _native as nat
+lib = nat.load()
+out = {}
+for n, d, dtype, k in [(70_001, 1536, "bf16", 10), (70_001, 1536, "bf16", 100), (9_000, 1536, "fp32", 25), (40_000, 50, "fp32", 10)]:
+    store = CatalogStore.synthetic(0, n, d, dtype, scale_rows=True)
+    q = synth.query_f32(1, d)
+    excl = np.random.default_rng(1).choice(n, size=133, replace=False)
+    kc = lib.rebert_candidates_for_k(k)
+    ptr, ne = store.stage_inputs(q, None, None, excl, k, kc)
+    s = store._scratch()
+    f = nat.Filter(); f.exclude_rows, f.n_exclude = ptr, ne
+    keys = {}
+    for hint in ("0", "1"):
+        for dyn in ("0", "12", "50", "100"):
+            for stages in ("2", "4"):
+                os.environ.update(REBERT_GEMV_CTA_HINT=hint, REBERT_GEMV_DYN_PCT=dyn, REBERT_GEMV_STAGES=stages)
+                for _ in range(3):                              # repeated launches: the counters must be left at zero
+                    nat.check(lib.rebert_gemv_topk(C.byref(store._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
+                                                   s.ws.numel(), s.cand.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                keys[(hint, dyn, stages)] = s.cand.cpu().numpy().copy()
+    first = next(iter(keys.values()))
+    out[f"{n}x{d}:{dtype}:k{k}"] = {"identical": all(np.array_equal(first, v) for v in keys.values()),
+                                   "filled": int((first != 0).sum()), "kc": kc,
+                                   "digest": __import__("hashlib").sha1(first.tobytes()).hexdigest()}
+print(json.dumps(out))
+"""
+
+
+_KNOB_DIGESTS = {}
+
+
+@pytest.mark.parametrize("pdl", ["1", "0"])
+def test_scheduling_knobs_change_speed_never_results(pdl):
+    """Threshold hints, the static / dynamically claimed tile schedule, the pipeline depth and programmatic dependent
+    launch are speed knobs: the candidate keys must be bit-identical under every combination (own process: the
+    library reads its knobs at the first launch)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, REBERT_PDL=pdl)
+    r = subprocess.run([sys.executable, "-c", _KNOB_SCRIPT, repo], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(res) == 4
+    for case, v in res.items():
+        assert v["identical"] and v["filled"] == v["kc"], (case, v)
+        assert _KNOB_DIGESTS.setdefault(case, v["digest"]) == v["digest"], case      # ... and with PDL on or off
