@@ -55,7 +55,8 @@ typedef enum {
     REBERT_ERR_DEVICE = -5        /* not an sm_100 device */
 } rebert_status;
 
-typedef enum { REBERT_F32 = 0, REBERT_BF16 = 1 } rebert_dtype;
+/* REBERT_I8 is the dtype of a PREFILTER SHADOW only (rebert_catalog_quantize_i8): never the catalog of record. */
+typedef enum { REBERT_F32 = 0, REBERT_BF16 = 1, REBERT_I8 = 2 } rebert_dtype;
 
 typedef void* rebert_stream;      /* a cudaStream_t */
 
@@ -103,6 +104,17 @@ REBERT_API int rebert_catalog_store_rows(const float* src, int64_t n, int32_t d,
 /* Row norms of the STORED values: norm64[r] = sqrt(sum x^2) in fp64 (0 -> 1), inv_norm[r] = (float)(1/norm64[r]). */
 REBERT_API int rebert_catalog_norms(const void* rows, int64_t n, int32_t ld, int32_t dtype, float* inv_norm, double* norm64,
                          rebert_stream stream);
+
+/* Optional int8 PREFILTER SHADOW of a catalog: halves (bf16) or quarters (fp32) the bytes the single-query fast pass
+ * streams.  Row r is stored as q8[r, c] = rint(x[r, c] / s_r) with s_r = max|x[r, :]| / 127, and
+ * factor[r] = (float)(s_r / ||x_r||), so that  score~(r) = factor[r] * sum_c q8[r, c] * q_c  approximates the cosine.
+ * *out_max_err (device double) receives max_r ||x_r - s_r q8_r|| / ||x_r||: by Cauchy-Schwarz |score~ - score| <= that
+ * value for ANY unit query, a rigorous bound the caller adds to its proof margin.  The shadow is described by its own
+ * rebert_catalog_t {rows = out_rows, inv_norm = out_factor, norm64 = src->norm64, dtype = REBERT_I8, ld = layout of
+ * (d, REBERT_I8)} and is accepted by rebert_gemv_topk ONLY; candidates are always re-scored from the catalog of
+ * record by rebert_finalize_topk, so results never depend on the shadow's precision. */
+REBERT_API int rebert_catalog_quantize_i8(const rebert_catalog_t* src, void* out_rows, int32_t ld8, float* out_factor,
+                                          double* out_max_err, rebert_stream stream);
 
 /* ---- query / profile (lib.py:51-52) ------------------------------------------------------- */
 /* b queries q[b, d] fp32 -> unit vectors: qn64 = q / ||q|| (fp64, zero norm -> 1), qn32 = (float) qn64,

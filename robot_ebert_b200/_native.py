@@ -8,7 +8,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librebert_b200.so")
 
 F32, BF16 = 0, 1
-DTYPES = {"fp32": F32, "bf16": BF16}
+I8 = 2          # prefilter shadow only (rebert_catalog_quantize_i8)
+DTYPES = {"fp32": F32, "bf16": BF16, "i8": I8}
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_DEVICE = 0, -1, -2, -3, -4, -5
 
@@ -43,6 +44,7 @@ _SIGS = {
     "rebert_check_device": (C.c_int, []),
     "rebert_catalog_layout": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
     "rebert_catalog_store_rows": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
+    "rebert_catalog_quantize_i8": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, _P, _P]),
     "rebert_catalog_norms": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
     "rebert_query_normalize": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "rebert_profile_accumulate": (C.c_int, [C.POINTER(Catalog), _P, _P, _P, C.c_int32, _P, _P, _P]),

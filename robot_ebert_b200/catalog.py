@@ -196,6 +196,8 @@ class CatalogStore:
         self.elements_per_lane = epc if chunks <= 16 else (chunks // 32) * epc   # mirrors csrc row_layout()
         # fp32 error bound of the fast pass on a unit-vector dot
         self.fast_eps = float((self.elements_per_lane + 12) * 2.0 ** -24)
+        self._c8 = None            # int8 prefilter shadow (enable_prefilter)
+        self.q8_eps = float("inf")
 
     # ------------------------------------------------------------------ construction -----------
     @staticmethod
@@ -276,6 +278,31 @@ class CatalogStore:
             torch.cuda.current_stream().synchronize()
         return cls(rows, inv_norm, norm64, n, d, ld, dtype, row0 if row_base is None else row_base, None)
 
+    def enable_prefilter(self) -> float:
+        """Build the int8 PREFILTER SHADOW of this shard (n x ld8 bytes + one fp32 factor per row): the single-request fast
+        pass then streams 1 byte per element instead of 2 (bf16) or 4 (fp32), keeps 256 candidates, and the exact pass
+        re-scores them from the catalog of record as always.  Returns the proven bound on |shadow score - true score|:
+        max_r ||x_r - dequant(q8_r)|| / ||x_r|| (Cauchy-Schwarz, any unit query) plus the worst-case error of the two
+        int8 query planes.  A request whose proof margin does not clear that bound silently takes the standard path, so
+        results never depend on the shadow."""
+        lib = nat.load()
+        ld8, _ = self.layout(self.n, self.d, "i8")
+        with torch.cuda.device(self.device):
+            rows8 = torch.empty((max(self.n, 1), ld8), dtype=torch.int8, device=self.device)
+            factor = torch.empty(_align(max(self.n, 1), 4), dtype=torch.float32, device=self.device)
+            max_err = torch.zeros(1, dtype=torch.float64, device=self.device)
+            nat.check(lib.rebert_catalog_quantize_i8(C.byref(self._c), rows8.data_ptr(), ld8, factor.data_ptr(), max_err.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream))
+            row_err = float(max_err.item())
+        self._q8_rows, self._q8_factor = rows8, factor
+        self._c8 = nat.Catalog(rows=rows8.data_ptr(), inv_norm=factor.data_ptr(), norm64=self.norm64.data_ptr(), n=self.n,
+                               row_base=self.row_base, d=self.d, ld=ld8, dtype=nat.DTYPES["i8"], reserved=0)
+        # query planes: |q - (dh*hi + dl*lo)| <= dl/2 per element with dl = max|q| / (127*254) <= 1 / (127*254) for ||q|| <= 1
+        query_err = float(np.sqrt(self.d)) / (127.0 * 254.0 * 2.0)
+        self.q8_row_err = row_err
+        self.q8_eps = row_err + 1.01 * (1.0 + row_err) * query_err + 4e-6      # + fp32 rounding of factor / int->float / final products
+        return self.q8_eps
+
     def set_metadata(self, genre_bits: np.ndarray, year: np.ndarray) -> None:
         """Per-row side columns for the genre/year predicate (local row order)."""
         self.genre_bits = torch.from_numpy(np.ascontiguousarray(genre_bits, dtype=np.uint32).view(np.int32)).to(self.device)
@@ -301,7 +328,7 @@ class CatalogStore:
 
     def recommend(self, *, query: Optional[np.ndarray] = None, liked_rows: Optional[np.ndarray] = None,
                   weights: Optional[np.ndarray] = None, exclude_rows: Optional[np.ndarray] = None, k: int = 10,
-                  row_filter: Optional[RowFilter] = None, return_info: bool = False):
+                  row_filter: Optional[RowFilter] = None, return_info: bool = False, prefilter: Optional[bool] = None):
         """Top-k rows by cosine to `query`, or by mean cosine to `liked_rows` (lib.py:51-55).
 
         query        fp32 [D] host vector (not normalised), OR
@@ -309,6 +336,8 @@ class CatalogStore:
         exclude_rows global row ids that must not be returned (the user's rated movies, lib.py:48)
         Returns (rows int64[k'], scores float64[k']), k' = min(k, #allowed rows), ordered (score desc, row asc).
         Host buffers in, host buffers out: the H2D/D2H copies are part of the call.
+        prefilter: None = use the int8 shadow when enable_prefilter() has built one and k <= PREFILTER_MAX_K; True = try it
+        for any k <= 240; False = never.  The result is the same either way.
         """
         if (query is None) == (liked_rows is None):
             raise ValueError("pass exactly one of query / liked_rows")
@@ -324,6 +353,15 @@ class CatalogStore:
             if return_info:
                 return rows, scores, {"kc": 0, "margin": float("inf"), "proven_exact": True, "exact_sweep": True}
             return rows, scores
+        if prefilter and self._c8 is None:
+            raise ValueError("prefilter=True needs enable_prefilter()")
+        if self._c8 is not None and (prefilter or (prefilter is None and k <= self.PREFILTER_MAX_K)):
+            res = self._recommend_prefilter(lib, query, liked_rows, weights, exclude_rows, k, row_filter)
+            if res is not None:                        # proven on the shadow's candidates; otherwise fall through
+                rows, scores, margin = res
+                if return_info:
+                    return rows, scores, {"kc": 256, "margin": margin, "proven_exact": True, "exact_sweep": False, "prefilter": True}
+                return rows, scores
         while True:
             rows, scores, margin = self._recommend_once(lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter)
             if margin > self.fast_eps or kc >= 256:
@@ -343,6 +381,22 @@ class CatalogStore:
         if return_info:
             return rows, scores, {"kc": kc, "margin": margin, "proven_exact": proven, "exact_sweep": swept}
         return rows, scores
+
+    # 256 candidates absorb the shadow's proven error bound (~0.009 for gaussian rows) only while the k-th and the 256-th
+    # best scores are far enough apart; beyond k ~ 16 the proof usually fails and the attempt would be wasted work.
+    PREFILTER_MAX_K = 16
+
+    def _recommend_prefilter(self, lib, query, liked_rows, weights, exclude_rows, k, row_filter):
+        """Fast pass over the int8 shadow (256 candidates) + exact pass over the catalog of record.  Returns
+        (rows, scores, margin) when the margin proves the candidate set exact under the shadow's error bound, else None."""
+        with _on_device(self.device):
+            excl_ptr, ne = self.stage_inputs(query, liked_rows, weights, exclude_rows, k, 256)
+            s = self._scratch()
+            self.enqueue_topk(k, 256, excl_ptr, ne, row_filter, prefilter=True)
+            s.h_out.copy_(s.d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        rows, scores, margin = unpack_result(s.h_out_np, k)
+        return (rows, scores, margin) if margin > self.q8_eps else None
 
     SWEEP_CAP = 1 << 16
 
@@ -518,7 +572,8 @@ class CatalogStore:
         nat.check(lib.rebert_profile_finalize(s.sum64.data_ptr(), s.wsum.data_ptr(), 1, self.ld, s.qn32.data_ptr(),
                                               s.qn64.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
 
-    def enqueue_topk(self, k: int, kc: int, excl_ptr=None, n_excl: int = 0, row_filter: Optional[RowFilter] = None):
+    def enqueue_topk(self, k: int, kc: int, excl_ptr=None, n_excl: int = 0, row_filter: Optional[RowFilter] = None,
+                     prefilter: bool = False):
         """Device-resident step: fused score+mask+top-k over the shard, then the exact fp64 pass, for the query /
         profile already sitting in this thread's scratch (qn32, qn64).  Result lands packed in scratch.d_out.
         Nothing is copied and nothing synchronises."""
@@ -529,7 +584,8 @@ class CatalogStore:
         f = self._filter_struct(row_filter) or nat.Filter()
         if n_excl:
             f.exclude_rows, f.n_exclude = excl_ptr, n_excl
-        nat.check(lib.rebert_gemv_topk(C.byref(self._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
+        # prefilter: the fast pass streams the int8 shadow (kc must be 256); the exact pass below always reads the real rows
+        nat.check(lib.rebert_gemv_topk(C.byref(self._c8 if prefilter else self._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
                                        s.ws.numel(), s.cand.data_ptr(), st))
         ob = s.d_out.data_ptr()
         nat.check(lib.rebert_finalize_topk(C.byref(self._c), s.qn64.data_ptr(), s.cand.data_ptr(), kc, k, ob,

@@ -63,7 +63,7 @@ int num_sms() {
 
 RowLayout row_layout(int d, int dtype) {
     RowLayout L;
-    L.esize = dtype == REBERT_BF16 ? 2 : 4;
+    L.esize = dtype == REBERT_BF16 ? 2 : (dtype == REBERT_I8 ? 1 : 4);
     L.epc = 16 / L.esize;
     int chunks = (d * L.esize + 15) / 16;
     if (chunks <= 16) {
@@ -199,6 +199,45 @@ __global__ void query_normalize_kernel(const float* __restrict__ q, int d, int l
         if (qn32) qn32[(int64_t)blockIdx.x * ld + c] = (float)v;
         if (qnbf16) qnbf16[(int64_t)blockIdx.x * ld + c] = __ushort_as_bfloat16(f32_to_bf16_rne((float)v));
     }
+}
+
+// int8 prefilter shadow: one warp per row, two passes over the (cache-resident) row: max|x| -> scale, then quantise,
+// accumulate the squared quantisation error in fp64 and fold max_r err_r / ||x_r|| into one device double.
+template <typename T>
+__global__ void quantize_i8_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n, int d, int ld,
+                                   int ld8, int8_t* __restrict__ out, float* __restrict__ factor,
+                                   unsigned long long* __restrict__ max_err_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double worst = 0.0;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        const T* row = rows + r * ld;
+        float mx = 0.f;
+        for (int c = lane; c < d; c += 32) mx = fmaxf(mx, fabsf((float)elem_f64<T>(row, c)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float scale = mx > 0.f ? mx / 127.f : 1.f;
+        double err2 = 0.0;
+        for (int c = lane; c < ld8; c += 32) {
+            int q = 0;
+            if (c < d) {
+                const float x = (float)elem_f64<T>(row, c);
+                q = __float2int_rn(x / scale);
+                q = max(-127, min(127, q));
+                const double e = (double)x - (double)q * (double)scale;
+                err2 = fma(e, e, err2);
+            }
+            out[r * ld8 + c] = (int8_t)q;
+        }
+        err2 = warp_sum(err2);
+        if (lane == 0) {
+            const double nrm = norm64[r];
+            factor[r] = (float)((double)scale / nrm);
+            worst = fmax(worst, sqrt(err2) / nrm);
+        }
+    }
+    if (lane == 0 && worst > 0.0) atomicMax(max_err_bits, (unsigned long long)__double_as_longlong(worst));   // >= 0: bit order == numeric order
 }
 
 // Request staging for the host-buffer entry point: ONE CTA reads the raw query and the exclusion list straight from
@@ -441,7 +480,7 @@ REBERT_API int rebert_check_device(void) {
 
 REBERT_API int rebert_catalog_layout(int64_t n, int32_t d, int32_t dtype, int32_t* ld, size_t* rows_bytes) {
     REBERT_REQUIRE(n >= 0 && d > 0, "catalog_layout: n=%lld d=%d", (long long)n, d);
-    REBERT_REQUIRE(dtype == REBERT_F32 || dtype == REBERT_BF16, "catalog_layout: dtype %d", dtype);
+    REBERT_REQUIRE(dtype == REBERT_F32 || dtype == REBERT_BF16 || dtype == REBERT_I8, "catalog_layout: dtype %d", dtype);
     RowLayout L = row_layout(d, dtype);
     if (ld) *ld = L.ld;
     if (rows_bytes) *rows_bytes = (size_t)n * L.ld * L.esize;
@@ -470,6 +509,26 @@ REBERT_API int rebert_catalog_norms(const void* rows, int64_t n, int32_t ld, int
     if (dtype == REBERT_F32) norms_kernel<float><<<g, 256, 0, st>>>((const float*)rows, n, ld, inv_norm, norm64);
     else if (dtype == REBERT_BF16) norms_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)rows, n, ld, inv_norm, norm64);
     else REBERT_REQUIRE(false, "catalog_norms: dtype %d", dtype);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
+REBERT_API int rebert_catalog_quantize_i8(const rebert_catalog_t* src, void* out_rows, int32_t ld8, float* out_factor,
+                                          double* out_max_err, rebert_stream stream) {
+    REBERT_REQUIRE(src && src->rows && src->norm64 && out_rows && out_factor && out_max_err, "catalog_quantize_i8: null argument");
+    REBERT_REQUIRE(src->dtype == REBERT_F32 || src->dtype == REBERT_BF16, "catalog_quantize_i8: source dtype %d", src->dtype);
+    RowLayout L8 = row_layout(src->d, REBERT_I8);
+    REBERT_REQUIRE(ld8 == L8.ld, "catalog_quantize_i8: ld8=%d does not match rebert_catalog_layout (%d)", ld8, L8.ld);
+    cudaStream_t st = (cudaStream_t)stream;
+    REBERT_CUDA(cudaMemsetAsync(out_max_err, 0, sizeof(double), st));
+    if (src->n == 0) return REBERT_OK;
+    const int g = grid_for(src->n * 32, 256);
+    if (src->dtype == REBERT_F32)
+        quantize_i8_kernel<float><<<g, 256, 0, st>>>((const float*)src->rows, src->norm64, src->n, src->d, src->ld, ld8,
+                                                     (int8_t*)out_rows, out_factor, (unsigned long long*)out_max_err);
+    else
+        quantize_i8_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src->rows, src->norm64, src->n, src->d, src->ld,
+                                                             ld8, (int8_t*)out_rows, out_factor, (unsigned long long*)out_max_err);
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }

@@ -19,6 +19,8 @@
 //   * launched with programmatic stream serialization: no global access before griddepcontrol.wait.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace rebert {
@@ -36,6 +38,7 @@ struct GemvParams {
     int64_t      n;
     int64_t      num_tiles;
     int          ld;
+    int          d;         // logical columns (int8 shadow: query elements beyond d are zero)
     int          cpl;       // runtime chunks per lane (generic kernel)
     int          tile_rows;
     int          stages;
@@ -74,6 +77,19 @@ template <> struct Elem<__nv_bfloat16> {
         acc = fmaf(bf16hi(v.z), q[5], acc);
         acc = fmaf(bf16lo(v.w), q[6], acc);
         acc = fmaf(bf16hi(v.w), q[7], acc);
+    }
+};
+
+// int8 prefilter shadow (rebert_catalog_quantize_i8): 16 elements per chunk, integer dot products (dp4a) against the query
+// split into two int8 planes (q ~ dh * hi + dl * lo, dl = dh / 254), exact int32 accumulation.
+template <> struct Elem<int8_t> {
+    static constexpr int EPC = 16;
+    __device__ static __forceinline__ void dot(const uint4&, const float*, float&) {}   // unused: the int8 path has its own loop
+    __device__ static __forceinline__ void dot2(const uint4& v, const uint32_t* q, int& hi, int& lo) {
+        hi = __dp4a((int)v.x, (int)q[0], hi); lo = __dp4a((int)v.x, (int)q[4], lo);
+        hi = __dp4a((int)v.y, (int)q[1], hi); lo = __dp4a((int)v.y, (int)q[5], lo);
+        hi = __dp4a((int)v.z, (int)q[2], hi); lo = __dp4a((int)v.z, (int)q[6], lo);
+        hi = __dp4a((int)v.w, (int)q[3], hi); lo = __dp4a((int)v.w, (int)q[7], lo);
     }
 };
 
@@ -241,7 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     constexpr int EPC = Elem<T>::EPC;
     constexpr int RPW = 32 / LANES;              // rows a warp scores at once
     constexpr bool kRegQ = CPL > 0;              // query chunks live in registers
-    constexpr int QREGS = kRegQ ? CPL * EPC : 1;
+    constexpr bool kI8 = std::is_same<T, int8_t>::value;   // int8 prefilter shadow (register-query variants only)
+    constexpr int QREGS = (kRegQ && !kI8) ? CPL * EPC : 1;
+    constexpr int QIREGS = kI8 ? CPL * 8 : 1;    // per chunk: 4 words of the hi plane + 4 of the lo plane
     constexpr int kQuantLane = 4 * M - 1;        // list entry kc/8 - 1 lives in keys[0] of this lane (kc = 32 M)
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -277,6 +295,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     }
     if (excl_staged) {
         for (int c = threadIdx.x; c < p.filter.n_exclude; c += blockDim.x) excl_smem[c] = __ldg(p.filter.exclude_rows + c);
+    }
+    __shared__ float s_qmax[kConsumerWarps + 1];
+    if (kI8) {                                   // max |q| sets the quantisation step of the query planes
+        float m = 0.f;
+        for (int c = threadIdx.x; c < p.d; c += blockDim.x) m = fmaxf(m, fabsf(__ldg(p.q + c)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) s_qmax[threadIdx.x >> 5] = m;
     }
     __syncthreads();
 
@@ -354,7 +380,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
         const int sub = lane / LANES;            // which of the warp's RPW rows this lane works on
         const int cl = lane % LANES;             // chunk lane within the row
         float q[QREGS];
-        if (kRegQ) {
+        uint32_t qi[QIREGS];
+        float dh = 1.f, dl = 1.f;
+        if constexpr (kI8) {
+            float qmax = 0.f;
+#pragma unroll
+            for (int w = 0; w <= kConsumerWarps; ++w) qmax = fmaxf(qmax, s_qmax[w]);
+            dh = qmax > 0.f ? qmax / 127.f : 1.f;
+            dl = dh / 254.f;
+#pragma unroll
+            for (int j = 0; j < (kI8 ? CPL : 0); ++j) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t ph = 0, pl = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int idx = (j * LANES + cl) * 16 + w * 4 + b;
+                        const float qv = idx < p.d ? __ldg(p.q + idx) : 0.f;
+                        int h = __float2int_rn(qv / dh);
+                        h = max(-127, min(127, h));
+                        int l = __float2int_rn((qv - (float)h * dh) / dl);
+                        l = max(-127, min(127, l));
+                        ph |= (uint32_t)(h & 0xFF) << (8 * b);
+                        pl |= (uint32_t)(l & 0xFF) << (8 * b);
+                    }
+                    qi[j * 8 + w] = ph;
+                    qi[j * 8 + 4 + w] = pl;
+                }
+            }
+        } else if (kRegQ) {
 #pragma unroll
             for (int j = 0; j < (kRegQ ? CPL : 0); ++j)
 #pragma unroll
@@ -396,7 +450,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                 float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
                 const uint4* pa = tile + (size_t)(vA ? rA : 0) * row_chunks + cl;
                 const uint4* pb = tile + (size_t)(vB ? rB : 0) * row_chunks + cl;
-                if (kRegQ) {
+                if constexpr (kI8) {
+                    int ah0 = 0, al0 = 0, ah1 = 0, al1 = 0, bh0 = 0, bl0 = 0, bh1 = 0, bl1 = 0;
+#pragma unroll
+                    for (int j = 0; j < (kI8 ? CPL : 0); ++j) {
+                        const uint4 va = pa[j * LANES];
+                        const uint4 vb = pb[j * LANES];
+                        if (j & 1) { Elem<int8_t>::dot2(va, qi + j * 8, ah1, al1); Elem<int8_t>::dot2(vb, qi + j * 8, bh1, bl1); }
+                        else       { Elem<int8_t>::dot2(va, qi + j * 8, ah0, al0); Elem<int8_t>::dot2(vb, qi + j * 8, bh0, bl0); }
+                    }
+                    int sah = ah0 + ah1, sal = al0 + al1, sbh = bh0 + bh1, sbl = bl0 + bl1;
+#pragma unroll
+                    for (int o = LANES / 2; o > 0; o >>= 1) {
+                        sah += __shfl_xor_sync(0xffffffffu, sah, o);
+                        sal += __shfl_xor_sync(0xffffffffu, sal, o);
+                        sbh += __shfl_xor_sync(0xffffffffu, sbh, o);
+                        sbl += __shfl_xor_sync(0xffffffffu, sbl, o);
+                    }
+                    a0 = fmaf(dh, (float)sah, dl * (float)sal);      // already reduced over the row's lanes
+                    b0 = fmaf(dh, (float)sbh, dl * (float)sbl);
+                } else if (kRegQ) {
 #pragma unroll
                     for (int j = 0; j < (kRegQ ? CPL : 0); ++j) {
                         const uint4 va = pa[j * LANES];
@@ -420,10 +493,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                     }
                 }
                 float sa = a0 + a1, sb = b0 + b1;
+                if constexpr (!kI8) {
 #pragma unroll
-                for (int o = LANES / 2; o > 0; o >>= 1) {
-                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
-                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                    for (int o = LANES / 2; o > 0; o >>= 1) {
+                        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                    }
                 }
                 const float ia = vA ? (rA < nrows4 ? inv_s[rA] : __ldg(p.inv_norm + row0 + rA)) : 0.f;
                 const float ib = vB ? (rB < nrows4 ? inv_s[rB] : __ldg(p.inv_norm + row0 + rB)) : 0.f;
@@ -603,6 +678,36 @@ static int launch_gemv_m(const GemvParams& p, const GemvLaunch& g, int kc, cudaS
     return REBERT_OK;
 }
 
+// int8 prefilter shadow: register-query variants, kc = 256 only (the candidate list must absorb the quantisation error)
+template <int CPL, int LANES>
+static int launch_gemv_i8_one(const GemvParams& p, const GemvLaunch& g, cudaStream_t st) {
+    auto kern = gemv_topk_kernel<int8_t, CPL, LANES, 8>;
+    { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
+    REBERT_CUDA(launch_pdl(kern, dim3(g.grid), dim3(kThreads), g.smem, st, p));
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+static int launch_gemv_i8(const RowLayout& L, const GemvParams& p, const GemvLaunch& g, cudaStream_t st) {
+    if (L.lanes < 32) {
+        switch (L.lanes) {
+            case 2: return launch_gemv_i8_one<1, 2>(p, g, st);
+            case 4: return launch_gemv_i8_one<1, 4>(p, g, st);
+            case 8: return launch_gemv_i8_one<1, 8>(p, g, st);
+            case 16: return launch_gemv_i8_one<1, 16>(p, g, st);
+        }
+    }
+    switch (L.cpl) {
+        case 1: return launch_gemv_i8_one<1, 32>(p, g, st);
+        case 2: return launch_gemv_i8_one<2, 32>(p, g, st);
+        case 3: return launch_gemv_i8_one<3, 32>(p, g, st);
+        case 4: return launch_gemv_i8_one<4, 32>(p, g, st);
+        case 6: return launch_gemv_i8_one<6, 32>(p, g, st);
+        case 12: return launch_gemv_i8_one<12, 32>(p, g, st);
+    }
+    set_error("gemv_topk: no int8 kernel for rows of %d chunks per lane", L.cpl);
+    return REBERT_ERR_UNSUPPORTED;
+}
+
 template <typename T>
 static int launch_gemv(const RowLayout& L, const GemvParams& p, const GemvLaunch& g, int kc, cudaStream_t st) {
     if (L.lanes < 32) {
@@ -655,7 +760,8 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
                      void* workspace, size_t workspace_bytes, uint64_t* cand_keys, rebert_stream stream) {
     REBERT_REQUIRE(cat && cat->rows && cat->inv_norm && qn32 && workspace && cand_keys, "gemv_topk: null argument");
     REBERT_REQUIRE(cat->n >= 0 && cat->n < (1ll << 31), "gemv_topk: shard rows %lld out of range", (long long)cat->n);
-    REBERT_REQUIRE(cat->dtype == REBERT_F32 || cat->dtype == REBERT_BF16, "gemv_topk: dtype %d", cat->dtype);
+    REBERT_REQUIRE(cat->dtype == REBERT_F32 || cat->dtype == REBERT_BF16 || cat->dtype == REBERT_I8, "gemv_topk: dtype %d", cat->dtype);
+    REBERT_REQUIRE(cat->dtype != REBERT_I8 || kc == 256, "gemv_topk: the int8 prefilter shadow needs kc = 256 (got %d)", kc);
     REBERT_REQUIRE(((uintptr_t)cat->rows & 127) == 0 && ((uintptr_t)cat->inv_norm & 15) == 0,
                    "gemv_topk: catalog rows must be 128-byte and inv_norm 16-byte aligned");
     RowLayout L = row_layout(cat->d, cat->dtype);
@@ -683,6 +789,7 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.q = qn32;
     p.n = cat->n;
     p.ld = L.ld;
+    p.d = cat->d;
     p.cpl = L.cpl;
     p.tile_rows = g.tile_rows;
     p.num_tiles = (cat->n + g.tile_rows - 1) / g.tile_rows;
@@ -708,6 +815,7 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.cand_keys = cand_keys;
     p.merge_cap = g.merge_cap;
 
+    if (cat->dtype == REBERT_I8) return launch_gemv_i8(L, p, g, st);
     return cat->dtype == REBERT_F32 ? launch_gemv<float>(L, p, g, kc, st) : launch_gemv<__nv_bfloat16>(L, p, g, kc, st);
 }
 

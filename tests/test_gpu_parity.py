@@ -353,3 +353,47 @@ def test_scheduling_knobs_change_speed_never_results(pdl):
     for case, v in res.items():
         assert v["identical"] and v["filled"] == v["kc"], (case, v)
         assert _KNOB_DIGESTS.setdefault(case, v["digest"]) == v["digest"], case      # ... and with PDL on or off
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("n,d,k", [(200_003, 1536, 10), (60_000, 1536, 100), (30_011, 50, 25), (9_001, 32, 10), (40_000, 768, 240)])
+def test_int8_prefilter_same_results_as_the_plain_path_and_the_oracle(dtype, n, d, k):
+    """The int8 shadow only chooses candidates; ids and fp64 scores must equal the plain path's and the oracle's."""
+    store = CatalogStore.synthetic(0, n, d, dtype, scale_rows=True)
+    eps = store.enable_prefilter()
+    assert 0.0 < eps < 0.05                                     # gaussian rows: ~0.009 at any d (per-row scale)
+    q = synth.query_f32(1, d)
+    excl = np.random.default_rng(5).choice(n, size=133, replace=False)
+    rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True, prefilter=True)
+    plain_rows, plain_scores = store.recommend(query=q, exclude_rows=excl, k=k, prefilter=False)
+    np.testing.assert_array_equal(rows, plain_rows)
+    np.testing.assert_array_equal(scores, plain_scores)         # same exact-pass kernel on the same rows: same bits
+    want_rows, want_scores = ora.query_rows(_stored_f64(store), q.astype(np.float64), excl, k)
+    np.testing.assert_array_equal(rows, want_rows)
+    np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL)
+    if n >= 200_000 and k <= 10:
+        assert info.get("prefilter") is True and info["margin"] > eps      # 10th and 256th best of 200k rows are ~0.02 apart
+    # a profile request (mean of unit rows, norm < 1) through the same route
+    (rated, rts), = synth.user_ratings(2, n, 1)
+    liked = rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1]
+    r2, s2 = store.recommend(liked_rows=liked, exclude_rows=rated, k=k, prefilter=True)
+    w2, ws2 = ora.recommend_rows(_stored_f64(store), liked, rated, k)
+    np.testing.assert_array_equal(r2, w2)
+    np.testing.assert_allclose(s2, ws2, rtol=SCORE_RTOL)
+
+
+def test_int8_prefilter_falls_back_when_its_bound_cannot_prove_the_result():
+    """Rows dominated by one huge element quantise badly (bound ~ 0.09 at d = 1536): the proof fails and the request
+    silently takes the plain path — results still equal the oracle's."""
+    n, d, k = 50_000, 1536, 10
+    m = synth.catalog_rows_f32(0, 0, n, d)
+    m[::3, 7] = 400.0                                           # one dominant column in every third row
+    store = CatalogStore.from_host(None, m, "bf16")
+    eps = store.enable_prefilter()
+    assert eps > 0.02
+    q = synth.query_f32(1, d)
+    rows, scores, info = store.recommend(query=q, k=k, return_info=True)
+    assert not info.get("prefilter") and info["proven_exact"]
+    want_rows, want_scores = ora.query_rows(_stored_f64(store), q.astype(np.float64), None, k)
+    np.testing.assert_array_equal(rows, want_rows)
+    np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL)
