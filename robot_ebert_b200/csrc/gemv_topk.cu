@@ -442,6 +442,57 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
             const int nrows = left < p.tile_rows ? (int)left : p.tile_rows;
             const int nrows4 = nrows & ~3;
 
+            if constexpr (kI8) {
+                // int8 shadow: rows are half as long, so a warp has to turn rows around twice as fast to keep up with HBM;
+                // FOUR rows per step (8 independent dp4a chains, 8 shuffle reductions in flight) hide the per-step latency.
+                for (int base = warp * RPW; base < nrows; base += 4 * kConsumerWarps * RPW) {
+                    int rr[4];
+                    bool vv[4];
+                    const uint4* pr[4];
+                    int hs[4] = {0, 0, 0, 0}, ls[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        rr[u] = base + sub + u * kConsumerWarps * RPW;
+                        vv[u] = rr[u] < nrows;
+                        pr[u] = tile + (size_t)(vv[u] ? rr[u] : 0) * row_chunks + cl;
+                    }
+#pragma unroll
+                    for (int j = 0; j < (kI8 ? CPL : 0); ++j) {
+                        uint4 x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) x[u] = pr[u][j * LANES];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) Elem<int8_t>::dot2(x[u], qi + j * 8, hs[u], ls[u]);
+                    }
+#pragma unroll
+                    for (int o = LANES / 2; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            hs[u] += __shfl_xor_sync(0xffffffffu, hs[u], o);
+                            ls[u] += __shfl_xor_sync(0xffffffffu, ls[u], o);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {          // u ascending = rows ascending, which WarpTopK::insert relies on
+                        const float inv = vv[u] ? (rr[u] < nrows4 ? inv_s[rr[u]] : __ldg(p.inv_norm + row0 + rr[u])) : 0.f;
+                        const float sc_lane = fmaf(dh, (float)hs[u], dl * (float)ls[u]) * inv;
+                        unsigned mm = __ballot_sync(0xffffffffu, vv[u] && cl == 0 && sc_lane > top.thr && sc_lane >= hint);
+                        while (mm) {
+                            const int src = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const float sc = __shfl_sync(0xffffffffu, sc_lane, src);
+                            const uint32_t lr = (uint32_t)(row0 + base + u * kConsumerWarps * RPW + src / LANES);
+                            if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) {
+                                top.insert(make_key(sc, lr), lane);
+                                publish_hints<kQuantLane>(top.keys[0], top.thr, warp, lane, p.cta_hint, &s_hint, s_wq);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                continue;
+            }
             // two row groups per step for ILP: rows rA and rB = rA + kConsumerWarps*RPW
             for (int base = warp * RPW; base < nrows; base += 2 * kConsumerWarps * RPW) {
                 const int rA = base + sub;
@@ -450,26 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                 float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
                 const uint4* pa = tile + (size_t)(vA ? rA : 0) * row_chunks + cl;
                 const uint4* pb = tile + (size_t)(vB ? rB : 0) * row_chunks + cl;
-                if constexpr (kI8) {
-                    int ah0 = 0, al0 = 0, ah1 = 0, al1 = 0, bh0 = 0, bl0 = 0, bh1 = 0, bl1 = 0;
-#pragma unroll
-                    for (int j = 0; j < (kI8 ? CPL : 0); ++j) {
-                        const uint4 va = pa[j * LANES];
-                        const uint4 vb = pb[j * LANES];
-                        if (j & 1) { Elem<int8_t>::dot2(va, qi + j * 8, ah1, al1); Elem<int8_t>::dot2(vb, qi + j * 8, bh1, bl1); }
-                        else       { Elem<int8_t>::dot2(va, qi + j * 8, ah0, al0); Elem<int8_t>::dot2(vb, qi + j * 8, bh0, bl0); }
-                    }
-                    int sah = ah0 + ah1, sal = al0 + al1, sbh = bh0 + bh1, sbl = bl0 + bl1;
-#pragma unroll
-                    for (int o = LANES / 2; o > 0; o >>= 1) {
-                        sah += __shfl_xor_sync(0xffffffffu, sah, o);
-                        sal += __shfl_xor_sync(0xffffffffu, sal, o);
-                        sbh += __shfl_xor_sync(0xffffffffu, sbh, o);
-                        sbl += __shfl_xor_sync(0xffffffffu, sbl, o);
-                    }
-                    a0 = fmaf(dh, (float)sah, dl * (float)sal);      // already reduced over the row's lanes
-                    b0 = fmaf(dh, (float)sbh, dl * (float)sbl);
-                } else if (kRegQ) {
+                if (kRegQ) {                 // (the int8 shadow has its own loop above and never gets here)
 #pragma unroll
                     for (int j = 0; j < (kRegQ ? CPL : 0); ++j) {
                         const uint4 va = pa[j * LANES];
@@ -493,12 +525,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                     }
                 }
                 float sa = a0 + a1, sb = b0 + b1;
-                if constexpr (!kI8) {
 #pragma unroll
-                    for (int o = LANES / 2; o > 0; o >>= 1) {
-                        sa += __shfl_xor_sync(0xffffffffu, sa, o);
-                        sb += __shfl_xor_sync(0xffffffffu, sb, o);
-                    }
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
                 }
                 const float ia = vA ? (rA < nrows4 ? inv_s[rA] : __ldg(p.inv_norm + row0 + rA)) : 0.f;
                 const float ib = vB ? (rB < nrows4 ? inv_s[rB] : __ldg(p.inv_norm + row0 + rB)) : 0.f;

@@ -12,14 +12,18 @@ from robot_ebert_b200 import CatalogStore, synth, _native as nat
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_250_000
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+I8 = len(sys.argv) > 3 and sys.argv[3] == "i8"            # trace the int8 prefilter shadow's fast pass (kc = 256)
 lib = nat.load(); dev = torch.device("cuda:0")
 store = CatalogStore.synthetic(0, n, 1536, "bf16", device=dev)
 q = synth.query_f32(1, 1536); excl = np.random.default_rng(1).choice(n, size=133, replace=False)
-kc = lib.rebert_candidates_for_k(K)
+kc = 256 if I8 else lib.rebert_candidates_for_k(K)
+if I8:
+    store.enable_prefilter()
+cat = store._c8 if I8 else store._c
 ptr, ne = store.stage_inputs(q, None, None, excl, K, kc)
 s = store._scratch(); f = nat.Filter(); f.exclude_rows, f.n_exclude = ptr, ne
 st = torch.cuda.current_stream().cuda_stream
-def gemv(): nat.check(lib.rebert_gemv_topk(C.byref(store._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(), s.ws.numel(), s.cand.data_ptr(), st))
+def gemv(): nat.check(lib.rebert_gemv_topk(C.byref(cat), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(), s.ws.numel(), s.cand.data_ptr(), st))
 sms = torch.cuda.get_device_properties(dev).multi_processor_count
 L = 6
 bufs = [torch.zeros((sms + 1) * 8, dtype=torch.int64, device=dev) for _ in range(L)]
@@ -32,7 +36,15 @@ for i in range(L):
     gemv()
 b.record(); torch.cuda.synchronize()
 os.environ.pop("REBERT_GEMV_TRACE")
-print(json.dumps({"rows": n, "k": K, "event_us_per_launch": round(a.elapsed_time(b) / L * 1e3, 2)}))
+ob = s.d_out.data_ptr()
+def fin(): nat.check(lib.rebert_finalize_topk(C.byref(store._c), s.qn64.data_ptr(), s.cand.data_ptr(), kc, K, ob, ob + 8*K, ob + 16*K, ob + 16*K + 8, st))
+fin(); torch.cuda.synchronize()
+fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+fa.record()
+for _ in range(20): fin()
+fb.record(); torch.cuda.synchronize()
+print(json.dumps({"finalize_us_at_kc": kc, "us": round(fa.elapsed_time(fb) / 20 * 1e3, 2)}))
+print(json.dumps({"rows": n, "k": K, "i8": I8, "event_us_per_launch": round(a.elapsed_time(b) / L * 1e3, 2)}))
 names = ["entry", "prologue_done", "first_tile", "warp0_done", "all_warps_done", "list_written"]
 prev_end = None
 for i in range(L):
