@@ -10,6 +10,8 @@ Workload (BASELINE.json `metric`): single-query cosine top-10 with a 133-row see
 `value`  : queries/s with the query already resident in HBM (kernels only).
 `e2e`    : queries/s through CatalogStore.recommend / ShardedCatalog.recommend with HOST buffers in and out
            (pinned H2D of the request, D2H of the result, stream sync) inside the timed region.
+`batched` / `prefilter_int8` are secondary measurements printed beside the headline (BASELINE configs 3/4 on the tcgen05
+path; the same request with the opt-in int8 prefilter shadow, same ids and scores) — never instead of it.
 `--impl reference` times the reference's own CPU path (oracle/, pandas + scikit-learn, float64, all host threads) on
 a bounded row sample of the same workload and scales to the full catalog.
 """

@@ -1,7 +1,10 @@
 // Host-buffer entry point: one C call = one request of the reference's hot path (lib.py:43-55) end to end.
-// Host pointers in, host pointers out; the H2D copy of the packed request, every kernel, the D2H copy of the result
-// and the stream synchronisation all happen inside.  Scratch (pinned host + device) is provided by the caller, so
-// the library still allocates nothing and concurrent callers only need their own scratch + stream.
+// Host pointers in, host pointers out; staging the request, every kernel and the stream synchronisation all happen
+// inside.  A raw query is read by the first kernel straight from the caller's pinned block (zero-copy) and the exact
+// pass writes its packed result straight into that block, so a query request involves no copy-engine operation at
+// all; a liked-rows request ships its lists with one H2D copy.  rebert_recommend_host_sharded appends the fused NVLink
+// exchange + merge for one rank of a row-sharded catalog.  Scratch (pinned host + device) is provided by the caller,
+// so the library still allocates nothing and concurrent callers only need their own scratch + stream.
 #include "common.cuh"
 
 namespace rebert {
