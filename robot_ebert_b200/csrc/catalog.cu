@@ -247,12 +247,37 @@ __global__ void quantize_i8_kernel(const T* __restrict__ rows, const double* __r
 __global__ void __launch_bounds__(256) stage_query_kernel(const float* __restrict__ q_host, int d, int ld, float* __restrict__ qn32,
                                                           double* __restrict__ qn64, const int32_t* __restrict__ excl_host,
                                                           int n_excl, int32_t* __restrict__ excl_dev) {
-    extern __shared__ float s_src[];                 // [d]
+    extern __shared__ __align__(16) float s_src[];   // [d]
     __shared__ double red[32];
     pdl_trigger();
     pdl_wait();
-    for (int c = threadIdx.x; c < d; c += blockDim.x) s_src[c] = q_host[c];
-    for (int c = threadIdx.x; c < n_excl; c += blockDim.x) excl_dev[c] = excl_host[c];
+    // Every load below crosses PCIe (~2 us round trip): issue them all before the first use — 16-byte loads, four per
+    // thread in flight (covers d <= 4096 in one round trip; the pinned block is 16-byte aligned).
+    {
+        const int d4 = d >> 2;
+        const float4* q4 = (const float4*)q_host;
+        for (int c0 = threadIdx.x; c0 < d4; c0 += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j * blockDim.x;
+                v[j] = c < d4 ? q4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j * blockDim.x;
+                if (c < d4) ((float4*)s_src)[c] = v[j];
+            }
+        }
+        for (int c = (d4 << 2) + threadIdx.x; c < d; c += blockDim.x) s_src[c] = q_host[c];
+        int e[4];
+        for (int c0 = threadIdx.x; c0 < n_excl; c0 += 4 * blockDim.x) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int c = c0 + j * blockDim.x; e[j] = c < n_excl ? excl_host[c] : 0; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int c = c0 + j * blockDim.x; if (c < n_excl) excl_dev[c] = e[j]; }
+        }
+    }
     __syncthreads();
     double acc = 0.0;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
