@@ -224,14 +224,19 @@ def batched_leg(store, sharded, world, rows_total, dev, steps=3, warmup=2):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     flops = 2.0 * B * rows_total * DIM
-    peak = 1590.0
+    peak, sustained = 1590.0, None
     try:
-        peak = float(json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        mp = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        peak = float(mp["bf16_tflops"])
+        sustained = float(mp["bf16_tflops_sustained"])            # cuBLAS back to back for seconds: the power-capped regime
     except Exception:
         pass
     return {"workload": f"{B} users x {rows_total} x {DIM} bf16, top-{KB}, {N_EXCL}-row exclusions per user",
             "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "tflops": flops / (ms * 1e-3) / 1e12,
-            "frac_of_measured_bf16_peak": flops / (ms * 1e-3) / 1e12 / (peak * world), "bound": "tensor",
+            "frac_of_measured_bf16_peak": flops / (ms * 1e-3) / 1e12 / (peak * world),
+            "frac_of_sustained_bf16_peak": (flops / (ms * 1e-3) / 1e12 / (sustained * world)) if sustained else None,
+            "peak_note": "burst = cuBLAS best of 10; sustained = cuBLAS back to back for seconds (the regime a ~100 ms batch runs in)",
+            "bound": "tensor",
             "includes": "threshold sample + fused GEMM filter + per-query select + fp64 exact pass" + (" + all-gather + merge" if world > 1 else ""),
             "queries_rerun_on_single_query_path": int((status_of() != 0).sum().item()),
             "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
