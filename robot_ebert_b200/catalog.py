@@ -45,6 +45,7 @@ class _Scratch:
         self.kc = 0
         self.k_cap = 0
         self.nl_cap = self.ne_cap = self.hk_cap = 0
+        self.sne_cap = self.shk_cap = 0
         dev = store.device
         ld = store.ld
         self.qn32 = torch.zeros(ld, dtype=torch.float32, device=dev)
@@ -55,17 +56,30 @@ class _Scratch:
     def ensure_host(self, n_liked: int, n_excl: int, k: int):
         """Pinned + device scratch of rebert_recommend_host, grown geometrically."""
         if n_liked > self.nl_cap or n_excl > self.ne_cap or k > self.hk_cap:
-            lib = nat.load()
             self.nl_cap = max(self.nl_cap, 1024, 1 << max(n_liked - 1, 0).bit_length())
             self.ne_cap = max(self.ne_cap, 1024, 1 << max(n_excl - 1, 0).bit_length())
             self.hk_cap = max(self.hk_cap, 16, 1 << (k - 1).bit_length())
-            pb, db = C.c_size_t(0), C.c_size_t(0)
-            nat.check(lib.rebert_recommend_host_scratch(C.byref(self.store._c), self.nl_cap, self.ne_cap, self.hk_cap,
-                                                        C.byref(pb), C.byref(db)))
-            self.hpin = torch.empty(pb.value, dtype=torch.uint8).pin_memory()
-            self.hdev = torch.zeros(db.value, dtype=torch.uint8, device=self.store.device)   # zero once (ticket counter)
+            self.hpin, self.hdev = self._host_scratch(self.nl_cap, self.ne_cap, self.hk_cap)
             self.h_rows = np.empty(self.hk_cap, dtype=np.int64)
             self.h_scores = np.empty(self.hk_cap, dtype=np.float64)
+
+    def ensure_host_sharded(self, n_excl: int, k: int):
+        """Scratch of rebert_recommend_host_sharded.  Kept apart from ensure_host's: that entry lays the scratch out for
+        n_liked_cap = 0, and the zero-filled-once ticket words must never share bytes with another layout's data."""
+        if n_excl > self.sne_cap or k > self.shk_cap:
+            self.sne_cap = max(self.sne_cap, 1024, 1 << max(n_excl - 1, 0).bit_length())
+            self.shk_cap = max(self.shk_cap, 16, 1 << (k - 1).bit_length())
+            self.shpin, self.shdev = self._host_scratch(0, self.sne_cap, self.shk_cap)
+            self.sh_rows = np.empty(self.shk_cap, dtype=np.int64)
+            self.sh_scores = np.empty(self.shk_cap, dtype=np.float64)
+
+    def _host_scratch(self, nl_cap: int, ne_cap: int, k_cap: int):
+        lib = nat.load()
+        pb, db = C.c_size_t(0), C.c_size_t(0)
+        nat.check(lib.rebert_recommend_host_scratch(C.byref(self.store._c), nl_cap, ne_cap, k_cap, C.byref(pb), C.byref(db)))
+        pinned = torch.empty(pb.value, dtype=torch.uint8).pin_memory()
+        device = torch.zeros(db.value, dtype=torch.uint8, device=self.store.device)   # zero once (ticket / claim counters)
+        return pinned, device
 
     def ensure_in(self, nbytes: int):
         if nbytes > self.in_cap:

@@ -114,20 +114,20 @@ class CudaShardBackend:
         if exclude_rows is not None and len(exclude_rows):
             ex = sorted_unique_i32(exclude_rows)
             ne = int(ex.shape[0])
-        s.ensure_host(0, ne, k)
+        s.ensure_host_sharded(ne, k)
         f = st._filter_struct(row_filter)
         cnt, margin = C.c_int32(0), C.c_double(0.0)
         self._seq += 1
         with _on_device(self.device):
             rc = lib.rebert_recommend_host_sharded(
                 C.byref(st._c), q.ctypes.data, None if ex is None else ex.ctypes.data, ne, None if f is None else C.byref(f), k, kc,
-                s.ne_cap, s.hpin.data_ptr(), s.hpin.numel(), s.hdev.data_ptr(), s.hdev.numel(), self._peer_ptrs, self._p2p_world,
-                self._p2p_rank, self.K_MAX, self._seq & 0xFFFFFFFF or 1, s.h_rows.ctypes.data, s.h_scores.ctypes.data,
+                s.sne_cap, s.shpin.data_ptr(), s.shpin.numel(), s.shdev.data_ptr(), s.shdev.numel(), self._peer_ptrs, self._p2p_world,
+                self._p2p_rank, self.K_MAX, self._seq & 0xFFFFFFFF or 1, s.sh_rows.ctypes.data, s.sh_scores.ctypes.data,
                 C.byref(cnt), C.byref(margin), torch.cuda.current_stream().cuda_stream)
         nat.check(rc)
         st.last_h2d_bytes = 4 * st.d + 4 * ne            # read by the staging kernel straight from the pinned block
         n = cnt.value
-        return s.h_rows[:n].copy(), s.h_scores[:n].copy(), margin.value
+        return s.sh_rows[:n].copy(), s.sh_scores[:n].copy(), margin.value
 
     def stage(self, query, liked_rows, weights, exclude_rows, k, kc):
         st = self.store
