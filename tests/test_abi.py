@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 from robot_ebert_b200 import _native as nat
@@ -99,10 +100,32 @@ def test_c_abi_argument_validation_without_a_gpu():
     assert lib.rebert_gemm_plan(1_000_000, 64, 240, C.byref(plan)) == nat.OK and plan.kc == 320
     assert lib.rebert_gemm_plan(1_000_000, 64, 50, C.byref(plan)) == nat.OK and plan.kc == 96
     assert lib.rebert_gemm_plan(1_000_000, 4096, 5000, C.byref(plan)) == nat.ERR_UNSUPPORTED
+    # int8 prefilter shadow: layout (1 byte per element), argument checks of the quantiser, kc = 256 only in the fast pass
+    ld8, nbytes = C.c_int32(0), C.c_size_t(0)
+    assert lib.rebert_catalog_layout(10, 1536, nat.I8, C.byref(ld8), C.byref(nbytes)) == nat.OK
+    assert (ld8.value, nbytes.value) == (1536, 15360)
+    assert lib.rebert_catalog_layout(10, 50, nat.I8, C.byref(ld8), None) == nat.OK and ld8.value == 64
+    assert lib.rebert_catalog_quantize_i8(C.byref(cat), None, 32, None, None, None) == nat.ERR_INVALID
+    cat8 = nat.Catalog(rows=128, inv_norm=128, norm64=128, n=10, row_base=0, d=32, ld=32, dtype=nat.I8, reserved=0)
+    assert lib.rebert_catalog_quantize_i8(C.byref(cat8), 128, 32, 128, 128, None) == nat.ERR_INVALID and b"source dtype" in lib.rebert_last_error()
+    assert lib.rebert_gemv_topk(C.byref(cat8), 128, C.byref(f), 32, 128, 1 << 20, 128, None) == nat.ERR_INVALID
+    assert b"kc = 256" in lib.rebert_last_error()
+    # sharded host entry: same validation as the single-GPU entry, before any CUDA call
+    assert lib.rebert_recommend_host_sharded(C.byref(cat), None, None, 0, None, 10, 32, 0, None, 0, None, 0, None, 2, 0, 240, 1,
+                                             None, None, None, None, None) == nat.ERR_INVALID
     with pytest.raises(ValueError):
         nat.check(nat.ERR_INVALID)
     with pytest.raises(nat.NativeError):
         nat.check(nat.ERR_UNSUPPORTED)
+
+
+def test_sorted_unique_i32_passes_sorted_input_through():
+    from robot_ebert_b200.catalog import sorted_unique_i32
+    a = np.array([1, 5, 9], dtype=np.int32)
+    assert sorted_unique_i32(a) is a or np.shares_memory(sorted_unique_i32(a), a)          # no copy, no sort
+    np.testing.assert_array_equal(sorted_unique_i32([9, 1, 5, 5, 1]), [1, 5, 9])
+    np.testing.assert_array_equal(sorted_unique_i32(np.array([3, 3], dtype=np.int64)), [3])
+    assert sorted_unique_i32(np.array([7], dtype=np.int64)).dtype == np.int32
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
