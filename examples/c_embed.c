@@ -23,10 +23,12 @@ static int gpu_part(long long n, int d, int k) {
     size_t bytes = 0, pinned_bytes = 0, device_bytes = 0;
     void *rows = NULL, *pinned = NULL, *scratch = NULL, *qdev = NULL;
     float *inv = NULL, *q = NULL;
-    double *nrm = NULL, margin = 0.0, *scores = NULL;
+    double *nrm = NULL, *scores = NULL;
     int64_t* out_rows = NULL;
     int32_t excl[100];
     rebert_catalog_t cat;
+    rebert_proof_t proof;
+    rebert_request_info_t info;
 
     RB(rebert_check_device());
     RB(rebert_catalog_layout(n, d, REBERT_BF16, &ld, &bytes));
@@ -49,9 +51,12 @@ static int gpu_part(long long n, int d, int k) {
     CK(cudaMemset(scratch, 0, device_bytes));                                        /* zero once: ticket counter */
     out_rows = (int64_t*)malloc((size_t)k * sizeof(int64_t));
     scores = (double*)malloc((size_t)k * sizeof(double));
+    memset(&proof, 0, sizeof(proof));
+    proof.fast_eps = 1e-5;                                                            /* > (elements per lane + 12) * 2^-24, DESIGN.md 4.2 */
+    proof.widen = 1;
     RB(rebert_recommend_host(&cat, q, NULL, NULL, 0, excl, nex, NULL, k, kc, 1024, 1024, pinned, pinned_bytes, scratch, device_bytes,
-                             out_rows, scores, &cnt, &margin, NULL));
-    printf("results %d margin_ok %d\n", cnt, margin > 1e-5);
+                             &proof, NULL, out_rows, scores, &cnt, &info, NULL));
+    printf("results %d margin_ok %d\n", cnt, info.proven);
     for (i = 0; i < cnt; ++i) printf("row %lld score %.17g\n", (long long)out_rows[i], scores[i]);
     return 0;
 }

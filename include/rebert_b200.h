@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define REBERT_ABI_VERSION 1
+#define REBERT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define REBERT_API __attribute__((visibility("default")))
@@ -87,6 +87,43 @@ typedef struct {
     uint16_t        year_lo, year_hi;/* keep year_lo <= year <= year_hi */
     uint32_t        reserved;
 } rebert_filter_t;
+
+/* How ONE RANK of a row-sharded catalog reaches its peers: NVLink peer memory, no NCCL on the request path.
+ * Every rank owns a peer-mapped buffer of rebert_exchange_buffer_bytes(world, k_max, prof_len, channels) bytes,
+ * ZERO-FILLED once; peer_buffers is a HOST array of the `world` device addresses under which THIS process sees the
+ * ranks' buffers (e.g. torch symmetric memory's buffer_ptrs).  The buffer holds `channels` independent channels, one per
+ * concurrent request stream (the reference serves from a threadpool, api/users.py:151): calls on one channel must be
+ * issued in the same order by every rank, calls on different channels are independent.  seq is the call number on the
+ * channel, starting at 1, the same on every rank.  A 32-bit tag of the request travels with every result; the merge
+ * refuses (error) to combine results whose tags differ, i.e. when the ranks' request order on a channel diverged. */
+typedef struct {
+    const uint64_t* peer_buffers;
+    int32_t  world, rank;
+    int32_t  k_max;      /* largest k the buffers were sized for */
+    int32_t  prof_len;   /* largest padded row length (ld) of a liked-rows request; 0 = query requests only */
+    int32_t  channels, channel;
+    uint32_t seq;
+    uint32_t reserved;
+} rebert_exchange_t;
+
+/* Proof policy of rebert_recommend_host: which fast passes to try and what their error bounds are.  A result is PROVEN
+ * (ids bit-exact) when the exact pass's margin exceeds the bound of the fast pass that produced the
+ * candidates. */
+typedef struct {
+    const rebert_catalog_t* shadow;  /* int8 prefilter shadow (rebert_catalog_quantize_i8) or NULL */
+    double  shadow_eps;              /* proven bound on |shadow score - true score| (rows + query planes) */
+    double  fast_eps;                /* proven bound of the plain fp32 fast pass */
+    int32_t shadow_max_k;            /* try the shadow only for k <= this */
+    int32_t widen;                   /* 1: while the margin does not clear the bound, retry with 4x candidates (<= 256) */
+} rebert_proof_t;
+
+typedef struct {
+    int32_t kc;          /* candidates of the attempt that produced the result */
+    int32_t attempts;    /* fast passes run (each one consumed one exchange sequence number on a row shard) */
+    int32_t proven;      /* 1: margin > bound; 0: not proven — the caller must take an exhaustive route (rebert_collect_above) */
+    int32_t used_shadow; /* 1: the result came from the int8 shadow's candidates */
+    double  margin;
+} rebert_request_info_t;
 
 /* ---- library ------------------------------------------------------------------------------ */
 REBERT_API int         rebert_abi_version(void);
@@ -137,6 +174,9 @@ REBERT_API int32_t rebert_candidates_for_k(int32_t k);
  * threshold word that every launch leaves at zero again); after that it can be reused by consecutive calls on the
  * same stream without further clearing. */
 REBERT_API size_t  rebert_gemv_workspace_bytes(int64_t n, int32_t kc);
+/* Zero the control words again after a launch that did not run to completion (a fault): they sit at a kc-independent
+ * place at the start of the workspace, so one workspace serves every kc. */
+REBERT_API int     rebert_workspace_reset(void* workspace, size_t workspace_bytes, rebert_stream stream);
 /* Fast pass.  score(r) = <qn32, row r> * inv_norm[r] in fp32; keeps the kc best allowed rows of the shard.
  * Output: cand_keys[kc] sorted best-first (packed (score, local row) keys; unused slots are 0). */
 REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, int32_t kc,
@@ -149,6 +189,19 @@ REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* q
                          int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin,
                          rebert_stream stream);
 
+/* ---- device-resident request: ONE launch (lib.py:51-55 for a prepared query / profile) ------------------------- */
+/* Fast pass + exact pass + ranking in a single kernel launch: the last CTA of the streaming kernel re-scores the kc
+ * candidates in fp64 from `cat` (the catalog of record), orders them and writes the packed result
+ *     out_packed[0..k) rows | [k..2k) fp64 score bits | [2k] count (low 32 bits) + tag (high 32 bits) | [2k+1] margin
+ * (device memory or device-addressable pinned host memory).  shadow != NULL: the fast pass streams the int8 shadow
+ * (kc must be 256).  exchange != NULL with world > 1: the same launch also runs the NVLink exchange + merge, so that
+ * out_packed is the merged result a single GPU would return (margin = the smallest over the ranks); *err_flag (int32,
+ * device or pinned) becomes 1 + rank if a peer did not deliver within ~10 s, 101 + rank if its request tag differs. */
+REBERT_API int rebert_recommend_device(const rebert_catalog_t* cat, const rebert_catalog_t* shadow, const float* qn32, const double* qn64,
+                                       const rebert_filter_t* filter, int32_t k, int32_t kc, void* workspace, size_t workspace_bytes,
+                                       int64_t* out_packed, uint32_t tag, const rebert_exchange_t* exchange, int32_t* err_flag,
+                                       rebert_stream stream);
+
 /* ---- host-buffer entry point: one call = one request, end to end -------------------------- */
 /* Scratch sizes for rebert_recommend_host with lists of at most n_liked_cap / n_exclude_cap entries and results of k.
  * pinned: page-locked host memory (cudaHostAlloc / pinned torch tensor); device: device memory, ZERO-FILLED once. */
@@ -156,30 +209,28 @@ REBERT_API int rebert_recommend_host_scratch(const rebert_catalog_t* cat, int32_
                                              size_t* pinned_bytes, size_t* device_bytes);
 /* lib.py:43-55 for one request with HOST buffers: pass `query` [d] fp32 (not normalised) OR `liked_rows` (+ optional
  * weights), plus the sorted unique GLOBAL `exclude_rows`; device_filter may add device-resident bitmap / genre / year
- * tests.  Packs the request into the pinned block; a raw query is read from there by the first kernel (zero-copy), a
- * liked-rows request takes ONE H2D copy; then normalise or build the profile, fused score+mask+top-k, fp64 exact pass
- * whose packed result the kernel writes straight into the pinned block (no D2H copy operation), and a stream
- * synchronisation.  `pinned` must therefore be page-locked memory the device can address (cudaHostAlloc /
- * cudaMallocHost / a pinned torch tensor).  out_rows / out_scores are host [k] (-1 / -inf padded), *out_count <= k.
+ * tests.  The request is packed into the pinned block and read from there by the first kernel (zero-copy, no copy-engine
+ * operation): a staging kernel normalises the query or builds the profile (mean of the liked rows' unit vectors), then
+ * ONE launch does fused score + mask + top-k + fp64 exact pass and writes the packed result straight into the pinned
+ * block; a stream synchronisation ends the call.  Catalogs small enough for one CTA (n * ld <= 131072 elements: the
+ * reference's production 2269 x 32) are served by a single kernel that scores every row exactly in fp64.
+ * `pinned` must therefore be page-locked memory the device can address.  out_rows / out_scores are host [k]
+ * (-1 / -inf padded), *out_count <= k.
+ * proof  (may be NULL = one attempt with `kc`, info->proven = 0): see rebert_proof_t — int8 shadow first, then the plain
+ *        fast pass with kc, 4 kc, ... 256 candidates until the margin proves the id set.
+ * exchange (may be NULL = single GPU): this rank's view of a row-sharded catalog.  Every rank calls with the same
+ *        request; liked rows owned by other shards are summed there and the fp64 partial profiles are exchanged and
+ *        added in rank order; the local results are exchanged and merged inside the scoring launch.  Each attempt uses
+ *        sequence numbers exchange->seq, seq + 1, ... (info->attempts of them).
  * Returns REBERT_ERR_INVALID with "Found array with 0 sample(s)" when liked_rows is given but empty (the reference's
  * own failure for a user without liked movies). */
 REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* query, const int32_t* liked_rows,
                                      const float* liked_w, int32_t n_liked, const int32_t* exclude_rows, int32_t n_exclude,
                                      const rebert_filter_t* device_filter, int32_t k, int32_t kc, int32_t n_liked_cap,
                                      int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
-                                     size_t device_bytes, int64_t* out_rows, double* out_scores, int32_t* out_count,
-                                     double* out_margin, rebert_stream stream);
-
-/* The same call for ONE RANK of a row-sharded catalog (query requests): local fast + exact pass over this rank's shard,
- * then the fused NVLink exchange + merge (rebert_exchange_merge, arguments as there: peer_buffers / world / rank / k_max /
- * seq), whose merged result lands in the pinned block.  Every rank calls it with the same query, exclusions and seq and
- * gets the same answer a single GPU would return; *out_margin is the smallest proof margin over the ranks. */
-REBERT_API int rebert_recommend_host_sharded(const rebert_catalog_t* cat, const float* query, const int32_t* exclude_rows,
-                                             int32_t n_exclude, const rebert_filter_t* device_filter, int32_t k, int32_t kc,
-                                             int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
-                                             size_t device_bytes, const uint64_t* peer_buffers, int32_t world, int32_t rank,
-                                             int32_t k_max, uint32_t seq, int64_t* out_rows, double* out_scores,
-                                             int32_t* out_count, double* out_margin, rebert_stream stream);
+                                     size_t device_bytes, const rebert_proof_t* proof, const rebert_exchange_t* exchange,
+                                     int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_request_info_t* info,
+                                     rebert_stream stream);
 
 /* ---- merge of per-shard results (lib.py:55 across shards) --------------------------------- */
 /* For each of b queries merge `lists` sorted result lists into the best k.  List l of query u is at
@@ -190,19 +241,17 @@ REBERT_API int rebert_merge_topk(const int64_t* rows, const double* scores, cons
                       int64_t scores_stride, int64_t counts_stride, int32_t lists, int32_t b, int32_t k,
                       int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_stream stream);
 
-/* Fused exchange + merge over NVLink peer memory for the row-sharded single-query path (one kernel instead of an
- * all-gather plus a merge).  Every rank owns a peer-mapped buffer of rebert_exchange_buffer_bytes(world, k_max) bytes,
- * ZERO-FILLED once; peer_buffers is a HOST array of the `world` device addresses under which THIS process sees the
- * ranks' buffers (e.g. torch symmetric memory's buffer_ptrs).  local_packed / out_packed are packed result blocks of
- * 2k+2 64-bit words: rows[k] | fp64 scores[k] | count | margin (what rebert_finalize_topk writes when its four outputs
- * point into one block).  seq is the call number, starting at 1 and incremented by every rank on every call.
- * The kernel stores the local block into every peer, publishes a flag, waits for all peers' flags and merges under
- * (score desc, row asc); *err_flag (int32 in device or device-addressable pinned memory) becomes non-zero if a peer did
- * not deliver within ~10 s.  out_packed may likewise point into pinned host memory. */
-REBERT_API size_t rebert_exchange_buffer_bytes(int32_t world, int32_t k_max);
-REBERT_API int rebert_exchange_merge(const uint64_t* peer_buffers, int32_t world, int32_t rank, int32_t k, int32_t k_max,
-                                     uint32_t seq, const int64_t* local_packed, int64_t* out_packed, int32_t* err_flag,
-                                     rebert_stream stream);
+/* Stand-alone forms of the two exchange steps over NVLink peer memory (rebert_exchange_t above).
+ * rebert_exchange_merge: local_packed / out_packed are packed result blocks of 2k+2 64-bit words (layout as in
+ * rebert_recommend_device).  The kernel stores the local block into every peer, publishes a flag, waits for all peers'
+ * flags and merges under (score desc, row asc); out_packed / err_flag may point into pinned host memory.
+ * rebert_profile_exchange: sum64 [ld] = this rank's fp64 partial profile (rebert_profile_accumulate); the partials are
+ * exchanged, added in rank order and divided by wsum[0]: p32 / p64 [ld] receive the profile, identical on every rank. */
+REBERT_API size_t rebert_exchange_buffer_bytes(int32_t world, int32_t k_max, int32_t prof_len, int32_t channels);
+REBERT_API int rebert_exchange_merge(const rebert_exchange_t* exchange, int32_t k, const int64_t* local_packed, int64_t* out_packed,
+                                     int32_t* err_flag, rebert_stream stream);
+REBERT_API int rebert_profile_exchange(const rebert_exchange_t* exchange, int32_t ld, double* sum64, const double* wsum, float* p32,
+                                       double* p64, int32_t* err_flag, rebert_stream stream);
 
 /* ---- subset scoring for the search re-rank (lib.py:105-106) ------------------------------- */
 /* out[u, j] = <p64[u], row sub_rows[j]> / norm64 in fp64 for m candidate GLOBAL rows (all must be in this shard). */

@@ -11,6 +11,7 @@ F32, BF16 = 0, 1
 I8 = 2          # prefilter shadow only (rebert_catalog_quantize_i8)
 DTYPES = {"fp32": F32, "bf16": BF16, "i8": I8}
 
+ABI_VERSION = 2
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_DEVICE = 0, -1, -2, -3, -4, -5
 
 
@@ -30,6 +31,24 @@ class Filter(C.Structure):
     _fields_ = [("exclude_bitmap", C.c_void_p), ("exclude_rows", C.c_void_p), ("n_exclude", C.c_int32),
                 ("genre_any", C.c_uint32), ("genre_bits", C.c_void_p), ("year", C.c_void_p),
                 ("year_lo", C.c_uint16), ("year_hi", C.c_uint16), ("reserved", C.c_uint32)]
+
+
+class Exchange(C.Structure):
+    """rebert_exchange_t: one rank's view of the peer-mapped exchange buffers of a row-sharded catalog."""
+    _fields_ = [("peer_buffers", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("k_max", C.c_int32),
+                ("prof_len", C.c_int32), ("channels", C.c_int32), ("channel", C.c_int32), ("seq", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class Proof(C.Structure):
+    """rebert_proof_t: which fast passes rebert_recommend_host may try and their proven error bounds."""
+    _fields_ = [("shadow", C.POINTER(Catalog)), ("shadow_eps", C.c_double), ("fast_eps", C.c_double),
+                ("shadow_max_k", C.c_int32), ("widen", C.c_int32)]
+
+
+class RequestInfo(C.Structure):
+    _fields_ = [("kc", C.c_int32), ("attempts", C.c_int32), ("proven", C.c_int32), ("used_shadow", C.c_int32),
+                ("margin", C.c_double)]
 
 
 class GemmPlan(C.Structure):
@@ -55,13 +74,15 @@ _SIGS = {
     "rebert_finalize_topk": (C.c_int, [C.POINTER(Catalog), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "rebert_recommend_host_scratch": (C.c_int, [C.POINTER(Catalog), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "rebert_recommend_host": (C.c_int, [C.POINTER(Catalog), _P, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(Filter), C.c_int32, C.c_int32,
-                                        C.c_int32, C.c_int32, _P, C.c_size_t, _P, C.c_size_t, _P, _P, _P, _P, _P]),
-    "rebert_recommend_host_sharded": (C.c_int, [C.POINTER(Catalog), _P, _P, C.c_int32, C.POINTER(Filter), C.c_int32, C.c_int32, C.c_int32,
-                                                _P, C.c_size_t, _P, C.c_size_t, _P, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
-                                                _P, _P, _P, _P, _P]),
+                                        C.c_int32, C.c_int32, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(Proof), C.POINTER(Exchange),
+                                        _P, _P, _P, C.POINTER(RequestInfo), _P]),
+    "rebert_recommend_device": (C.c_int, [C.POINTER(Catalog), C.POINTER(Catalog), _P, _P, C.POINTER(Filter), C.c_int32, C.c_int32, _P,
+                                          C.c_size_t, _P, C.c_uint32, C.POINTER(Exchange), _P, _P]),
+    "rebert_workspace_reset": (C.c_int, [_P, C.c_size_t, _P]),
     "rebert_merge_topk": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
-    "rebert_exchange_buffer_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
-    "rebert_exchange_merge": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P]),
+    "rebert_exchange_buffer_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "rebert_exchange_merge": (C.c_int, [C.POINTER(Exchange), C.c_int32, _P, _P, _P, _P]),
+    "rebert_profile_exchange": (C.c_int, [C.POINTER(Exchange), C.c_int32, _P, _P, _P, _P, _P, _P]),
     "rebert_score_subset": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "rebert_collect_above": (C.c_int, [C.POINTER(Catalog), _P, C.POINTER(Filter), C.c_float, _P, C.c_int32, _P, _P]),
     "rebert_scores_dense": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, _P, _P]),
@@ -88,7 +109,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rebert_abi_version() != 1:
+    if lib.rebert_abi_version() != ABI_VERSION:
         raise ImportError("rebert_b200 ABI version mismatch")
     _lib = lib
     return lib

@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
-import warnings
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -45,7 +44,6 @@ class _Scratch:
         self.kc = 0
         self.k_cap = 0
         self.nl_cap = self.ne_cap = self.hk_cap = 0
-        self.sne_cap = self.shk_cap = 0
         dev = store.device
         ld = store.ld
         self.qn32 = torch.zeros(ld, dtype=torch.float32, device=dev)
@@ -62,16 +60,6 @@ class _Scratch:
             self.hpin, self.hdev = self._host_scratch(self.nl_cap, self.ne_cap, self.hk_cap)
             self.h_rows = np.empty(self.hk_cap, dtype=np.int64)
             self.h_scores = np.empty(self.hk_cap, dtype=np.float64)
-
-    def ensure_host_sharded(self, n_excl: int, k: int):
-        """Scratch of rebert_recommend_host_sharded.  Kept apart from ensure_host's: that entry lays the scratch out for
-        n_liked_cap = 0, and the zero-filled-once ticket words must never share bytes with another layout's data."""
-        if n_excl > self.sne_cap or k > self.shk_cap:
-            self.sne_cap = max(self.sne_cap, 1024, 1 << max(n_excl - 1, 0).bit_length())
-            self.shk_cap = max(self.shk_cap, 16, 1 << (k - 1).bit_length())
-            self.shpin, self.shdev = self._host_scratch(0, self.sne_cap, self.shk_cap)
-            self.sh_rows = np.empty(self.shk_cap, dtype=np.int64)
-            self.sh_scores = np.empty(self.shk_cap, dtype=np.float64)
 
     def _host_scratch(self, nl_cap: int, ne_cap: int, k_cap: int):
         lib = nat.load()
@@ -349,9 +337,12 @@ class CatalogStore:
         liked_rows   global row ids of the liked movies (+ optional weights; default 1 = the reference)
         exclude_rows global row ids that must not be returned (the user's rated movies, lib.py:48)
         Returns (rows int64[k'], scores float64[k']), k' = min(k, #allowed rows), ordered (score desc, row asc).
-        Host buffers in, host buffers out: the H2D/D2H copies are part of the call.
+        Host buffers in, host buffers out: one C call (rebert_recommend_host) packs the request into pinned memory, the
+        kernels read it from there and write the result back there.
         prefilter: None = use the int8 shadow when enable_prefilter() has built one and k <= PREFILTER_MAX_K; True = try it
         for any k <= 240; False = never.  The result is the same either way.
+        The ids are PROVEN exact or the call raises: a request no candidate list can prove (mass ties) takes the exhaustive
+        sweep, then the threshold-bisection route; if even that cannot decide, RuntimeError.
         """
         if (query is None) == (liked_rows is None):
             raise ValueError("pass exactly one of query / liked_rows")
@@ -369,48 +360,36 @@ class CatalogStore:
             return rows, scores
         if prefilter and self._c8 is None:
             raise ValueError("prefilter=True needs enable_prefilter()")
-        if self._c8 is not None and (prefilter or (prefilter is None and k <= self.PREFILTER_MAX_K)):
-            res = self._recommend_prefilter(lib, query, liked_rows, weights, exclude_rows, k, row_filter)
-            if res is not None:                        # proven on the shadow's candidates; otherwise fall through
-                rows, scores, margin = res
-                if return_info:
-                    return rows, scores, {"kc": 256, "margin": margin, "proven_exact": True, "exact_sweep": False, "prefilter": True}
-                return rows, scores
-        while True:
-            rows, scores, margin = self._recommend_once(lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter)
-            if margin > self.fast_eps or kc >= 256:
-                break
-            kc = min(256, kc * 4)                       # candidate set not provably exact: widen and redo
-        proven = margin > self.fast_eps
-        swept = False
-        if not proven and len(rows) == k:
+        shadow_max_k = 0
+        if self._c8 is not None and prefilter is not False:
+            shadow_max_k = 240 if prefilter else self.PREFILTER_MAX_K
+        rows, scores, info = self._recommend_host(query, liked_rows, weights, exclude_rows, k, kc, row_filter, shadow_max_k)
+        rows, scores, info = self._close_proof(lib, rows, scores, info, query, liked_rows, weights, exclude_rows, k, row_filter)
+        if return_info:
+            return rows, scores, info
+        return rows, scores
+
+    def _close_proof(self, lib, rows, scores, info, query, liked_rows, weights, exclude_rows, k, row_filter):
+        """Fail closed: a result whose margin proved nothing goes through the exhaustive routes or raises."""
+        if info["proven_exact"]:
+            return rows, scores, info
+        res = None
+        if len(rows) == k:
             # Mass ties: more rows than any candidate list holds sit within fp32 noise of the k-th score.  Sweep for every
             # allowed row that could still belong to the top-k, re-score those in fp64, order them: provably exact.
             res = self._exact_sweep(lib, query, liked_rows, weights, exclude_rows, k, row_filter, float(scores[k - 1]))
-            if res is not None:
-                rows, scores = res
-                proven = swept = True
-        if not proven:
-            warnings.warn(f"top-{k}: fp32 candidate margin {margin:.3e} <= {self.fast_eps:.3e}; ids may differ from fp64 order")
-        if return_info:
-            return rows, scores, {"kc": kc, "margin": margin, "proven_exact": proven, "exact_sweep": swept}
-        return rows, scores
+        if res is None:
+            try:                                   # sweep buffer overflow: the bisection route handles any tie mass it can hold
+                res = self._recommend_large_k(lib, query, liked_rows, weights, exclude_rows, k, row_filter)
+            except RuntimeError as e:
+                raise RuntimeError(f"top-{k}: the result cannot be proven exact (margin {info['margin']:.3e} <= "
+                                   f"{self.fast_eps:.3e}) and the exhaustive route failed: {e}") from e
+        info = dict(info, proven_exact=True, exact_sweep=True)
+        return res[0], res[1], info
 
     # 256 candidates absorb the shadow's proven error bound (~0.009 for gaussian rows) only while the k-th and the 256-th
     # best scores are far enough apart; beyond k ~ 16 the proof usually fails and the attempt would be wasted work.
     PREFILTER_MAX_K = 16
-
-    def _recommend_prefilter(self, lib, query, liked_rows, weights, exclude_rows, k, row_filter):
-        """Fast pass over the int8 shadow (256 candidates) + exact pass over the catalog of record.  Returns
-        (rows, scores, margin) when the margin proves the candidate set exact under the shadow's error bound, else None."""
-        with _on_device(self.device):
-            excl_ptr, ne = self.stage_inputs(query, liked_rows, weights, exclude_rows, k, 256)
-            s = self._scratch()
-            self.enqueue_topk(k, 256, excl_ptr, ne, row_filter, prefilter=True)
-            s.h_out.copy_(s.d_out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        rows, scores, margin = unpack_result(s.h_out_np, k)
-        return (rows, scores, margin) if margin > self.q8_eps else None
 
     SWEEP_CAP = 1 << 16
 
@@ -476,8 +455,11 @@ class CatalogStore:
                                           stream.cuda_stream))
         return sub.cpu().numpy().astype(np.int64), exact[0].cpu().numpy()
 
-    def _recommend_once(self, lib, query, liked_rows, weights, exclude_rows, k, kc, row_filter):
-        """One rebert_recommend_host call: host buffers in, host buffers out, copies + kernels + sync inside."""
+    def _recommend_host(self, query, liked_rows, weights, exclude_rows, k, kc, row_filter, shadow_max_k=0, exchange=None,
+                        shadow_eps=None):
+        """One rebert_recommend_host call: host buffers in, host buffers out; staging, kernels, proof loop and stream sync
+        inside.  exchange: a nat.Exchange for one rank of a row-sharded catalog (sharding.py).  Returns (rows, scores, info)."""
+        lib = nat.load()
         s = self._scratch()
         d = self.d
         q = lk = w = ex = None
@@ -491,25 +473,36 @@ class CatalogStore:
             nl = int(lk.shape[0])
             if weights is not None:
                 w = np.ascontiguousarray(weights, dtype=np.float32)
+                if w.shape != lk.shape:
+                    raise ValueError("weights must match liked_rows")
         if exclude_rows is not None and len(exclude_rows):
             ex = sorted_unique_i32(exclude_rows)
             ne = int(ex.shape[0])
         s.ensure_host(nl, ne, k)
         f = self._filter_struct(row_filter)
-        cnt, margin = C.c_int32(0), C.c_double(0.0)
-        off_rp = _align(4 * d)
-        self.last_h2d_bytes = (off_rp + 16 + _align(4 * ne) + 2 * _align(4 * nl)) if lk is not None else \
-            (off_rp + 16 + _align(4 * ne) if ne else off_rp)
+        proof = nat.Proof()
+        proof.fast_eps, proof.widen = self.fast_eps, 1
+        if shadow_max_k and self._c8 is not None:
+            proof.shadow = C.pointer(self._c8)
+            proof.shadow_eps = self.q8_eps if shadow_eps is None else shadow_eps
+            proof.shadow_max_k = shadow_max_k
+        cnt, info = C.c_int32(0), nat.RequestInfo()
+        # bytes the kernels fetch from / write to the pinned block over PCIe (zero-copy: no copy-engine operation)
+        self.last_h2d_bytes = (4 * d if lk is None else 4 * nl * (2 if w is not None else 1)) + 4 * ne
+        self.last_d2h_bytes = 8 * (2 * k + 2)
         with _on_device(self.device):
             rc = lib.rebert_recommend_host(
                 C.byref(self._c), None if q is None else q.ctypes.data, None if lk is None else lk.ctypes.data,
                 None if w is None else w.ctypes.data, nl, None if ex is None else ex.ctypes.data, ne,
                 None if f is None else C.byref(f), k, kc, s.nl_cap, s.ne_cap, s.hpin.data_ptr(), s.hpin.numel(),
-                s.hdev.data_ptr(), s.hdev.numel(), s.h_rows.ctypes.data, s.h_scores.ctypes.data, C.byref(cnt),
-                C.byref(margin), torch.cuda.current_stream().cuda_stream)
+                s.hdev.data_ptr(), s.hdev.numel(), C.byref(proof), None if exchange is None else C.byref(exchange),
+                s.h_rows.ctypes.data, s.h_scores.ctypes.data, C.byref(cnt), C.byref(info),
+                torch.cuda.current_stream().cuda_stream)
         nat.check(rc)
         n = cnt.value
-        return s.h_rows[:n].copy(), s.h_scores[:n].copy(), margin.value
+        return s.h_rows[:n].copy(), s.h_scores[:n].copy(), {
+            "kc": info.kc, "margin": info.margin, "proven_exact": bool(info.proven), "exact_sweep": False,
+            "prefilter": bool(info.used_shadow), "attempts": info.attempts}
 
     def _filter_struct(self, row_filter: Optional[RowFilter]):
         """rebert_filter_t for the device-resident predicates of a RowFilter (None when there are none)."""
@@ -606,6 +599,47 @@ class CatalogStore:
                                            ob + 8 * k, ob + 16 * k, ob + 16 * k + 8, st))
         return s.d_out
 
+    def enqueue_fused(self, k: int, kc: int, excl_ptr=None, n_excl: int = 0, row_filter: Optional[RowFilter] = None,
+                      prefilter: bool = False, exchange=None, err_ptr=None, out_ptr=None):
+        """Device-resident request in ONE launch (rebert_recommend_device): fused score+mask+top-k, fp64 exact pass and
+        ranking in the tail of the same kernel (+ the NVLink exchange and merge when `exchange` is given), for the query /
+        profile already sitting in this thread's scratch.  Result lands packed in scratch.d_out (or at out_ptr)."""
+        lib = nat.load()
+        s = self._scratch()
+        s.ensure_out(k, kc)
+        f = self._filter_struct(row_filter) or nat.Filter()
+        if n_excl:
+            f.exclude_rows, f.n_exclude = excl_ptr, n_excl
+        nat.check(lib.rebert_recommend_device(C.byref(self._c), C.byref(self._c8) if prefilter else None, s.qn32.data_ptr(),
+                                              s.qn64.data_ptr(), C.byref(f), k, kc, s.ws.data_ptr(), s.ws.numel(),
+                                              s.d_out.data_ptr() if out_ptr is None else out_ptr, 0,
+                                              None if exchange is None else C.byref(exchange), err_ptr,
+                                              torch.cuda.current_stream().cuda_stream))
+        return s.d_out
+
+    def topk_prepared(self, k: int, excl_ptr=None, n_excl: int = 0, row_filter: Optional[RowFilter] = None):
+        """PROVEN top-k for the query / profile already in this thread's scratch (qn32, qn64): the fused launch with
+        4x more candidates until the margin clears the fp32 bound, then the exhaustive sweep; raises if neither proves
+        the ids.  Used for the queries a batched pass hands back."""
+        lib = nat.load()
+        s = self._scratch()
+        kc = lib.rebert_candidates_for_k(k)
+        if kc == 0:
+            raise ValueError(f"k={k} is outside the supported range (1..240)")
+        while True:
+            self.enqueue_fused(k, kc, excl_ptr, n_excl, row_filter)
+            r, sc, margin = unpack_result(s.d_out.cpu().numpy(), k)
+            if margin > self.fast_eps or kc >= 256:
+                break
+            kc = min(256, kc * 4)
+        if not margin > self.fast_eps:
+            res = self.sweep_above(float(sc[k - 1]) - 2.0 * self.fast_eps, excl_ptr, n_excl, row_filter) if len(r) == k else None
+            if res is None or len(res[0]) < k:
+                raise RuntimeError(f"top-{k}: the result cannot be proven exact (margin {margin:.3e} <= {self.fast_eps:.3e})")
+            order = np.lexsort((res[0], -res[1]))[:k]
+            r, sc = res[0][order], res[1][order]
+        return r, sc
+
     # ------------------------------------------------------------------ batched (tensor cores) --
     def prepare_queries(self, queries: np.ndarray):
         """Host fp32 [b, d] query matrix -> device (qn32, qn64, qnbf16) unit vectors [b, ld]."""
@@ -699,17 +733,14 @@ class CatalogStore:
             redo = np.nonzero(status)[0]
             if len(redo):
                 s = self._scratch()
-                kc = lib.rebert_candidates_for_k(k)
                 ecp = None if excl_ptr is None else np.asarray(excl_ptr, dtype=np.int64)
-                for u in redo:                                   # exact single-query kernel for the unproven ones
-                    s.ensure_out(k, kc)
+                for u in redo:                                   # proven single-query route for the ones the batch could not prove
                     s.qn32.copy_(qn32[u])
                     s.qn64.copy_(qn64[u])
                     ptr, ne = None, 0
                     if ecp is not None and ecp[u + 1] > ecp[u]:
                         ptr, ne = ec.data_ptr() + 4 * int(ecp[u]), int(ecp[u + 1] - ecp[u])
-                    self.enqueue_topk(k, kc, ptr, ne, row_filter)
-                    r, sc, _ = unpack_result(s.d_out.cpu().numpy(), k)
+                    r, sc = self.topk_prepared(k, ptr, ne, row_filter)
                     rows[u, :], scores[u, :] = -1, -np.inf
                     rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
         if return_info:
@@ -732,14 +763,12 @@ class CatalogStore:
             ecp, ecol = sorted_csr(excl_ptr, excl_col)
             ec = torch.from_numpy(ecol).to(self.device)
         for u in range(b):
-            s.ensure_out(k, kc)
             s.qn32.copy_(qn32[u])
             s.qn64.copy_(qn64[u])
             ptr, ne = None, 0
             if ecp is not None and ecp[u + 1] > ecp[u]:
                 ptr, ne = ec.data_ptr() + 4 * int(ecp[u]), int(ecp[u + 1] - ecp[u])
-            self.enqueue_topk(k, kc, ptr, ne, row_filter)
-            r, sc, _ = unpack_result(s.d_out.cpu().numpy(), k)
+            r, sc = self.topk_prepared(k, ptr, ne, row_filter)
             rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
         if return_info:
             return rows, scores, counts, {"status": np.zeros(b, dtype=np.int32), "plan": None}

@@ -8,7 +8,8 @@
 
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "exchange.cuh"
+#include "request.cuh"
 
 namespace rebert {
 
@@ -243,7 +244,7 @@ __global__ void quantize_i8_kernel(const T* __restrict__ rows, const double* __r
 // Request staging for the host-buffer entry point: ONE CTA reads the raw query and the exclusion list straight from
 // the caller's pinned host block (zero-copy over PCIe, no copy-engine operation in front of the kernels), normalises the
 // query exactly as query_normalize_kernel does (same per-thread and reduction order => same bits) and drops the
-// exclusion list into device scratch for the scoring kernel.
+// exclusion list into device scratch for the scoring kernel.  (Helpers in request.cuh, shared with small.cu.)
 __global__ void __launch_bounds__(256) stage_query_kernel(const float* __restrict__ q_host, int d, int ld, float* __restrict__ qn32,
                                                           double* __restrict__ qn64, const int32_t* __restrict__ excl_host,
                                                           int n_excl, int32_t* __restrict__ excl_dev) {
@@ -251,50 +252,10 @@ __global__ void __launch_bounds__(256) stage_query_kernel(const float* __restric
     __shared__ double red[32];
     pdl_trigger();
     pdl_wait();
-    // Every load below crosses PCIe (~2 us round trip): issue them all before the first use — 16-byte loads, four per
-    // thread in flight (covers d <= 4096 in one round trip; the pinned block is 16-byte aligned).
-    {
-        const int d4 = d >> 2;
-        const float4* q4 = (const float4*)q_host;
-        for (int c0 = threadIdx.x; c0 < d4; c0 += 4 * blockDim.x) {
-            float4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = c0 + j * blockDim.x;
-                v[j] = c < d4 ? q4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = c0 + j * blockDim.x;
-                if (c < d4) ((float4*)s_src)[c] = v[j];
-            }
-        }
-        for (int c = (d4 << 2) + threadIdx.x; c < d; c += blockDim.x) s_src[c] = q_host[c];
-        int e[4];
-        for (int c0 = threadIdx.x; c0 < n_excl; c0 += 4 * blockDim.x) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const int c = c0 + j * blockDim.x; e[j] = c < n_excl ? excl_host[c] : 0; }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const int c = c0 + j * blockDim.x; if (c < n_excl) excl_dev[c] = e[j]; }
-        }
-    }
+    fetch_query_zero_copy(q_host, d, s_src);
+    copy_list_zero_copy(excl_host, n_excl, excl_dev);
     __syncthreads();
-    double acc = 0.0;
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-        double x = (double)s_src[c];
-        acc = fma(x, x, acc);
-    }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) red[0] = v;
-    }
-    __syncthreads();
-    double nrm = sqrt(red[0]);
-    if (nrm == 0.0) nrm = 1.0;
+    const double nrm = query_norm_256(s_src, d, red);
     for (int c = threadIdx.x; c < ld; c += blockDim.x) {
         double v = c < d ? (double)s_src[c] / nrm : 0.0;
         qn64[c] = v;
@@ -309,89 +270,64 @@ int stage_query_launch(const float* q_host, int d, int ld, float* qn32, double* 
     return REBERT_OK;
 }
 
-// One CTA per user.  The user's entries (local row, weight, row norm) are staged in shared memory in blocks; each
-// thread owns one 16-byte chunk of the row (4 fp32 / 8 bf16 columns) with fp64 accumulators and walks the entries in
-// CSR order — a fixed summation order, so the profile is deterministic — with four row loads in flight.
-// Entries outside this shard are skipped (their partial sums come from the owning rank through the all-reduce).
-template <typename T> struct RowChunk;
-template <> struct RowChunk<float> {
-    static constexpr int EPC = 4;
-    __device__ static __forceinline__ void unpack(const uint4& v, double* x) {
-        x[0] = (double)__uint_as_float(v.x); x[1] = (double)__uint_as_float(v.y);
-        x[2] = (double)__uint_as_float(v.z); x[3] = (double)__uint_as_float(v.w);
-    }
-};
-template <> struct RowChunk<__nv_bfloat16> {
-    static constexpr int EPC = 8;
-    __device__ static __forceinline__ void unpack(const uint4& v, double* x) {
-        x[0] = (double)bf16lo(v.x); x[1] = (double)bf16hi(v.x); x[2] = (double)bf16lo(v.y); x[3] = (double)bf16hi(v.y);
-        x[4] = (double)bf16lo(v.z); x[5] = (double)bf16hi(v.z); x[6] = (double)bf16lo(v.w); x[7] = (double)bf16hi(v.w);
-    }
-};
-
-constexpr int kProfBlock = 512;     // entries staged per round
-
+// One CTA per user (profile_accumulate_cta, request.cuh): the user's entries (local row, weight, row norm) are staged in
+// shared memory in blocks; each thread owns 16-byte chunks of the row with fp64 accumulators and walks the entries in CSR
+// order — a fixed summation order, so the profile is deterministic — with four row loads in flight.
+// Entries outside this shard are skipped (their partial sums come from the owning rank through the exchange).
 template <typename T, bool DIV>
 __global__ void __launch_bounds__(256) profile_accumulate_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n,
                                                                  int64_t row_base, int ld, const int64_t* __restrict__ row_ptr,
                                                                  const int32_t* __restrict__ col, const float* __restrict__ w,
                                                                  double* __restrict__ sum64, double* __restrict__ wsum) {
-    constexpr int EPC = RowChunk<T>::EPC;
-    __shared__ int s_row[kProfBlock];
-    __shared__ double s_w[kProfBlock];      // weight (DIV) or weight / norm (!DIV)
-    __shared__ double s_n[kProfBlock];      // norm (DIV only)
     const int u = blockIdx.x;
     const int64_t e0 = row_ptr[u], e1 = row_ptr[u + 1];
-    const int chunks = ld / EPC;
-    for (int g0 = 0; g0 < chunks; g0 += blockDim.x) {
-        const int g = g0 + threadIdx.x;
-        double acc[EPC];
-#pragma unroll
-        for (int i = 0; i < EPC; ++i) acc[i] = 0.0;
-        for (int64_t b0 = e0; b0 < e1; b0 += kProfBlock) {
-            const int nb = (int)((e1 - b0) < kProfBlock ? (e1 - b0) : kProfBlock);
-            __syncthreads();
-            for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-                const int64_t r = (int64_t)col[b0 + i] - row_base;
-                const bool mine = r >= 0 && r < n;
-                const double wt = w ? (double)w[b0 + i] : 1.0;
-                const double nrm = mine ? norm64[r] : 1.0;
-                s_row[i] = mine ? (int)r : -1;
-                s_w[i] = DIV ? wt : wt / nrm;
-                s_n[i] = nrm;
-            }
-            __syncthreads();
-            if (g < chunks) {
-                for (int i = 0; i < nb; i += 4) {
-                    uint4 v[4];
-                    int rr[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        rr[j] = (i + j < nb) ? s_row[i + j] : -1;
-                        if (rr[j] >= 0) v[j] = __ldg((const uint4*)(rows + (size_t)rr[j] * ld) + g);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (rr[j] < 0) continue;
-                        double x[EPC];
-                        RowChunk<T>::unpack(v[j], x);
-                        const double wt = s_w[i + j], nrm = s_n[i + j];
-#pragma unroll
-                        for (int t = 0; t < EPC; ++t) acc[t] = DIV ? fma(wt, x[t] / nrm, acc[t]) : fma(x[t], wt, acc[t]);
-                    }
-                }
-            }
-        }
-        if (g < chunks) {
-#pragma unroll
-            for (int t = 0; t < EPC; ++t) sum64[(int64_t)u * ld + (int64_t)g * EPC + t] = acc[t];
-        }
+    profile_accumulate_cta<T, DIV>(rows, norm64, n, row_base, ld, col + e0, w ? w + e0 : nullptr, (int)(e1 - e0),
+                                   sum64 + (int64_t)u * ld, wsum + u);
+}
+
+// Single liked-rows request (host-buffer entry point): ONE CTA reads the liked rows (+ weights) and the exclusion list
+// zero-copy from the caller's pinned block, builds this shard's fp64 partial profile with the very arithmetic of
+// profile_accumulate_kernel<T, true> (sklearn's divide-first order), on a row shard exchanges the partials with the peers
+// (exchange.cuh, summed in rank order) and divides by the weight sum: qn32 / qn64 are ready for the scoring kernel.
+// Replaces an H2D copy + accumulate + (all-reduce) + finalize.
+template <typename T>
+__global__ void __launch_bounds__(256) stage_profile_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n,
+                                                            int64_t row_base, int ld, const int32_t* __restrict__ liked_host,
+                                                            const float* __restrict__ w_host, int n_liked,
+                                                            const int32_t* __restrict__ excl_host, int n_excl, int32_t* __restrict__ excl_dev,
+                                                            double* __restrict__ sum64, double* __restrict__ wsum,
+                                                            float* __restrict__ qn32, double* __restrict__ qn64, Exchange x) {
+    pdl_trigger();
+    pdl_wait();
+    copy_list_zero_copy(excl_host, n_excl, excl_dev);
+    profile_accumulate_cta<T, true, 16>(rows, norm64, n, row_base, ld, liked_host, w_host, n_liked, sum64, wsum);
+    __syncthreads();
+    if (x.world > 1) {
+        exchange_profile(x, ld, sum64, sum64);
+        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        double sw = 0.0;
-        for (int64_t e = e0; e < e1; ++e) sw += w ? (double)w[e] : 1.0;
-        wsum[u] = sw;
+    const double ws = wsum[0];
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        const double v = ws != 0.0 ? sum64[c] / ws : 0.0;
+        qn64[c] = v;
+        qn32[c] = (float)v;
     }
+}
+
+int stage_profile_launch(const rebert_catalog_t* cat, const int32_t* liked_host, const float* w_host, int n_liked, const int32_t* excl_host,
+                         int n_excl, int32_t* excl_dev, double* sum64, double* wsum, float* qn32, double* qn64, const Exchange* x,
+                         cudaStream_t st) {
+    Exchange xe;
+    memset(&xe, 0, sizeof(xe));
+    if (x) xe = *x;
+    if (cat->dtype == REBERT_F32)
+        REBERT_CUDA(launch_pdl(stage_profile_kernel<float>, dim3(1), dim3(256), 0, st, (const float*)cat->rows, cat->norm64, cat->n,
+                               cat->row_base, cat->ld, liked_host, w_host, n_liked, excl_host, n_excl, excl_dev, sum64, wsum, qn32, qn64, xe));
+    else
+        REBERT_CUDA(launch_pdl(stage_profile_kernel<__nv_bfloat16>, dim3(1), dim3(256), 0, st, (const __nv_bfloat16*)cat->rows, cat->norm64,
+                               cat->n, cat->row_base, cat->ld, liked_host, w_host, n_liked, excl_host, n_excl, excl_dev, sum64, wsum, qn32,
+                               qn64, xe));
+    return REBERT_OK;
 }
 
 __global__ void profile_finalize_kernel(const double* __restrict__ sum64, const double* __restrict__ wsum, int ld,
@@ -570,6 +506,8 @@ REBERT_API int rebert_profile_accumulate(const rebert_catalog_t* cat, const int6
                               int32_t b, double* sum64, double* wsum, rebert_stream stream) {
     REBERT_REQUIRE(cat && cat->rows && cat->norm64 && row_ptr && col && sum64 && wsum && b > 0,
                    "profile_accumulate: bad arguments");
+    REBERT_REQUIRE(cat->ld * (cat->dtype == REBERT_BF16 ? 2 : 4) <= kProfMaxIter * 256 * 16, "profile_accumulate: rows of %d elements are too long",
+                   cat->ld);
     cudaStream_t st = (cudaStream_t)stream;
     // few users: element-wise division like sklearn's normalize(); large batches: one reciprocal per liked row (1 ulp apart)
     const bool div = b <= 8;

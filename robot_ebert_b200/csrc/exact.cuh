@@ -1,0 +1,167 @@
+// Exact (fp64) re-score of one catalog row and the (score desc, row asc) ranking of a candidate list — shared by the
+// standalone exact pass (finalize.cu), the fused tail of the single-query kernel (gemv_topk.cu) and the one-CTA kernel
+// for tiny catalogs (small.cu), so that every route produces bit-identical scores for the same row and query.
+//
+// The formula is the oracle's (sklearn cosine_similarity, lib.py:51): x / ||x||, y / ||y||, dot.  DIV = true keeps
+// sklearn's operation order (normalize() divides every element by the row norm BEFORE the dot), which is what makes rows
+// that tie exactly in the float64 reference (d = 1, scaled one-hot rows) tie here as well.
+#pragma once
+
+#include "common.cuh"
+
+namespace rebert {
+
+__device__ __forceinline__ bool better(double sa, int64_t ra, double sb, int64_t rb) {
+    return sa > sb || (sa == sb && ra < rb);
+}
+
+template <bool DIV> __device__ __forceinline__ double unit(double x, double nrm) { return DIV ? x / nrm : x; }
+
+// 16-byte chunk of a stored row times the matching query slice.  q[p] holds query elements 2p, 2p+1 of the chunk.
+template <typename T> struct ChunkDot;
+template <> struct ChunkDot<float> {
+    static constexpr int EPC = 4;
+    static constexpr int PAIRS = 2;
+    template <bool DIV>
+    __device__ static __forceinline__ double dot(const uint4& v, const double2* q, double acc, double nrm) {
+        acc = fma(q[0].x, unit<DIV>((double)__uint_as_float(v.x), nrm), acc);
+        acc = fma(q[0].y, unit<DIV>((double)__uint_as_float(v.y), nrm), acc);
+        acc = fma(q[1].x, unit<DIV>((double)__uint_as_float(v.z), nrm), acc);
+        acc = fma(q[1].y, unit<DIV>((double)__uint_as_float(v.w), nrm), acc);
+        return acc;
+    }
+};
+template <> struct ChunkDot<__nv_bfloat16> {
+    static constexpr int EPC = 8;
+    static constexpr int PAIRS = 4;
+    template <bool DIV>
+    __device__ static __forceinline__ double dot(const uint4& v, const double2* q, double acc, double nrm) {
+        acc = fma(q[0].x, unit<DIV>((double)bf16lo(v.x), nrm), acc);
+        acc = fma(q[0].y, unit<DIV>((double)bf16hi(v.x), nrm), acc);
+        acc = fma(q[1].x, unit<DIV>((double)bf16lo(v.y), nrm), acc);
+        acc = fma(q[1].y, unit<DIV>((double)bf16hi(v.y), nrm), acc);
+        acc = fma(q[2].x, unit<DIV>((double)bf16lo(v.z), nrm), acc);
+        acc = fma(q[2].y, unit<DIV>((double)bf16hi(v.z), nrm), acc);
+        acc = fma(q[3].x, unit<DIV>((double)bf16lo(v.w), nrm), acc);
+        acc = fma(q[3].y, unit<DIV>((double)bf16hi(v.w), nrm), acc);
+        return acc;
+    }
+};
+
+// Where the fp64 query comes from.  "Pair planes" in shared memory: element e of chunk ch lives at
+// ((e >> 1) * chunks + ch) * 2 + (e & 1), so the 32 lanes of a warp (consecutive chunks) read consecutive 16-byte
+// double2's — conflict-free LDS.128.  "Global": the natural [ld] layout, read through the read-only path.
+struct QueryPlanes {
+    const double* sq;
+    int chunks;
+    template <int PAIRS> __device__ __forceinline__ void load(int ch, double2* q) const {
+#pragma unroll
+        for (int p = 0; p < PAIRS; ++p) q[p] = *(const double2*)(sq + ((size_t)p * chunks + ch) * 2);
+    }
+};
+struct QueryGlobal {
+    const double* q64;
+    template <int PAIRS> __device__ __forceinline__ void load(int ch, double2* q) const {
+#pragma unroll
+        for (int p = 0; p < PAIRS; ++p) q[p] = __ldg((const double2*)(q64 + (size_t)ch * (2 * PAIRS)) + p);
+    }
+};
+__device__ __forceinline__ void stage_query_planes(const double* __restrict__ q, int ld, int epc, double* s_q) {
+    const int chunks = ld / epc;
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        const int ch = i / epc, e = i - ch * epc;
+        s_q[((size_t)(e >> 1) * chunks + ch) * 2 + (e & 1)] = q[i];
+    }
+}
+
+// One warp, one row: every lane returns the score.  The summation order is fixed (lane-strided chunks, two
+// accumulators, xor-shuffle tree), so the result depends on nothing but the row and the query.
+template <typename T, bool DIV, typename Q>
+__device__ __forceinline__ double exact_score_row(const T* __restrict__ rows, int ld, const double* __restrict__ norm64,
+                                                  uint32_t local_row, const Q& qsrc, int lane) {
+    constexpr int EPC = ChunkDot<T>::EPC;
+    constexpr int PAIRS = ChunkDot<T>::PAIRS;
+    const int chunks = ld / EPC;
+    const uint4* row = (const uint4*)(rows + (size_t)local_row * ld);
+    const double nrm = __ldg(norm64 + local_row);
+    double a0 = 0.0, a1 = 0.0;
+    int ch = lane;
+    for (; ch + 32 < chunks; ch += 64) {                 // two independent 16-byte loads in flight per lane
+        const uint4 v0 = __ldg(row + ch), v1 = __ldg(row + ch + 32);
+        double2 q0[PAIRS], q1[PAIRS];
+        qsrc.template load<PAIRS>(ch, q0);
+        qsrc.template load<PAIRS>(ch + 32, q1);
+        a0 = ChunkDot<T>::template dot<DIV>(v0, q0, a0, nrm);
+        a1 = ChunkDot<T>::template dot<DIV>(v1, q1, a1, nrm);
+    }
+    if (ch < chunks) {
+        double2 q0[PAIRS];
+        qsrc.template load<PAIRS>(ch, q0);
+        a0 = ChunkDot<T>::template dot<DIV>(__ldg(row + ch), q0, a0, nrm);
+    }
+    return DIV ? warp_sum(a0 + a1) : warp_sum(a0 + a1) / nrm;
+}
+
+// Runtime-dtype front end (the catalog of record is fp32 or bf16), sklearn operation order.
+template <typename Q>
+__device__ __forceinline__ double exact_score_row_rt(const void* rows, int dtype, int ld, const double* norm64, uint32_t local_row,
+                                                     const Q& qsrc, int lane) {
+    if (dtype == REBERT_F32) return exact_score_row<float, true>((const float*)rows, ld, norm64, local_row, qsrc, lane);
+    return exact_score_row<__nv_bfloat16, true>((const __nv_bfloat16*)rows, ld, norm64, local_row, qsrc, lane);
+}
+
+// Rank `kc` re-scored candidates (s_row[c] < 0 = empty slot) by (score desc, row asc): the best k go to o_rows / o_scores
+// (-1 / -inf padded), their number to *o_count.  fast_last = fast score of the worst kept candidate when the fast pass's
+// list was full (list_full): *o_margin = exact k-th - fast_last - 4 max|fast - exact| proves the id set when it exceeds the
+// fast pass's error bound; +inf when the list was not full (every allowed row is a candidate), -inf when two distinct
+// scores at or above the k-th place sit within 4 ulp and the caller computed them divide-after (neartie_matters).
+// Every thread of the CTA must call; outputs may be shared, global or device-addressable pinned host memory.
+__device__ __forceinline__ void rank_candidates(const double* s_score, const int64_t* s_row, int kc, int k, bool list_full, double fast_last,
+                                                double maxerr, bool neartie_matters, int64_t* o_rows, double* o_scores, int32_t* o_count,
+                                                double* o_margin, int* s_tmp /* 2 ints of shared scratch */,
+                                                double* s_kth /* 1 double of shared scratch */) {
+    if (threadIdx.x == 0) { s_tmp[0] = 0; s_tmp[1] = 0; *s_kth = 0.0; }
+    __syncthreads();
+    int mine = 0;
+    for (int c = threadIdx.x; c < kc; c += blockDim.x) mine += s_row[c] >= 0;
+    if (mine) atomicAdd(&s_tmp[0], mine);
+    __syncthreads();
+    const int valid = s_tmp[0];
+    const int nout = valid < k ? valid : k;
+    for (int c = threadIdx.x; c < kc; c += blockDim.x) {
+        const int64_t r = s_row[c];
+        if (r < 0) continue;
+        const double sc = s_score[c];
+        int rank = 0;
+        bool near = false;
+        for (int j = 0; j < kc; ++j) {
+            const int64_t rj = s_row[j];
+            if (rj < 0) continue;
+            const double sj = s_score[j];
+            if (better(sj, rj, sc, r)) ++rank;
+            const double gap = fabs(sj - sc);
+            near |= gap != 0.0 && gap <= 8.9e-16 * fmax(fabs(sc), 1e-300);   // distinct scores within 4 ulp
+        }
+        if (neartie_matters && near && rank <= k) s_tmp[1] = 1;    // a divide-after formula cannot be trusted to order these
+        if (rank < k) {
+            o_rows[rank] = r;
+            o_scores[rank] = sc;
+            if (rank == k - 1) *s_kth = sc;
+        }
+    }
+    for (int i = nout + threadIdx.x; i < k; i += blockDim.x) {
+        o_rows[i] = -1;
+        o_scores[i] = -INFINITY;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *o_count = nout;
+        if (o_margin) {
+            double mg = (list_full && valid >= k) ? *s_kth - fast_last - 4.0 * maxerr : INFINITY;
+            if (s_tmp[1]) mg = -INFINITY;
+            *o_margin = mg;
+        }
+    }
+}
+
+}  // namespace rebert

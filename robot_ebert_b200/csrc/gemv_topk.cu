@@ -16,12 +16,18 @@
 //   * at the end the 8 warp lists are rank-merged through shared memory into one sorted list per CTA, and the last
 //     CTA to finish (atomic ticket) merges the per-CTA lists behind two pruning thresholds — one launch per query.
 //     The N-long score vector never exists;
-//   * launched with programmatic stream serialization: no global access before griddepcontrol.wait.
+//   * FUSED TAIL (rebert_gemv_topk_fused, the request path): the last CTA does not stop at the candidate keys — its warps
+//     re-score the kc winners in fp64 with the oracle's formula (exact.cuh), rank them by (score desc, row asc), write the
+//     packed result (device or pinned host memory) and, on a row shard, run the NVLink exchange + merge (exchange.cuh).
+//     One launch per request instead of three;
+//   * launched with programmatic stream serialization: no access to memory an earlier kernel of the stream writes before
+//     griddepcontrol.wait.  The catalog is immutable, so the producer starts streaming the first tiles BEFORE that wait:
+//     the first TMA round trip overlaps the previous kernel's tail (query staging / the previous request's merge).
 #include <stdlib.h>
 
 #include <type_traits>
 
-#include "common.cuh"
+#include "exchange.cuh"
 
 namespace rebert {
 
@@ -53,7 +59,21 @@ struct GemvParams {
     int64_t      static_rounds;  // every CTA takes tiles blockIdx.x + i * grid for i < static_rounds, the rest are claimed
     unsigned long long* trace;  // tuning only (REBERT_GEMV_TRACE): [grid + 1][8] %globaltimer stamps, or nullptr
     int          cta_hint;  // 1 = CTA-level quantile hint from the warps' (kc/8)-th best keys (default; 0 is a tuning knob)
+    int          merge_prune; // 1 = the CTA merge drops keys below the threshold hints (default; 0 is a tuning knob)
+    int          early_tma; // 1 = first tiles are requested before griddepcontrol.wait (default; 0 is a tuning knob)
     int          merge_cap; // keys the final merge may hold in shared memory (power of two)
+    int*         cta_count; // [grid] keys each CTA published
+    // ---- fused tail (fused != 0): exact pass + result (+ exchange) inside this launch
+    int          fused;
+    int          k;
+    const void*  x_rows;    // catalog of record the exact pass reads (differs from `rows` when an int8 shadow is streamed)
+    const double* x_norm64;
+    const double* q64;      // [x_ld] fp64 unit query / profile
+    int          x_ld, x_dtype;
+    int64_t      row_base;
+    unsigned long long* out_packed;  // rows k | fp64 scores k | count + tag | margin   (device or pinned host memory)
+    uint32_t     tag;
+    Exchange     xchg;      // xchg.world > 1: the last CTA exchanges + merges with the peers before writing out_packed
 };
 
 template <typename T> struct Elem;
@@ -180,20 +200,25 @@ __device__ void chunked_merge(const uint64_t* __restrict__ in, int total, int kc
     for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
 }
 
-__device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int kc, int cap, uint64_t* buf,
-                            uint64_t* __restrict__ out) {
+constexpr int kMaxLists = 256;               // per-CTA lists the final merge can index (grid <= number of SMs <= 256)
+
+// `out` may be shared or global memory.  counts_g[l] = keys list l really holds (the rest of its kc slots are zero).
+__device__ void final_merge(const uint64_t* __restrict__ lists_g, const int* __restrict__ counts_g, int lists, int kc, int cap,
+                            uint64_t* buf, uint64_t* out) {
     __shared__ unsigned long long s_t0, s_t1;
     __shared__ int s_cnt;
-    const int total = lists * kc;
+    __shared__ int s_lcnt[kMaxLists];
+    __shared__ int s_pref[kMaxLists + 1];
     if (threadIdx.x == 0) { s_t0 = 0; s_t1 = 0; s_cnt = 0; }
     __syncthreads();
-    // T0 and the prefix set of T1 come from the same round of loads (every L2 round trip here is on the critical path
-    // of the whole launch: the other CTAs have already gone)
+    // The list sizes, T0 and the prefix set of T1 come from the same round of loads (every L2 round trip here is on the
+    // critical path of the whole launch: the other CTAs have already gone)
     const int P = (kc + lists - 1) / lists;
     const int S = P * lists;                       // kc <= S < kc + lists <= cap
     unsigned long long t0 = 0;
     for (int l = threadIdx.x; l < lists; l += blockDim.x) {
         const unsigned long long v = ldcg_u64(lists_g + (size_t)l * kc + kc - 1);
+        s_lcnt[l] = __ldcg(counts_g + l);
         t0 = v > t0 ? v : t0;
     }
     for (int e0 = threadIdx.x; e0 < S; e0 += 2 * blockDim.x) {
@@ -210,6 +235,12 @@ __device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int
     }
     if ((threadIdx.x & 31) == 0 && t0) atomicMax(&s_t0, t0);
     __syncthreads();
+    // exclusive prefix of the list sizes (<= 256 lists: every thread sums its own prefix, no scan needed)
+    for (int l = threadIdx.x; l <= lists; l += blockDim.x) {
+        int acc = 0;
+        for (int j = 0; j < l; ++j) acc += s_lcnt[j];
+        s_pref[l] = acc;
+    }
     // T1: rank-count for the kc-th largest of the prefix set
     for (int e = threadIdx.x; e < S; e += blockDim.x) {
         const uint64_t key = buf[e];
@@ -220,14 +251,21 @@ __device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int
     }
     __syncthreads();
     const uint64_t T = s_t0 > s_t1 ? s_t0 : s_t1;
-    // gather survivors (loads issued sixteen at a time so their L2 latencies overlap: 148 lists of 32 keys = one round)
+    const int total = s_pref[lists];
+    // gather survivors: only the slots the lists really fill are read (hint pruning leaves ~kc per CTA of the 8 kc a CTA
+    // could hold), sixteen loads in flight per thread so their L2 latencies overlap
     constexpr int kInFlight = 16;
     for (int i0 = threadIdx.x; i0 < total; i0 += kInFlight * blockDim.x) {
         uint64_t kk[kInFlight];
 #pragma unroll
         for (int j = 0; j < kInFlight; ++j) {
             const int i = i0 + j * blockDim.x;
-            kk[j] = i < total ? ldcg_u64(lists_g + i) : 0;
+            kk[j] = 0;
+            if (i < total) {
+                int lo = 0, hi = lists;                  // list l with s_pref[l] <= i < s_pref[l + 1]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pref[mid] <= i) lo = mid; else hi = mid; }
+                kk[j] = ldcg_u64(lists_g + (size_t)lo * kc + (i - s_pref[lo]));
+            }
         }
 #pragma unroll
         for (int j = 0; j < kInFlight; ++j) {
@@ -241,7 +279,7 @@ __device__ void final_merge(const uint64_t* __restrict__ lists_g, int lists, int
     const int cnt = s_cnt;
     if (cnt > cap) {                               // mass ties: correct but slow path
         __syncthreads();
-        chunked_merge(lists_g, total, kc, cap, buf, out);
+        chunked_merge(lists_g, lists * kc, kc, cap, buf, out);
         return;
     }
     int p2 = 2;
@@ -278,6 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     REBERT_TRACE(0);                                   // kernel entry
 
+    __shared__ int s_tile[kMaxStages];          // tile held by each stage, written by the producer before it arms the barrier
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -285,10 +324,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
         }
         fence_mbar_init();
     }
-    // Programmatic dependent launch: everything above touched shared memory only.  Let the next kernel of the stream
-    // place its CTAs as ours retire, then wait until the previous kernel (query normalisation / profile build / the
-    // previous request) has completed before the first global access.
+    __syncthreads();
+    // Programmatic dependent launch: let the next kernel of the stream place its CTAs as ours retire.
     pdl_trigger();
+    // The catalog (rows, inv_norm) is immutable, so the first tiles can be requested BEFORE waiting for the previous kernel
+    // of the stream (query staging / profile build / the previous request's merge): the first TMA round trip and the
+    // pipeline fill overlap that kernel's tail.  Everything an earlier kernel writes — the query, the exclusion list, the
+    // workspace counters — is touched only after pdl_wait().
+    const int row_bytes_e = p.ld * (int)sizeof(T);
+    int early = 0;                                     // tiles issued before pdl_wait (producer lane only)
+    auto issue_tile = [&](int it, int64_t t, uint64_t policy) {
+        const int s = it % p.stages;
+        s_tile[s] = (int)t;
+        const int64_t row0 = t * p.tile_rows;
+        const int64_t left = p.n - row0;
+        const int nrows = left < p.tile_rows ? (int)left : p.tile_rows;
+        const uint32_t bytes = (uint32_t)nrows * (uint32_t)row_bytes_e;
+        const uint32_t ibytes = (uint32_t)(nrows & ~3) * 4u;   // tail (<4 rows) is read through __ldg
+        unsigned char* dst = stage_base + (size_t)s * stage_stride;
+        mbar_arrive_expect_tx(&full_bar[s], bytes + ibytes);
+        bulk_g2s(dst, (const unsigned char*)p.rows + row0 * row_bytes_e, bytes, &full_bar[s], policy);
+        if (ibytes) bulk_g2s(dst + tile_bytes, p.inv_norm + row0, ibytes, &full_bar[s], policy);
+    };
+    if (warp == kConsumerWarps && lane == 0 && p.early_tma) {
+        const uint64_t policy = p.l2_policy == 0 ? l2_policy_evict_first() : (p.l2_policy == 2 ? l2_policy_evict_last() : l2_policy_evict_normal());
+        for (; early < p.stages && early < p.static_rounds; ++early) {
+            const int64_t t = blockIdx.x + early * (int64_t)gridDim.x;
+            if (t >= p.num_tiles) break;
+            issue_tile(early, t, policy);
+        }
+    }
     pdl_wait();
     if (!kRegQ) {
         for (int c = threadIdx.x; c < p.ld; c += blockDim.x) q_smem[c] = p.q[c];
@@ -304,7 +369,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if ((threadIdx.x & 31) == 0) s_qmax[threadIdx.x >> 5] = m;
     }
-    __syncthreads();
 
     WarpTopK<M> top;
     top.init();
@@ -317,7 +381,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     // It is recomputed only by a warp that has just inserted (the rare path); the per-tile cost stays one shared load.
     __shared__ unsigned s_hint;
     __shared__ unsigned s_wq[kConsumerWarps];   // orderable score of warp w's (kc/8)-th best key, 0 = not there yet
-    __shared__ int s_tile[kMaxStages];          // tile held by each stage, written by the producer before it arms the barrier
     if (threadIdx.x == 0) s_hint = 0u;
     if (threadIdx.x < kConsumerWarps) s_wq[threadIdx.x] = 0u;
     __syncthreads();
@@ -338,31 +401,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                 c0 = atomicAdd(p.tile_ctr, 1u); c1 = atomicAdd(p.tile_ctr, 1u);
                 c2 = atomicAdd(p.tile_ctr, 1u); c3 = atomicAdd(p.tile_ctr, 1u);
             }
-            int it = 0;
+            int it = early;                                                  // stages [0, early) were armed before pdl_wait
             auto issue = [&](int64_t t) {
                 const int s = it % p.stages;
                 const uint32_t round = (uint32_t)(it / p.stages);
                 mbar_wait(&empty_bar[s], (round & 1u) ^ 1u);
-                ++it;
                 if (t >= p.num_tiles) {                                      // tell the consumers there is nothing more
                     s_tile[s] = -1;
                     mbar_arrive(&full_bar[s]);
+                    ++it;
                     return false;
                 }
-                s_tile[s] = (int)t;
-                const int64_t row0 = t * p.tile_rows;
-                const int64_t left = p.n - row0;
-                const int nrows = left < p.tile_rows ? (int)left : p.tile_rows;
-                const uint32_t bytes = (uint32_t)nrows * (uint32_t)row_bytes;
-                const uint32_t ibytes = (uint32_t)(nrows & ~3) * 4u;   // tail (<4 rows) is read through __ldg
-                unsigned char* dst = stage_base + (size_t)s * stage_stride;
-                mbar_arrive_expect_tx(&full_bar[s], bytes + ibytes);
-                bulk_g2s(dst, (const unsigned char*)p.rows + row0 * row_bytes, bytes, &full_bar[s], policy);
-                if (ibytes) bulk_g2s(dst + tile_bytes, p.inv_norm + row0, ibytes, &full_bar[s], policy);
+                issue_tile(it, t, policy);
+                ++it;
                 return true;
             };
             bool more = true;
-            for (int64_t i = 0; i < p.static_rounds && more; ++i) more = issue(blockIdx.x + i * (int64_t)gridDim.x);
+            for (int64_t i = early; i < p.static_rounds && more; ++i) more = issue(blockIdx.x + i * (int64_t)gridDim.x);
             if (more && !has_tail) more = issue(p.num_tiles);                // static only: post the end marker
             while (more) {
                 if (!(more = issue(tail0 + c0))) break;
@@ -571,13 +626,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     REBERT_TRACE(4);                                   // all warps finished
     uint64_t* lists = (uint64_t*)smem;           // [kConsumerWarps][kc]
     const int kc = p.kc;
-    __shared__ int s_kept[kConsumerWarps];       // non-empty entries of each warp list
+    __shared__ int s_kept[kConsumerWarps];       // entries of each warp list that can still matter
     if (warp < kConsumerWarps) {
+        // Keys scoring below the best lower bound of the global kc-th best (CTA hint, or the grid-wide word) cannot be in
+        // the result: drop them here, so only ~kc of the CTA's 8 kc keys go through the rank merge and reach the final
+        // merge.  The lists are sorted, so the dropped keys are a tail and the zero-terminated-list convention holds.
+        const unsigned hb = p.merge_prune ? max(*(volatile unsigned*)&s_hint, __ldcg(p.ghint)) : 0u;
         int kept = 0;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            lists[warp * kc + m * 32 + lane] = top.keys[m];
-            kept += __popc(__ballot_sync(0xffffffffu, top.keys[m] != 0));
+            const uint64_t key = ((unsigned)(top.keys[m] >> 32) >= hb) ? top.keys[m] : 0;
+            lists[warp * kc + m * 32 + lane] = key;
+            kept += __popc(__ballot_sync(0xffffffffu, key != 0));
         }
         if (lane == 0) s_kept[warp] = kept;
     }
@@ -586,21 +646,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     int total = 0;
 #pragma unroll
     for (int w = 0; w < kConsumerWarps; ++w) total += s_kept[w];
-    for (int i = threadIdx.x; i < kConsumerWarps * kc; i += blockDim.x) {
-        const uint64_t key = lists[i];
-        if (key == 0) continue;
-        const int w = i / kc;
-        int rank = i - w * kc;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int w = 0, e = i;                        // i-th kept key overall = entry e of warp list w
+        while (e >= s_kept[w]) { e -= s_kept[w]; ++w; }
+        const uint64_t key = lists[w * kc + e];
+        int rank = e;
         for (int o = 0; o < kConsumerWarps; ++o) {
             if (o == w) continue;
             const uint64_t* L = lists + o * kc;
-            int lo = 0, hi = kc;                 // count of keys in L greater than key
+            int lo = 0, hi = s_kept[o];          // count of keys in L greater than key
             while (lo < hi) { int mid = (lo + hi) >> 1; if (L[mid] > key) lo = mid + 1; else hi = mid; }
             rank += lo;
         }
         if (rank < kc) out[rank] = key;
     }
     for (int i = total + threadIdx.x; i < kc; i += blockDim.x) out[i] = 0;
+    if (threadIdx.x == 0) p.cta_count[blockIdx.x] = total < kc ? total : kc;
 
     // ===================== last CTA to finish merges all per-CTA lists (no second launch) =====================
     __shared__ int s_last;
@@ -611,7 +672,52 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    final_merge(p.cta_lists, (int)gridDim.x, kc, p.merge_cap, (uint64_t*)smem, p.cand_keys);
+    if (!p.fused) {
+        final_merge(p.cta_lists, p.cta_count, (int)gridDim.x, kc, p.merge_cap, (uint64_t*)smem, p.cand_keys);
+    } else {
+        // ---- fused tail: exact pass over the kc winners, ranking, result (and the exchange on a row shard)
+        uint64_t* fk = (uint64_t*)smem + p.merge_cap;                  // [kc] winners, best fast score first
+        double* s_score = (double*)(fk + kc);                          // [kc]
+        int64_t* s_row = (int64_t*)(s_score + kc);                     // [kc]
+        unsigned long long* s_block = (unsigned long long*)(s_row + kc);   // [2k + 2] packed local result (row shards)
+        __shared__ unsigned long long s_maxerr;
+        __shared__ int s_tmp[2];
+        __shared__ double s_kth;
+        final_merge(p.cta_lists, p.cta_count, (int)gridDim.x, kc, p.merge_cap, (uint64_t*)smem, fk);
+        if (threadIdx.x == 0) s_maxerr = 0ull;
+        __syncthreads();
+        REBERT_TRACE(6);                               // winners known
+        const QueryGlobal qsrc{p.q64};
+        for (int c = warp; c < kc; c += kThreads / 32) {
+            const uint64_t key = fk[c];
+            double sc = -INFINITY;
+            int64_t gr = -1;
+            if (key != 0) {
+                const uint32_t lr = key_row(key);
+                sc = exact_score_row_rt(p.x_rows, p.x_dtype, p.x_ld, p.x_norm64, lr, qsrc, lane);
+                gr = p.row_base + lr;
+            }
+            if (lane == 0) {
+                s_score[c] = sc;
+                s_row[c] = gr;
+                if (key != 0) atomicMax(&s_maxerr, (unsigned long long)__double_as_longlong(fabs(sc - (double)key_score(key))));
+            }
+        }
+        __syncthreads();
+        REBERT_TRACE(7);                               // exact pass done
+        const int k = p.k;
+        const uint64_t last = fk[kc - 1];
+        const bool exchange = p.xchg.world > 1;
+        unsigned long long* blk = exchange ? s_block : p.out_packed;
+        rank_candidates(s_score, s_row, kc, k, last != 0, last ? (double)key_score(last) : 0.0,
+                        __longlong_as_double((long long)s_maxerr), /*neartie_matters=*/false, (int64_t*)blk, (double*)(blk + k),
+                        (int32_t*)(blk + 2 * k), (double*)(blk + 2 * k + 1), s_tmp, &s_kth);
+        if (threadIdx.x == 0) ((uint32_t*)(blk + 2 * k))[1] = p.tag;
+        if (exchange) {
+            __syncthreads();
+            exchange_results(p.xchg, k, s_block, p.out_packed);
+        }
+    }
     if (p.trace && threadIdx.x == 0) { p.trace[(size_t)gridDim.x * 8] = globaltimer_ns(); p.trace[(size_t)gridDim.x * 8 + 1] = blockIdx.x; }
     if (threadIdx.x == 0) { *p.counter = 0; *p.ghint = 0u; *p.tile_ctr = 0u; }
 }
@@ -626,6 +732,8 @@ struct GemvKnobs {
     int l2_policy = 0;
     int cta_hint = 1;
     int dyn_pct = 12;          // share of the tiles claimed dynamically at the end; 0 = all static
+    int merge_prune = 1;       // CTA merge drops keys below the threshold hints
+    int early_tma = 1;         // first tiles requested before griddepcontrol.wait
     unsigned long long* trace = nullptr;
 };
 static GemvKnobs read_knobs() {
@@ -635,6 +743,8 @@ static GemvKnobs read_knobs() {
     if (const char* e = getenv("REBERT_GEMV_L2_POLICY")) k.l2_policy = atoi(e);
     if (const char* e = getenv("REBERT_GEMV_CTA_HINT")) k.cta_hint = atoi(e) != 0;
     if (const char* e = getenv("REBERT_GEMV_DYN_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) k.dyn_pct = v; }
+    if (const char* e = getenv("REBERT_GEMV_MERGE_PRUNE")) k.merge_prune = atoi(e) != 0;
+    if (const char* e = getenv("REBERT_GEMV_EARLY_TMA")) k.early_tma = atoi(e) != 0;
     if (const char* e = getenv("REBERT_GEMV_TRACE")) k.trace = (unsigned long long*)strtoull(e, nullptr, 0);
     return k;
 }
@@ -674,12 +784,14 @@ static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic,
     g.smem = (size_t)stages * stage_stride + fixed;
     size_t merge_bytes = (size_t)kConsumerWarps * kc * sizeof(uint64_t);
     if (g.smem < merge_bytes) g.smem = merge_bytes;
-    // final merge buffer: a power of two >= max(2 kc, kc + grid), as large as the pipeline memory allows (<= 16384 keys)
+    // final merge buffer: a power of two >= max(2 kc, kc + grid), as large as the pipeline memory allows (<= 16384 keys);
+    // behind it the fused tail keeps the winners, their exact scores / rows and the packed local result (k <= kc)
     int need = 2 * kc > kc + num_sms() ? 2 * kc : kc + num_sms();
     int cap = 2;
     while (cap < need) cap <<= 1;
-    while (cap < 16384 && (size_t)cap * 2 * sizeof(uint64_t) <= g.smem) cap <<= 1;
-    if (g.smem < (size_t)cap * sizeof(uint64_t)) g.smem = (size_t)cap * sizeof(uint64_t);
+    const size_t tail_extra = (size_t)kc * 24 + (size_t)(2 * kc + 2) * 8;
+    while (cap < 16384 && (size_t)cap * 2 * sizeof(uint64_t) + tail_extra <= g.smem) cap <<= 1;
+    if (g.smem < (size_t)cap * sizeof(uint64_t) + tail_extra) g.smem = (size_t)cap * sizeof(uint64_t) + tail_extra;
     g.merge_cap = cap;
     const int64_t tiles = (n + tr - 1) / tr;
     int grid = num_sms();
@@ -781,14 +893,30 @@ REBERT_API int32_t rebert_candidates_for_k(int32_t k) {
     return 0;
 }
 
+// Workspace layout (kc-INDEPENDENT control words first, so one zero-filled-once workspace serves every kc a thread uses):
+//   [0, 128)      ticket counter, grid-wide hint, tile-claim counter  (zero before a launch; the last CTA leaves them zero)
+//   [128, 1152)   keys each CTA published (int32 x 256)
+//   [1152, ...)   per-CTA candidate lists [num_sms, kc] u64
+constexpr size_t kWsCtl = 128, kWsCounts = 4 * kMaxLists;
+
 REBERT_API size_t rebert_gemv_workspace_bytes(int64_t n, int32_t kc) {
     (void)n;
-    return (size_t)(num_sms() + 1) * (size_t)kc * sizeof(uint64_t) + 256;
+    return 128 + kWsCtl + kWsCounts + (size_t)num_sms() * (size_t)kc * sizeof(uint64_t) + 256;
 }
 
-REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, int32_t kc,
-                     void* workspace, size_t workspace_bytes, uint64_t* cand_keys, rebert_stream stream) {
-    REBERT_REQUIRE(cat && cat->rows && cat->inv_norm && qn32 && workspace && cand_keys, "gemv_topk: null argument");
+REBERT_API int rebert_workspace_reset(void* workspace, size_t workspace_bytes, rebert_stream stream) {
+    REBERT_REQUIRE(workspace && workspace_bytes >= 128 + kWsCtl + kWsCounts, "workspace_reset: bad arguments");
+    REBERT_CUDA(cudaMemsetAsync(workspace, 0, 128 + kWsCtl + kWsCounts, (cudaStream_t)stream));
+    return REBERT_OK;
+}
+
+}  // extern "C"
+
+namespace rebert {
+
+int gemv_launch(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, int32_t kc, void* workspace,
+                size_t workspace_bytes, uint64_t* cand_keys, const GemvFused* fused, cudaStream_t st) {
+    REBERT_REQUIRE(cat && cat->rows && cat->inv_norm && qn32 && workspace && (cand_keys || fused), "gemv_topk: null argument");
     REBERT_REQUIRE(cat->n >= 0 && cat->n < (1ll << 31), "gemv_topk: shard rows %lld out of range", (long long)cat->n);
     REBERT_REQUIRE(cat->dtype == REBERT_F32 || cat->dtype == REBERT_BF16 || cat->dtype == REBERT_I8, "gemv_topk: dtype %d", cat->dtype);
     REBERT_REQUIRE(cat->dtype != REBERT_I8 || kc == 256, "gemv_topk: the int8 prefilter shadow needs kc = 256 (got %d)", kc);
@@ -804,16 +932,27 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
         set_error("gemv_topk: workspace %zu < %zu", workspace_bytes, rebert_gemv_workspace_bytes(cat->n, kc));
         return REBERT_ERR_WORKSPACE;
     }
-    cudaStream_t st = (cudaStream_t)stream;
+    REBERT_REQUIRE(num_sms() <= kMaxLists, "gemv_topk: device has %d SMs, the final merge indexes at most %d lists", num_sms(), kMaxLists);
+    if (fused) {
+        const rebert_catalog_t* xc = fused->exact_cat;
+        REBERT_REQUIRE(xc && xc->rows && xc->norm64 && fused->q64 && fused->out_packed, "recommend_device: null argument");
+        REBERT_REQUIRE(xc->dtype == REBERT_F32 || xc->dtype == REBERT_BF16, "recommend_device: the catalog of record must be fp32 or bf16");
+        REBERT_REQUIRE(xc->n == cat->n && xc->d == cat->d && xc->row_base == cat->row_base, "recommend_device: shadow and catalog differ in shape");
+        REBERT_REQUIRE(fused->k > 0 && fused->k <= kc, "recommend_device: k=%d kc=%d", fused->k, kc);
+    }
     if (cat->n == 0) {
-        REBERT_CUDA(cudaMemsetAsync(cand_keys, 0, (size_t)kc * sizeof(uint64_t), st));
-        return REBERT_OK;
+        if (!fused) {
+            REBERT_CUDA(cudaMemsetAsync(cand_keys, 0, (size_t)kc * sizeof(uint64_t), st));
+            return REBERT_OK;
+        }
+        // an empty shard still has to answer (and, on a row shard, to take part in the exchange): run one empty tile
     }
     const bool generic = use_generic(L);
     const int n_excl = (filter && filter->exclude_rows && filter->n_exclude > 0) ? filter->n_exclude : 0;
     const GemvKnobs knobs = gemv_knobs();
     GemvLaunch g = plan_gemv(L, cat->n, kc, generic, n_excl, knobs);
     GemvParams p;
+    memset(&p, 0, sizeof(p));
     p.rows = cat->rows;
     p.inv_norm = cat->inv_norm;
     p.q = qn32;
@@ -827,10 +966,12 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     p.kc = kc;
     p.l2_policy = knobs.l2_policy;
     p.filter = make_filter(filter, cat->row_base);
-    p.cta_lists = (uint64_t*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
-    p.counter = (unsigned*)(p.cta_lists + (size_t)num_sms() * kc);
+    unsigned char* ws = (unsigned char*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
+    p.counter = (unsigned*)ws;
     p.ghint = p.counter + 1;
     p.tile_ctr = p.counter + 2;
+    p.cta_count = (int*)(ws + kWsCtl);
+    p.cta_lists = (uint64_t*)(ws + kWsCtl + kWsCounts);
     {
         // share of the tiles claimed dynamically at the end (balances SMs of unequal speed); 0 = all static
         const int dyn_pct = knobs.dyn_pct;
@@ -842,11 +983,58 @@ REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, 
     }
     p.trace = knobs.trace;
     p.cta_hint = knobs.cta_hint;
+    p.merge_prune = knobs.merge_prune;
+    p.early_tma = knobs.early_tma;
     p.cand_keys = cand_keys;
     p.merge_cap = g.merge_cap;
+    if (fused) {
+        p.fused = 1;
+        p.k = fused->k;
+        p.x_rows = fused->exact_cat->rows;
+        p.x_norm64 = fused->exact_cat->norm64;
+        p.x_ld = fused->exact_cat->ld;
+        p.x_dtype = fused->exact_cat->dtype;
+        p.q64 = fused->q64;
+        p.row_base = cat->row_base;
+        p.out_packed = fused->out_packed;
+        p.tag = fused->tag;
+        if (fused->xchg) p.xchg = *fused->xchg;
+    }
 
     if (cat->dtype == REBERT_I8) return launch_gemv_i8(L, p, g, st);
     return cat->dtype == REBERT_F32 ? launch_gemv<float>(L, p, g, kc, st) : launch_gemv<__nv_bfloat16>(L, p, g, kc, st);
+}
+
+}  // namespace rebert
+
+extern "C" {
+
+REBERT_API int rebert_gemv_topk(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, int32_t kc,
+                     void* workspace, size_t workspace_bytes, uint64_t* cand_keys, rebert_stream stream) {
+    REBERT_REQUIRE(cand_keys, "gemv_topk: null argument");
+    return gemv_launch(cat, qn32, filter, kc, workspace, workspace_bytes, cand_keys, nullptr, (cudaStream_t)stream);
+}
+
+REBERT_API int rebert_recommend_device(const rebert_catalog_t* cat, const rebert_catalog_t* shadow, const float* qn32, const double* qn64,
+                                       const rebert_filter_t* filter, int32_t k, int32_t kc, void* workspace, size_t workspace_bytes,
+                                       int64_t* out_packed, uint32_t tag, const rebert_exchange_t* exchange, int32_t* err_flag,
+                                       rebert_stream stream) {
+    REBERT_REQUIRE(cat && qn64 && out_packed, "recommend_device: null argument");
+    GemvFused f;
+    f.exact_cat = cat;
+    f.q64 = qn64;
+    f.k = k;
+    f.out_packed = (unsigned long long*)out_packed;
+    f.tag = tag;
+    Exchange x;
+    f.xchg = nullptr;
+    if (exchange && exchange->world > 1) {
+        int rc = make_exchange(exchange, err_flag, &x);
+        if (rc != REBERT_OK) return rc;
+        REBERT_REQUIRE(k <= exchange->k_max, "recommend_device: k=%d exceeds the exchange buffer's k_max=%d", k, exchange->k_max);
+        f.xchg = &x;
+    }
+    return gemv_launch(shadow ? shadow : cat, qn32, filter, kc, workspace, workspace_bytes, nullptr, &f, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,48 +1,77 @@
 // Host-buffer entry point: one C call = one request of the reference's hot path (lib.py:43-55) end to end.
-// Host pointers in, host pointers out; staging the request, every kernel and the stream synchronisation all happen
-// inside.  A raw query is read by the first kernel straight from the caller's pinned block (zero-copy) and the exact
-// pass writes its packed result straight into that block, so a query request involves no copy-engine operation at
-// all; a liked-rows request ships its lists with one H2D copy.  rebert_recommend_host_sharded appends the fused NVLink
-// exchange + merge for one rank of a row-sharded catalog.  Scratch (pinned host + device) is provided by the caller,
-// so the library still allocates nothing and concurrent callers only need their own scratch + stream.
-#include "common.cuh"
+// Host pointers in, host pointers out.  The request is packed into the caller's pinned block and read from there by the
+// first kernel (zero-copy: no copy-engine operation at all); a staging kernel normalises the query or builds the
+// profile; ONE launch does score + mask + top-k + fp64 exact pass (+ the NVLink exchange and merge on a row shard) and
+// writes the packed result straight into the pinned block; a stream synchronisation ends the call.  Catalogs that fit one
+// CTA (the reference's production 2 269 x 32) take a single kernel (small.cu).  The proof loop lives here too: int8
+// shadow first when the caller has one, then the plain fast pass with 4x more candidates until the margin proves the ids.
+// Scratch (pinned host + device) is provided by the caller, so the library still allocates nothing and concurrent
+// callers only need their own scratch + stream (+ their own exchange channel on a row shard).
+#include <stdlib.h>
+
+#include "exchange.cuh"
 
 namespace rebert {
+
+// REBERT_SMALL=0 switches the one-kernel route for tiny catalogs off (tests compare it with the general route).  Read once,
+// unless REBERT_GEMV_TUNE is set (the convention of the scoring kernel's knobs): getenv is off the per-request path.
+static bool small_route_enabled() {
+    static const bool tuning = getenv("REBERT_GEMV_TUNE") != nullptr;
+    static const bool cached = [] { const char* e = getenv("REBERT_SMALL"); return !(e && e[0] == '0'); }();
+    if (!tuning) return cached;
+    const char* e = getenv("REBERT_SMALL");
+    return !(e && e[0] == '0');
+}
 
 static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct HostLayout {
-    // request block (identical offsets in the pinned buffer and at the start of the device scratch)
-    size_t off_q, off_rp, off_excl, off_col, off_w, in_bytes;
-    // device-only
-    size_t off_qn32, off_qn64, off_sum64, off_wsum, off_ws, ws_bytes, off_cand, off_out, out_bytes, dev_bytes;
-    // pinned-only: result block after the request block
-    size_t pin_out, pin_bytes;
+    // pinned block: request (query | exclusions | liked rows | weights), then the result block, the error word and the
+    // in-flight marker
+    size_t off_q, off_excl, off_col, off_w, in_bytes, pin_out, out_bytes, pin_err, pin_bytes;
+    // device scratch
+    size_t off_dexcl, off_qn32, off_qn64, off_sum64, off_wsum, off_ws, ws_bytes, dev_bytes;
 };
 
 static HostLayout host_layout(int ld, int d, int n_liked_cap, int n_excl_cap, int k, int kc, int64_t n) {
     HostLayout L;
     L.off_q = 0;
-    L.off_rp = al16((size_t)d * 4);
-    L.off_excl = L.off_rp + 16;
+    L.off_excl = al16((size_t)d * 4);
     L.off_col = L.off_excl + al16((size_t)n_excl_cap * 4);
     L.off_w = L.off_col + al16((size_t)n_liked_cap * 4);
     L.in_bytes = L.off_w + al16((size_t)n_liked_cap * 4);
-    size_t o = al256(L.in_bytes);
+    L.pin_out = al256(L.in_bytes);
+    L.out_bytes = (size_t)(2 * k + 2) * 8;
+    L.pin_err = L.pin_out + al16(L.out_bytes);
+    L.pin_bytes = L.pin_err + 256;
+    size_t o = 0;
+    L.ws_bytes = rebert_gemv_workspace_bytes(n, kc);
+    L.off_ws = o; o += al256(L.ws_bytes);                  // first: its control words are what "zero-filled once" is about
+    L.off_dexcl = o; o += al256((size_t)n_excl_cap * 4);
     L.off_qn32 = o; o += al256((size_t)ld * 4);
     L.off_qn64 = o; o += al256((size_t)ld * 8);
     L.off_sum64 = o; o += al256((size_t)ld * 8);
     L.off_wsum = o; o += 256;
-    L.ws_bytes = rebert_gemv_workspace_bytes(n, kc);
-    L.off_ws = o; o += al256(L.ws_bytes);
-    L.off_cand = o; o += al256((size_t)kc * 8);
-    L.out_bytes = (size_t)(2 * k + 2) * 8;
-    L.off_out = o; o += al256(L.out_bytes);
     L.dev_bytes = o;
-    L.pin_out = al256(L.in_bytes);
-    L.pin_bytes = L.pin_out + al256(L.out_bytes + 8);        // + the exchange kernel's error word (sharded entry point)
     return L;
+}
+
+// 32-bit tag of a request (FNV-1a over 64-bit words): travels with every rank's result so the merge can refuse to combine
+// answers to different requests.
+static uint32_t request_tag(const void* a, size_t na, const void* b, size_t nb, const void* c, size_t nc, uint64_t salt) {
+    uint64_t h = 0xcbf29ce484222325ull ^ salt;
+    auto mix = [&](const void* p, size_t nbytes) {
+        const unsigned char* s = (const unsigned char*)p;
+        size_t i = 0;
+        for (; i + 8 <= nbytes; i += 8) { uint64_t v; memcpy(&v, s + i, 8); h = (h ^ v) * 0x100000001b3ull; h ^= h >> 29; }
+        for (; i < nbytes; ++i) h = (h ^ s[i]) * 0x100000001b3ull;
+    };
+    if (a) mix(a, na);
+    if (b) mix(b, nb);
+    if (c) mix(c, nc);
+    uint32_t t = (uint32_t)(h ^ (h >> 32));
+    return t ? t : 1u;
 }
 
 }  // namespace rebert
@@ -54,26 +83,19 @@ extern "C" {
 REBERT_API int rebert_recommend_host_scratch(const rebert_catalog_t* cat, int32_t n_liked_cap, int32_t n_exclude_cap, int32_t k,
                                              size_t* pinned_bytes, size_t* device_bytes) {
     REBERT_REQUIRE(cat && k > 0 && n_liked_cap >= 0 && n_exclude_cap >= 0, "recommend_host_scratch: bad arguments");
-    const int kc_max = 256;
-    HostLayout L = host_layout(cat->ld, cat->d, n_liked_cap, n_exclude_cap, k, kc_max, cat->n);
+    HostLayout L = host_layout(cat->ld, cat->d, n_liked_cap, n_exclude_cap, k, 256, cat->n);
     if (pinned_bytes) *pinned_bytes = L.pin_bytes;
     if (device_bytes) *device_bytes = L.dev_bytes;
     return REBERT_OK;
 }
 
-// Optional last step for a row-sharded catalog: the fused NVLink exchange + merge (rebert_exchange_merge).
-struct HostExchange {
-    const uint64_t* peer_buffers;
-    int32_t world, rank, k_max;
-    uint32_t seq;
-};
-
-static int recommend_host_impl(const rebert_catalog_t* cat, const float* query, const int32_t* liked_rows,
-                               const float* liked_w, int32_t n_liked, const int32_t* exclude_rows, int32_t n_exclude,
-                               const rebert_filter_t* device_filter, int32_t k, int32_t kc, int32_t n_liked_cap,
-                               int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
-                               size_t device_bytes, int64_t* out_rows, double* out_scores, int32_t* out_count,
-                               double* out_margin, rebert_stream stream, const HostExchange* ex) {
+REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* query, const int32_t* liked_rows,
+                                     const float* liked_w, int32_t n_liked, const int32_t* exclude_rows, int32_t n_exclude,
+                                     const rebert_filter_t* device_filter, int32_t k, int32_t kc, int32_t n_liked_cap,
+                                     int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
+                                     size_t device_bytes, const rebert_proof_t* proof, const rebert_exchange_t* exchange,
+                                     int64_t* out_rows, double* out_scores, int32_t* out_count, rebert_request_info_t* info,
+                                     rebert_stream stream) {
     REBERT_REQUIRE(cat && cat->rows && pinned && device_scratch && out_rows && out_scores && out_count, "recommend_host: null argument");
     REBERT_REQUIRE((query != nullptr) != (liked_rows != nullptr), "recommend_host: pass exactly one of query / liked_rows");
     REBERT_REQUIRE(k > 0 && kc >= k && kc <= 256, "recommend_host: k=%d kc=%d", k, kc);
@@ -84,12 +106,10 @@ static int recommend_host_impl(const rebert_catalog_t* cat, const float* query, 
         set_error("Found array with 0 sample(s): user has no liked movies in the catalog");
         return REBERT_ERR_INVALID;
     }
-    // device-only regions are placed by the capacities; the request block is packed by the actual list lengths
-    const HostLayout Lc = host_layout(cat->ld, cat->d, n_liked_cap, n_exclude_cap, k, 256, cat->n);
-    HostLayout L = host_layout(cat->ld, cat->d, liked_rows ? n_liked : 0, n_exclude, k, 256, cat->n);
-    L.off_qn32 = Lc.off_qn32; L.off_qn64 = Lc.off_qn64; L.off_sum64 = Lc.off_sum64; L.off_wsum = Lc.off_wsum;
-    L.off_ws = Lc.off_ws; L.ws_bytes = Lc.ws_bytes; L.off_cand = Lc.off_cand; L.off_out = Lc.off_out;
-    L.dev_bytes = Lc.dev_bytes; L.pin_out = Lc.pin_out; L.pin_bytes = Lc.pin_bytes;
+    const bool sharded = exchange && exchange->world > 1;
+    if (sharded) REBERT_REQUIRE(!liked_rows || cat->ld <= exchange->prof_len, "recommend_host: ld=%d exceeds the exchange buffer's prof_len=%d",
+                                cat->ld, exchange->prof_len);
+    const HostLayout L = host_layout(cat->ld, cat->d, n_liked_cap, n_exclude_cap, k, 256, cat->n);
     if (pinned_bytes < L.pin_bytes || device_bytes < L.dev_bytes) {
         set_error("recommend_host: scratch too small (pinned %zu < %zu or device %zu < %zu)", pinned_bytes, L.pin_bytes,
                   device_bytes, L.dev_bytes);
@@ -100,89 +120,124 @@ static int recommend_host_impl(const rebert_catalog_t* cat, const float* query, 
     unsigned char* dv = (unsigned char*)device_scratch;
     float* qn32 = (float*)(dv + L.off_qn32);
     double* qn64 = (double*)(dv + L.off_qn64);
+    int32_t* excl_dev = (int32_t*)(dv + L.off_dexcl);
+    int32_t* err_word = (int32_t*)(h + L.pin_err);
+    int32_t* in_flight = err_word + 1;
+    unsigned long long* res = (unsigned long long*)(h + L.pin_out);
     int rc;
-    // ---- the request goes into the pinned block.  A raw query is then read by the staging kernel straight from that
-    // block (zero-copy: no copy-engine operation in front of the kernels); a liked-rows request ships with ONE H2D copy.
+    // A previous call on this scratch that never completed (a fault between launch and synchronisation) may have left the
+    // scoring kernel's control words non-zero: clear them before they poison this request.
+    if (*in_flight == 0x5EBE47) {
+        rc = rebert_workspace_reset(dv + L.off_ws, L.ws_bytes, stream);
+        if (rc != REBERT_OK) return rc;
+    }
+    *in_flight = 0x5EBE47;
+    *err_word = 0;
+
+    // ---- the request goes into the pinned block; the kernels read it from there
     if (n_exclude) memcpy(h + L.off_excl, exclude_rows, (size_t)n_exclude * 4);
     if (query) {
         memcpy(h + L.off_q, query, (size_t)cat->d * 4);
-        rc = stage_query_launch((const float*)(h + L.off_q), cat->d, cat->ld, qn32, qn64, (const int32_t*)(h + L.off_excl),
-                                n_exclude, (int32_t*)(dv + L.off_excl), st);
-        if (rc != REBERT_OK) return rc;
     } else {
-        int64_t rp[2] = {0, n_liked};
-        memcpy(h + L.off_rp, rp, 16);
         memcpy(h + L.off_col, liked_rows, (size_t)n_liked * 4);
         if (liked_w) memcpy(h + L.off_w, liked_w, (size_t)n_liked * 4);
-        REBERT_CUDA(cudaMemcpyAsync(dv + L.off_rp, h + L.off_rp, L.in_bytes - L.off_rp, cudaMemcpyHostToDevice, st));
-        double* sum64 = (double*)(dv + L.off_sum64);
-        double* wsum = (double*)(dv + L.off_wsum);
-        rc = rebert_profile_accumulate(cat, (const int64_t*)(dv + L.off_rp), (const int32_t*)(dv + L.off_col),
-                                       liked_w ? (const float*)(dv + L.off_w) : nullptr, 1, sum64, wsum, stream);
+    }
+    const float* q_host = query ? (const float*)(h + L.off_q) : nullptr;
+    const int32_t* liked_host = query ? nullptr : (const int32_t*)(h + L.off_col);
+    const float* w_host = (!query && liked_w) ? (const float*)(h + L.off_w) : nullptr;
+    const int32_t* excl_host = (const int32_t*)(h + L.off_excl);
+
+    rebert_request_info_t inf;
+    memset(&inf, 0, sizeof(inf));
+    auto finish = [&]() {
+        const int32_t cnt = (int32_t)(uint32_t)res[2 * (size_t)k];
+        memcpy(out_rows, res, (size_t)k * 8);
+        memcpy(out_scores, res + k, (size_t)k * 8);
+        *out_count = cnt;
+        memcpy(&inf.margin, res + 2 * (size_t)k + 1, 8);
+        if (info) *info = inf;
+        *in_flight = 0;
+    };
+
+    // ---- tiny catalog on one GPU: the whole request is ONE kernel, every row scored exactly
+    if (!sharded && small_route_enabled() && small_catalog(cat, n_exclude)) {
+        rc = small_recommend_launch(cat, q_host, liked_host, w_host, n_liked, excl_host, n_exclude, device_filter, k, res, st);
         if (rc != REBERT_OK) return rc;
-        rc = rebert_profile_finalize(sum64, wsum, 1, cat->ld, qn32, qn64, nullptr, stream);
+        REBERT_CUDA(cudaStreamSynchronize(st));
+        inf.kc = 0; inf.attempts = 1; inf.proven = 1; inf.used_shadow = 0;
+        finish();
+        return REBERT_OK;
+    }
+
+    // ---- staging kernel: normalised query, or the profile (with the partial-profile exchange on a row shard)
+    uint32_t seq = sharded ? exchange->seq : 0;
+    Exchange x;
+    rebert_exchange_t ex;
+    if (sharded) {
+        ex = *exchange;
+        rc = make_exchange(&ex, err_word, &x);
         if (rc != REBERT_OK) return rc;
     }
+    if (query) {
+        rc = stage_query_launch(q_host, cat->d, cat->ld, qn32, qn64, excl_host, n_exclude, excl_dev, st);
+    } else {
+        rc = stage_profile_launch(cat, liked_host, w_host, n_liked, excl_host, n_exclude, excl_dev, (double*)(dv + L.off_sum64),
+                                  (double*)(dv + L.off_wsum), qn32, qn64, sharded ? &x : nullptr, st);
+    }
+    if (rc != REBERT_OK) return rc;
+
     rebert_filter_t f;
     memset(&f, 0, sizeof(f));
     if (device_filter) f = *device_filter;
-    if (n_exclude) {
-        f.exclude_rows = (const int32_t*)(dv + L.off_excl);
-        f.n_exclude = n_exclude;
-    }
-    uint64_t* cand = (uint64_t*)(dv + L.off_cand);
-    rc = rebert_gemv_topk(cat, qn32, &f, kc, dv + L.off_ws, L.ws_bytes, cand, stream);
-    if (rc != REBERT_OK) return rc;
-    // ---- exact pass.  Its packed result (rows[k] | scores[k] | count | margin) is written by the kernel straight into
-    // the pinned block (no D2H copy operation) — or, on a row shard, into device scratch for the exchange kernel, which
-    // then writes the merged block and its error word into the pinned block.
-    unsigned char* r = h + L.pin_out;
-    unsigned char* ob = ex ? dv + L.off_out : r;
-    rc = rebert_finalize_topk(cat, qn64, cand, kc, k, (int64_t*)ob, (double*)(ob + 8 * (size_t)k), (int32_t*)(ob + 16 * (size_t)k),
-                              (double*)(ob + 16 * (size_t)k + 8), stream);
-    if (rc != REBERT_OK) return rc;
-    int32_t* err_word = (int32_t*)(r + L.out_bytes);
-    if (ex) {
-        *err_word = 0;
-        rc = rebert_exchange_merge(ex->peer_buffers, ex->world, ex->rank, k, ex->k_max, ex->seq, (const int64_t*)ob, (int64_t*)r,
-                                   err_word, stream);
+    f.exclude_rows = n_exclude ? excl_dev : nullptr;
+    f.n_exclude = n_exclude;
+    const uint32_t tag = sharded ? request_tag(query ? (const void*)query : (const void*)liked_rows,
+                                               query ? (size_t)cat->d * 4 : (size_t)n_liked * 4, exclude_rows, (size_t)n_exclude * 4,
+                                               liked_w, liked_w ? (size_t)n_liked * 4 : 0, ((uint64_t)k << 32) | (uint32_t)n_liked)
+                                 : 0u;
+
+    // ---- proof loop: each attempt is ONE launch + one synchronisation
+    const bool try_shadow = proof && proof->shadow && k <= proof->shadow_max_k && proof->shadow_eps > 0.0;
+    int cur_kc = kc;
+    bool shadow_turn = try_shadow;
+    while (true) {
+        GemvFused gf;
+        gf.exact_cat = cat;
+        gf.q64 = qn64;
+        gf.k = k;
+        gf.out_packed = res;
+        gf.tag = tag;
+        gf.xchg = nullptr;
+        if (sharded) {
+            x.seq = seq ? seq : 1u;
+            gf.xchg = &x;
+        }
+        const int use_kc = shadow_turn ? 256 : cur_kc;
+        rc = gemv_launch(shadow_turn ? proof->shadow : cat, qn32, &f, use_kc, dv + L.off_ws, L.ws_bytes, nullptr, &gf, st);
         if (rc != REBERT_OK) return rc;
+        REBERT_CUDA(cudaStreamSynchronize(st));
+        ++inf.attempts;
+        ++seq;
+        if (*err_word != 0) {
+            if (*err_word > 100) set_error("recommend_host: rank %d answered a different request on this channel (request order diverged)", *err_word - 101);
+            else set_error("recommend_host: peer %d did not deliver its result to the exchange", *err_word - 1);
+            *in_flight = 0;
+            return REBERT_ERR_CUDA;
+        }
+        double margin;
+        memcpy(&margin, res + 2 * (size_t)k + 1, 8);
+        inf.kc = use_kc;
+        inf.used_shadow = shadow_turn ? 1 : 0;
+        if (!proof) { inf.proven = 0; break; }
+        const double eps = shadow_turn ? proof->shadow_eps : proof->fast_eps;
+        inf.proven = margin > eps ? 1 : 0;
+        if (inf.proven) break;
+        if (shadow_turn) { shadow_turn = false; continue; }     // not provable on the shadow: take the plain pass
+        if (!proof->widen || cur_kc >= 256) break;
+        cur_kc = cur_kc * 4 < 256 ? cur_kc * 4 : 256;            // candidate set not provably exact: widen and redo
     }
-    REBERT_CUDA(cudaStreamSynchronize(st));
-    if (ex && *err_word != 0) {
-        set_error("recommend_host_sharded: peer %d did not deliver its result to the exchange kernel", *err_word - 1);
-        return REBERT_ERR_CUDA;
-    }
-    const int32_t cnt = *(const int32_t*)(r + 16 * (size_t)k);
-    memcpy(out_rows, r, (size_t)k * 8);
-    memcpy(out_scores, r + 8 * (size_t)k, (size_t)k * 8);
-    *out_count = cnt;
-    if (out_margin) *out_margin = *(const double*)(r + 16 * (size_t)k + 8);
+    finish();
     return REBERT_OK;
-}
-
-REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* query, const int32_t* liked_rows,
-                                     const float* liked_w, int32_t n_liked, const int32_t* exclude_rows, int32_t n_exclude,
-                                     const rebert_filter_t* device_filter, int32_t k, int32_t kc, int32_t n_liked_cap,
-                                     int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
-                                     size_t device_bytes, int64_t* out_rows, double* out_scores, int32_t* out_count,
-                                     double* out_margin, rebert_stream stream) {
-    return recommend_host_impl(cat, query, liked_rows, liked_w, n_liked, exclude_rows, n_exclude, device_filter, k, kc, n_liked_cap,
-                               n_exclude_cap, pinned, pinned_bytes, device_scratch, device_bytes, out_rows, out_scores, out_count,
-                               out_margin, stream, nullptr);
-}
-
-REBERT_API int rebert_recommend_host_sharded(const rebert_catalog_t* cat, const float* query, const int32_t* exclude_rows,
-                                             int32_t n_exclude, const rebert_filter_t* device_filter, int32_t k, int32_t kc,
-                                             int32_t n_exclude_cap, void* pinned, size_t pinned_bytes, void* device_scratch,
-                                             size_t device_bytes, const uint64_t* peer_buffers, int32_t world, int32_t rank,
-                                             int32_t k_max, uint32_t seq, int64_t* out_rows, double* out_scores,
-                                             int32_t* out_count, double* out_margin, rebert_stream stream) {
-    REBERT_REQUIRE(query && peer_buffers, "recommend_host_sharded: null argument");
-    HostExchange ex;
-    ex.peer_buffers = peer_buffers; ex.world = world; ex.rank = rank; ex.k_max = k_max; ex.seq = seq;
-    return recommend_host_impl(cat, query, nullptr, nullptr, 0, exclude_rows, n_exclude, device_filter, k, kc, 0, n_exclude_cap, pinned,
-                               pinned_bytes, device_scratch, device_bytes, out_rows, out_scores, out_count, out_margin, stream, &ex);
 }
 
 }  // extern "C"

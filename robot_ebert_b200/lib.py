@@ -78,11 +78,11 @@ def get_movies(tmdb_ids: List[str]) -> List[Movie]:
     return _State.sql.get_movies(tmdb_ids)
 
 
-def _rated_rows(user_id: str):
-    """lib.py:36-47: the user's ratings restricted to catalog movies -> (rated rows, liked rows)."""
+def _rated_rows(ratings: Sequence[Tuple[str, float]]):
+    """lib.py:43-47: the user's ratings restricted to catalog movies -> (rated rows, liked rows)."""
     cat = _State.catalog
     rated, liked = [], []
-    for tmdb_id, rating in _State.sql.user_ratings(user_id):
+    for tmdb_id, rating in ratings:
         row = cat.row_of(tmdb_id)
         if row is None:                      # lib.py:44 — drop ratings of movies without an embedding
             continue
@@ -95,9 +95,10 @@ def _rated_rows(user_id: str):
 def get_user_recs(user_id: str, k: int = 10) -> List[Recommendation]:
     """get a list of movie recommendations based on a user's collaborative filtering embedding (lib.py:32-63)"""
     cat = _State.catalog
-    if not _State.sql.user_ratings(user_id):
+    ratings = _State.sql.user_ratings(user_id)                               # lib.py:36-38 — the one ratings read
+    if not ratings:
         return []                                                            # lib.py:39-40
-    rated, liked = _rated_rows(user_id)
+    rated, liked = _rated_rows(ratings)
     # lib.py:48-55 on the GPU: mean cosine to the liked movies, rated movies masked, top-k.
     # With no liked movie this raises ValueError exactly like sklearn does in the reference (SURVEY.md §3.2).
     rows, scores = cat.recommend(liked_rows=liked, exclude_rows=rated, k=k)
@@ -120,7 +121,7 @@ def run_search(chat_messages: List[ChatMessage], user_id: Optional[str] = None, 
     query_movies = get_movies(tmdb_ids=query_match_movies)                                       # lib.py:89
 
     if user_id:
-        _, liked = _rated_rows(user_id)                                                          # lib.py:94-98
+        _, liked = _rated_rows(_State.sql.user_ratings(user_id))                                 # lib.py:94-98
         if len(liked) == 0 and not _State.strict_reference_errors:
             user_scores = query_scores                                                           # the intent of lib.py:101-102
         else:

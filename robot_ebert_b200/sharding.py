@@ -12,14 +12,18 @@ the host logic can be exercised with gloo on CPU in tests; the product backend (
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+import logging
+import threading
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _native as nat
-from .catalog import CatalogStore, RowFilter, _on_device, large_k_search, sorted_csr, sorted_unique_i32, unpack_result
+from .catalog import CatalogStore, RowFilter, large_k_search, sorted_csr, unpack_result
+
+log = logging.getLogger("robot_ebert_b200")
 
 
 class ShardPlan:
@@ -49,9 +53,13 @@ class ShardPlan:
 
 
 class CudaShardBackend:
-    """Product backend: the local shard is a CatalogStore; every step is a kernel enqueued on the current stream."""
+    """Product backend: the local shard is a CatalogStore; every step is a kernel enqueued on the current stream.
+
+    Exchange paths: "p2p" (after setup_p2p: NVLink peer memory, the whole request is ONE C call per rank, no NCCL and no
+    torch op on the request path) or "nccl" (fallback when the platform cannot map peer buffers)."""
 
     K_MAX = 240          # largest k of the single-query path
+    CHANNELS = 16        # independent request streams of the peer-mapped buffers (one per serving thread)
 
     def __init__(self, store: CatalogStore):
         self.store = store
@@ -59,20 +67,25 @@ class CudaShardBackend:
         self._merged = {}
         self._host = {}
         self.exchange = "nccl"       # becomes "p2p" once setup_p2p() has mapped the peers' buffers
-        self._seq = 0
+        self.channels = 1
+        self._seq = [0]
+        self._nccl_lock = threading.Lock()      # the NCCL fallback keeps per-process buffers: one request at a time
+        self._err = {}
 
-    def setup_p2p(self, group=None) -> bool:
-        """Map one small symmetric buffer per rank (torch symmetric memory = CUDA VMM + fabric handles) so that the
-        exchange step becomes ONE kernel of P2P stores + flags + merge.  Falls back to NCCL all-gather if the
-        platform cannot provide peer mappings.  Collective: every rank must call it."""
+    def setup_p2p(self, group=None, channels: Optional[int] = None) -> bool:
+        """Map one symmetric buffer per rank (torch symmetric memory = CUDA VMM + fabric handles) holding `channels`
+        independent exchange channels, so that the exchange steps become P2P stores + flags inside the request's kernels.
+        Falls back to NCCL (and says so in the log) if the platform cannot provide peer mappings.
+        Collective: every rank must call it."""
         lib = nat.load()
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+        channels = int(channels or self.CHANNELS)
         ok = torch.zeros(1, dtype=torch.int32, device=self.device)
         try:
             import torch.distributed._symmetric_memory as symm
-            nbytes = lib.rebert_exchange_buffer_bytes(world, self.K_MAX)
+            nbytes = lib.rebert_exchange_buffer_bytes(world, self.K_MAX, self.store.ld, channels)
             if nbytes == 0:
-                raise RuntimeError("world size not supported by the exchange kernel")
+                raise RuntimeError("world size not supported by the exchange kernels")
             buf = symm.empty(nbytes // 8, dtype=torch.int64, device=self.device)
             buf.zero_()
             hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
@@ -83,51 +96,67 @@ class CudaShardBackend:
             ok.fill_(1)
         except Exception as e:  # noqa: BLE001 - any failure of the plumbing means: keep NCCL
             self._p2p_error = repr(e)
+            log.warning("rank %d: peer-memory exchange unavailable (%s)", rank, self._p2p_error)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all or nothing, and a barrier after the zero-fill
         torch.cuda.synchronize(self.device)
         self.exchange = "p2p" if int(ok.item()) == 1 else "nccl"
+        if self.exchange == "p2p":
+            self.channels = channels
+            self._seq = [0] * channels
+        log.info("rank %d/%d: row-shard exchange path = %s%s", rank, world, self.exchange,
+                 f" ({channels} channels)" if self.exchange == "p2p" else " (all-gather + merge kernel; requests are serialised)")
         return self.exchange == "p2p"
 
-    def exchange_merge(self, local: torch.Tensor, k: int) -> torch.Tensor:
-        """P2P exchange + merge of the packed local result (int64 [2k+2]) -> packed merged result (+1 word: error flag)."""
+    def exchange_struct(self, channel: int, seq: int) -> "nat.Exchange":
+        x = nat.Exchange()
+        x.peer_buffers = C.cast(self._peer_ptrs, C.c_void_p)
+        x.world, x.rank, x.k_max, x.prof_len = self._p2p_world, self._p2p_rank, self.K_MAX, self.store.ld
+        x.channels, x.channel, x.seq = self.channels, channel, (seq & 0xFFFFFFFF) or 1
+        return x
+
+    def next_seq(self, channel: int, n: int = 1) -> int:
+        """First of n fresh sequence numbers on `channel` (the caller holds the channel's lock)."""
+        first = self._seq[channel] + 1
+        self._seq[channel] += n
+        return first
+
+    def recommend_host(self, query, liked_rows, weights, exclude_rows, k: int, kc: int, row_filter: Optional[RowFilter],
+                       channel: int = 0, shadow_max_k: int = 0, shadow_eps=None):
+        """One C call per rank for a whole request on the P2P path (rebert_recommend_host with an exchange): zero-copy
+        request, query normalisation or profile build + partial-profile exchange, local fast + exact pass and the result
+        exchange + merge inside the scoring launch, proof loop, result written into pinned memory.  Collective in effect:
+        every rank must call it with the same arguments on the same channel.  Returns (rows, scores, info)."""
+        st = self.store
+        x = self.exchange_struct(channel, self._seq[channel] + 1)
+        try:
+            rows, scores, info = st._recommend_host(query, liked_rows, weights, exclude_rows, k, kc, row_filter, shadow_max_k,
+                                                    exchange=x, shadow_eps=shadow_eps)
+        except ValueError:
+            raise                                   # argument errors are raised before any exchange: sequence numbers unchanged
+        self._seq[channel] += info["attempts"]
+        return rows, scores, info
+
+    def exchange_merge(self, local: torch.Tensor, k: int, channel: int = 0) -> torch.Tensor:
+        """P2P exchange + merge of a packed local result (int64 [2k+2]) -> packed merged result (+1 word: error flag)."""
         lib = nat.load()
-        out = self._p2p_out.get(k)
+        out = self._p2p_out.get((k, channel))
         if out is None:
-            out = self._p2p_out[k] = torch.zeros(2 * k + 3, dtype=torch.int64, device=self.device)   # last word: peer-timeout flag
-        self._seq += 1
-        nat.check(lib.rebert_exchange_merge(self._peer_ptrs, self._p2p_world, self._p2p_rank, k, self.K_MAX,
-                                            self._seq & 0xFFFFFFFF or 1, local.data_ptr(), out.data_ptr(),
-                                            out.data_ptr() + 8 * (2 * k + 2), torch.cuda.current_stream().cuda_stream))
+            out = self._p2p_out[(k, channel)] = torch.zeros(2 * k + 3, dtype=torch.int64, device=self.device)   # last word: error flag
+        x = self.exchange_struct(channel, self.next_seq(channel))
+        nat.check(lib.rebert_exchange_merge(C.byref(x), k, local.data_ptr(), out.data_ptr(), out.data_ptr() + 8 * (2 * k + 2),
+                                            torch.cuda.current_stream().cuda_stream))
         return out
 
-    def recommend_query_host(self, query, exclude_rows, k: int, kc: int, row_filter: Optional[RowFilter]):
-        """One C call for a query request on the P2P path (rebert_recommend_host_sharded): zero-copy request, local fast +
-        exact pass, fused exchange + merge, result written into pinned memory, one stream sync.  Collective in effect:
-        every rank must call it with the same arguments.  Returns (rows, scores, margin)."""
-        lib = nat.load()
-        st = self.store
-        s = st._scratch()
-        q = np.ascontiguousarray(query, dtype=np.float32)
-        if q.shape != (st.d,):
-            raise ValueError(f"query must have shape ({st.d},)")
-        ex, ne = None, 0
-        if exclude_rows is not None and len(exclude_rows):
-            ex = sorted_unique_i32(exclude_rows)
-            ne = int(ex.shape[0])
-        s.ensure_host_sharded(ne, k)
-        f = st._filter_struct(row_filter)
-        cnt, margin = C.c_int32(0), C.c_double(0.0)
-        self._seq += 1
-        with _on_device(self.device):
-            rc = lib.rebert_recommend_host_sharded(
-                C.byref(st._c), q.ctypes.data, None if ex is None else ex.ctypes.data, ne, None if f is None else C.byref(f), k, kc,
-                s.sne_cap, s.shpin.data_ptr(), s.shpin.numel(), s.shdev.data_ptr(), s.shdev.numel(), self._peer_ptrs, self._p2p_world,
-                self._p2p_rank, self.K_MAX, self._seq & 0xFFFFFFFF or 1, s.sh_rows.ctypes.data, s.sh_scores.ctypes.data,
-                C.byref(cnt), C.byref(margin), torch.cuda.current_stream().cuda_stream)
-        nat.check(rc)
-        st.last_h2d_bytes = 4 * st.d + 4 * ne            # read by the staging kernel straight from the pinned block
-        n = cnt.value
-        return s.sh_rows[:n].copy(), s.sh_scores[:n].copy(), margin.value
+    def enqueue_fused(self, k: int, kc: int, row_filter: Optional[RowFilter], channel: int = 0) -> torch.Tensor:
+        """Device-resident sharded step for an already staged query (bench `value` loop): ONE launch per rank — local fast +
+        exact pass, exchange and merge in the kernel's tail.  Returns the packed merged result (+1 word: error flag)."""
+        ptr, ne = self._excl
+        out = self._p2p_out.get((k, channel))
+        if out is None:
+            out = self._p2p_out[(k, channel)] = torch.zeros(2 * k + 3, dtype=torch.int64, device=self.device)
+        x = self.exchange_struct(channel, self.next_seq(channel))
+        self.store.enqueue_fused(k, kc, ptr, ne, row_filter, exchange=x, err_ptr=out.data_ptr() + 8 * (2 * k + 2), out_ptr=out.data_ptr())
+        return out
 
     def stage(self, query, liked_rows, weights, exclude_rows, k, kc):
         st = self.store
@@ -155,7 +184,7 @@ class CudaShardBackend:
 
     def local_topk(self, k: int, kc: int, row_filter: Optional[RowFilter]) -> torch.Tensor:
         ptr, ne = self._excl
-        return self.store.enqueue_topk(k, kc, ptr, ne, row_filter)
+        return self.store.enqueue_fused(k, kc, ptr, ne, row_filter)
 
     def merge(self, gathered: torch.Tensor, k: int) -> torch.Tensor:
         """gathered int64 [G, 2k+2] packed per-rank results -> packed merged result int64 [2k+2] (margin = min)."""
@@ -181,14 +210,22 @@ class CudaShardBackend:
         torch.cuda.current_stream().synchronize()
         words = host.numpy()
         if n == 2 * k + 3 and int(words[2 * k + 2:].view(np.int32)[0]) != 0:
-            raise RuntimeError(f"peer {int(words[2 * k + 2:].view(np.int32)[0]) - 1} did not deliver its result to the exchange kernel")
+            code = int(words[2 * k + 2:].view(np.int32)[0])
+            raise RuntimeError(f"rank {code - 101} answered a different request on this channel" if code > 100
+                               else f"peer {code - 1} did not deliver its result to the exchange kernel")
         return unpack_result(words, k)
 
 
 class ShardedCatalog:
-    """The sharding layer.  Every rank calls recommend() with the same arguments and gets the same answer."""
+    """The sharding layer.  Every rank calls recommend() with the same arguments and gets the same answer.
 
-    def __init__(self, backend, n_total: int, group=None):
+    Drop-in for CatalogStore under robot_ebert_b200.lib (row_of / id_of / recommend / build_profiles / score_subset).
+    Thread safety: requests on one `channel` are serialised by a lock and must be issued in the same order by every
+    rank (each serving thread of a rank uses its own channel, the same one as its counterparts on the other ranks);
+    requests on different channels run concurrently.  A request tag travels with every rank's result, so ranks whose
+    request order on a channel diverged get an error instead of a merged answer to two different requests."""
+
+    def __init__(self, backend, n_total: int, group=None, ids: Optional[Sequence[str]] = None):
         self.backend = backend
         self.group = group
         self.world = dist.get_world_size(group)
@@ -196,6 +233,10 @@ class ShardedCatalog:
         self.plan = ShardPlan(n_total, self.world)
         backend._world = self.world
         self._gather = {}
+        self.ids = list(ids) if ids is not None else None
+        self._row_of = None
+        self._locks = [threading.Lock() for _ in range(max(1, getattr(backend, "channels", 1)))]
+        self.q8_eps = None
 
     @classmethod
     def synthetic(cls, seed: int, n_total: int, d: int, dtype: str = "bf16", scale_rows: bool = False, device=None,
@@ -207,25 +248,99 @@ class ShardedCatalog:
         backend.setup_p2p(group)
         return cls(backend, n_total, group)
 
+    @classmethod
+    def from_host(cls, ids: Optional[Sequence[str]], matrix: np.ndarray, dtype: str = "fp32", device=None, group=None,
+                  sort_ids: bool = True) -> "ShardedCatalog":
+        """Every rank passes the SAME [N, D] host matrix (what Chroma's collection.get returns, constants.py:55) and keeps
+        only its contiguous slice of the id-sorted rows in HBM; the id table stays whole on every rank."""
+        matrix = np.asarray(matrix, dtype=np.float32)
+        if matrix.ndim != 2:
+            raise ValueError("matrix must be [N, D]")
+        n = matrix.shape[0]
+        if ids is not None:
+            if len(ids) != n:
+                raise ValueError("len(ids) != rows")
+            ids = [str(i) for i in ids]
+            if len(set(ids)) != n:
+                raise ValueError("duplicate ids")
+            if sort_ids:
+                order = sorted(range(n), key=ids.__getitem__)
+                if order != list(range(n)):
+                    matrix = matrix[np.asarray(order)]
+                    ids = [ids[i] for i in order]
+        plan = ShardPlan(n, dist.get_world_size(group))
+        row0, cnt = plan.range(dist.get_rank(group))
+        store = CatalogStore.from_host(None, matrix[row0:row0 + cnt], dtype, device=device, row_base=row0)
+        backend = CudaShardBackend(store)
+        backend.setup_p2p(group)
+        return cls(backend, n, group, ids)
+
+    # ------------------------------------------------------------------ id map (global rows) ----
+    def row_of(self, tmdb_id: str) -> Optional[int]:
+        if self._row_of is None:
+            if self.ids is None:
+                raise ValueError("catalog has no id table")
+            self._row_of = {i: r for r, i in enumerate(self.ids)}
+        return self._row_of.get(tmdb_id)
+
+    def id_of(self, row: int) -> str:
+        return self.ids[row] if self.ids is not None else str(row)
+
+    def build_profiles(self, row_ptr, col, w=None):
+        """Sharded CatalogStore.build_profiles: fp64 partial sums all-reduced before the division (identical on every rank)."""
+        return self.backend.store.build_profiles(
+            row_ptr, col, w, reduce_fn=lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group))
+
+    def score_subset(self, p64: torch.Tensor, sub_rows: np.ndarray) -> np.ndarray:
+        """fp64 scores of `sub_rows` (global ids, any shard) against prepared profiles (lib.py:105-106): each rank scores
+        the rows it owns, one all-reduce puts them together."""
+        st = self.backend.store
+        local = torch.from_numpy(st.score_subset(p64, sub_rows)).to(st.device)
+        local = torch.nan_to_num(local, nan=0.0)                   # rows of other shards come back NaN
+        dist.all_reduce(local, op=dist.ReduceOp.SUM, group=self.group)
+        return local.cpu().numpy()
+
+    def enable_prefilter(self) -> float:
+        """Build every rank's int8 prefilter shadow (CatalogStore.enable_prefilter).  The proof bound is the LARGEST bound
+        over the ranks, so that every rank takes the same proven / not-proven decision.  Collective."""
+        eps = self.backend.store.enable_prefilter()
+        t = torch.tensor([eps], dtype=torch.float64, device=self.backend.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.q8_eps = float(t.item())
+        return self.q8_eps
+
     def _gather_buf(self, k: int, like: torch.Tensor) -> torch.Tensor:
         buf = self._gather.get(k)
         if buf is None:
             buf = self._gather[k] = torch.empty((self.world, 2 * k + 2), dtype=torch.int64, device=like.device)
         return buf
 
-    def enqueue(self, k: int, kc: int, row_filter=None) -> torch.Tensor:
-        """Device-resident step for an already staged query: local top-k -> all-gather -> merge (packed result)."""
-        local = self.backend.local_topk(k, kc, row_filter)
+    def enqueue(self, k: int, kc: int, row_filter=None, channel: int = 0) -> torch.Tensor:
+        """Device-resident step for an already staged query: local top-k -> exchange -> merge (packed result)."""
         if getattr(self.backend, "exchange", "nccl") == "p2p":
-            return self.backend.exchange_merge(local, k)             # one kernel: P2P stores + flags + merge
+            return self.backend.enqueue_fused(k, kc, row_filter, channel)   # one launch: fast + exact pass + exchange + merge
+        local = self.backend.local_topk(k, kc, row_filter)
         buf = self._gather_buf(k, local)
         dist.all_gather_into_tensor(buf.view(-1), local, group=self.group)
         return self.backend.merge(buf, k)
 
     def recommend(self, *, query=None, liked_rows=None, weights=None, exclude_rows=None, k: int = 10, row_filter=None,
-                  return_info: bool = False):
+                  return_info: bool = False, prefilter: Optional[bool] = None, channel: int = 0):
         if (query is None) == (liked_rows is None):
             raise ValueError("pass exactly one of query / liked_rows")
+        if k <= 0:
+            raise ValueError("k must be positive")
+        if liked_rows is not None and len(liked_rows) == 0:
+            raise ValueError("Found array with 0 sample(s): user has no liked movies in the catalog")
+        p2p = getattr(self.backend, "exchange", "nccl") == "p2p"
+        if not 0 <= channel < len(self._locks):
+            raise ValueError(f"channel must be in [0, {len(self._locks)})")
+        lock = self._locks[channel] if p2p else getattr(self.backend, "_nccl_lock", self._locks[0])
+        with lock:
+            return self._recommend_locked(query, liked_rows, weights, exclude_rows, k, row_filter, return_info, prefilter,
+                                          channel, p2p)
+
+    def _recommend_locked(self, query, liked_rows, weights, exclude_rows, k, row_filter, return_info, prefilter, channel, p2p):
         lib = nat.load()
         kc = lib.rebert_candidates_for_k(k)
         eps = getattr(getattr(self.backend, "store", None), "fast_eps", 0.0)
@@ -235,32 +350,52 @@ class ShardedCatalog:
             if return_info:
                 return rows, scores, {"kc": 0, "margin": float("inf"), "proven_exact": True, "exact_sweep": True}
             return rows, scores
-        fast_host = query is not None and getattr(self.backend, "exchange", "nccl") == "p2p"
-        while True:
-            if fast_host:
-                # query request on the P2P path: the whole step is ONE C call per rank (no torch ops, no NCCL)
-                rows, scores, margin = self.backend.recommend_query_host(query, exclude_rows, k, kc, row_filter)
-            else:
+        if prefilter and self.q8_eps is None:
+            raise ValueError("prefilter=True needs enable_prefilter()")
+        if p2p:
+            # the whole request is ONE C call per rank (no torch ops, no NCCL): staging, profile exchange, fused scoring
+            # launch with the result exchange in its tail, proof loop
+            shadow_max_k = 0
+            if self.q8_eps is not None and prefilter is not False:
+                shadow_max_k = 240 if prefilter else CatalogStore.PREFILTER_MAX_K
+            rows, scores, info = self.backend.recommend_host(query, liked_rows, weights, exclude_rows, k, kc, row_filter, channel,
+                                                             shadow_max_k, self.q8_eps)
+            margin, proven, kc = info["margin"], info["proven_exact"], info["kc"]
+        else:
+            while True:
                 partial = self.backend.stage(query, liked_rows, weights, exclude_rows, k, kc)
                 if partial is not None:
                     dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
                     self.backend.set_profile(partial)
                 packed = self.enqueue(k, kc, row_filter)
                 rows, scores, margin = self.backend.fetch(packed, k)
-            if margin > eps or kc >= 256:
-                break
-            kc = min(256, kc * 4)
-        proven, swept = margin > eps, False
-        if not proven and len(rows) == k and hasattr(self.backend, "sweep_local"):
-            # mass ties (see CatalogStore._exact_sweep): every rank sweeps its shard against the global k-th score
-            if fast_host:
-                self.backend.stage(query, None, None, exclude_rows, k, kc)     # the sweep reads the query from torch scratch
-            res = self._exact_sweep(float(scores[k - 1]) - 2.0 * eps, k, row_filter)
-            if res is not None:
-                rows, scores = res
-                proven = swept = True
+                if margin > eps or kc >= 256:
+                    break
+                kc = min(256, kc * 4)
+            proven = margin > eps
+            info = {"kc": kc, "margin": margin, "proven_exact": proven, "exact_sweep": False}
+        if not proven:
+            # Fail closed (see CatalogStore._close_proof).  The margin is the same on every rank, so all ranks take this
+            # branch together and the collectives below stay aligned.
+            res = None
+            if hasattr(self.backend, "sweep_local"):
+                partial = self.backend.stage(query, liked_rows, weights, exclude_rows, k, kc)    # the sweeps read torch scratch
+                if partial is not None:
+                    dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
+                    self.backend.set_profile(partial)
+                if len(rows) == k:
+                    res = self._exact_sweep(float(scores[k - 1]) - 2.0 * eps, k, row_filter)
+                if res is None:
+                    try:
+                        res = self._recommend_large_k(query, liked_rows, weights, exclude_rows, k, row_filter, eps)
+                    except RuntimeError:
+                        res = None
+            if res is None:
+                raise RuntimeError(f"top-{k}: the sharded result cannot be proven exact (margin {margin:.3e} <= {eps:.3e})")
+            rows, scores = res
+            info = dict(info, proven_exact=True, exact_sweep=True)
         if return_info:
-            return rows, scores, {"kc": kc, "margin": margin, "proven_exact": proven, "exact_sweep": swept}
+            return rows, scores, info
         return rows, scores
 
     def _recommend_large_k(self, query, liked_rows, weights, exclude_rows, k, row_filter, eps):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_binding_matches_header():
     assert sorted(nat.exported_symbols()) == _header_functions()
     lib = nat.load()
-    assert lib.rebert_abi_version() == 1
+    assert lib.rebert_abi_version() == nat.ABI_VERSION
 
 
 def test_layout_and_candidates_host_logic():
@@ -91,8 +91,10 @@ def test_c_abi_argument_validation_without_a_gpu():
     assert lib.rebert_finalize_topk(C.byref(cat), None, None, 32, 10, None, None, None, None, None) == nat.ERR_INVALID
     assert lib.rebert_catalog_layout(10, 32, 7, None, None) == nat.ERR_INVALID and b"dtype" in lib.rebert_last_error()
     assert lib.rebert_merge_topk(None, None, None, 1, 1, 1, 2, 1, 10, None, None, None, None) == nat.ERR_INVALID
-    assert lib.rebert_exchange_buffer_bytes(0, 10) == 0 and lib.rebert_exchange_buffer_bytes(17, 10) == 0
-    assert lib.rebert_exchange_buffer_bytes(8, 240) == (2 * 8 * 482 + 16) * 8
+    assert lib.rebert_exchange_buffer_bytes(0, 10, 0, 1) == 0 and lib.rebert_exchange_buffer_bytes(17, 10, 0, 1) == 0
+    # per channel: results [2][world][2 k_max + 2] + flags [2][world] + profiles [2][world][prof_len + 1] + flags [2][world]
+    assert lib.rebert_exchange_buffer_bytes(8, 240, 0, 1) == (2 * 8 * 482 + 16 + 2 * 8 * 1 + 16) * 8
+    assert lib.rebert_exchange_buffer_bytes(8, 240, 1536, 16) == 16 * (2 * 8 * 482 + 16 + 2 * 8 * 1537 + 16) * 8
     plan = nat.GemmPlan()
     assert lib.rebert_gemm_plan(1000, 16, 10, C.byref(plan)) == nat.ERR_UNSUPPORTED and b"too small" in lib.rebert_last_error()
     assert lib.rebert_gemm_plan(1_000_000, 4096, 100, C.byref(plan)) == nat.OK
@@ -110,9 +112,14 @@ def test_c_abi_argument_validation_without_a_gpu():
     assert lib.rebert_catalog_quantize_i8(C.byref(cat8), 128, 32, 128, 128, None) == nat.ERR_INVALID and b"source dtype" in lib.rebert_last_error()
     assert lib.rebert_gemv_topk(C.byref(cat8), 128, C.byref(f), 32, 128, 1 << 20, 128, None) == nat.ERR_INVALID
     assert b"kc = 256" in lib.rebert_last_error()
-    # sharded host entry: same validation as the single-GPU entry, before any CUDA call
-    assert lib.rebert_recommend_host_sharded(C.byref(cat), None, None, 0, None, 10, 32, 0, None, 0, None, 0, None, 2, 0, 240, 1,
-                                             None, None, None, None, None) == nat.ERR_INVALID
+    # host entry (single GPU and row shard alike): argument validation before any CUDA call
+    x = nat.Exchange()
+    x.world, x.rank, x.k_max, x.channels, x.seq = 2, 0, 240, 1, 1
+    assert lib.rebert_recommend_host(C.byref(cat), None, None, None, 0, None, 0, None, 10, 32, 0, 0, None, 0, None, 0, None, C.byref(x),
+                                     None, None, None, None, None) == nat.ERR_INVALID
+    assert lib.rebert_recommend_device(C.byref(cat), None, None, None, None, 10, 32, None, 0, None, 0, None, None, None) == nat.ERR_INVALID
+    assert lib.rebert_exchange_merge(C.byref(x), 10, 128, 128, 128, None) == nat.ERR_INVALID and b"null" in lib.rebert_last_error()
+    assert lib.rebert_workspace_reset(None, 0, None) == nat.ERR_INVALID
     with pytest.raises(ValueError):
         nat.check(nat.ERR_INVALID)
     with pytest.raises(nat.NativeError):
@@ -135,7 +142,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
         nat.load()
     monkeypatch.undo()
-    assert nat.load().rebert_abi_version() == 1
+    assert nat.load().rebert_abi_version() == nat.ABI_VERSION
 
 
 def test_header_is_plain_c_and_library_links_from_c(tmp_path):

@@ -315,19 +315,28 @@ for n, d, dtype, k in [(70_001, 1536, "bf16", 10), (70_001, 1536, "bf16", 100), 
     ptr, ne = store.stage_inputs(q, None, None, excl, k, kc)
     s = store._scratch()
     f = nat.Filter(); f.exclude_rows, f.n_exclude = ptr, ne
-    keys = {}
+    keys, fused = {}, {}
     for hint in ("0", "1"):
         for dyn in ("0", "12", "50", "100"):
-            for stages in ("2", "4"):
-                os.environ.update(REBERT_GEMV_CTA_HINT=hint, REBERT_GEMV_DYN_PCT=dyn, REBERT_GEMV_STAGES=stages)
+            for stages, prune, early in (("2", "1", "1"), ("4", "1", "1"), ("4", "0", "1"), ("4", "1", "0"), ("3", "0", "0")):
+                os.environ.update(REBERT_GEMV_CTA_HINT=hint, REBERT_GEMV_DYN_PCT=dyn, REBERT_GEMV_STAGES=stages,
+                                  REBERT_GEMV_MERGE_PRUNE=prune, REBERT_GEMV_EARLY_TMA=early)
                 for _ in range(3):                              # repeated launches: the counters must be left at zero
                     nat.check(lib.rebert_gemv_topk(C.byref(store._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
                                                    s.ws.numel(), s.cand.data_ptr(), torch.cuda.current_stream().cuda_stream))
-                keys[(hint, dyn, stages)] = s.cand.cpu().numpy().copy()
+                keys[(hint, dyn, stages, prune, early)] = s.cand.cpu().numpy().copy()
+                for _ in range(2):                              # the one-launch request path (exact pass in the kernel's tail)
+                    store.enqueue_fused(k, kc, ptr, ne)
+                fused[(hint, dyn, stages, prune, early)] = s.d_out.cpu().numpy().copy()
     first = next(iter(keys.values()))
+    ffirst = next(iter(fused.values()))
+    store.enqueue_topk(k, kc, ptr, ne)                           # two-kernel form: gemv_topk -> finalize_topk
+    two = s.d_out.cpu().numpy().copy()
     out[f"{n}x{d}:{dtype}:k{k}"] = {"identical": all(np.array_equal(first, v) for v in keys.values()),
+                                   "fused_identical": all(np.array_equal(ffirst, v) for v in fused.values()),
+                                   "fused_equals_two_kernel": bool(np.array_equal(ffirst, two)),
                                    "filled": int((first != 0).sum()), "kc": kc,
-                                   "digest": __import__("hashlib").sha1(first.tobytes()).hexdigest()}
+                                   "digest": __import__("hashlib").sha1(first.tobytes() + ffirst.tobytes()).hexdigest()}
 print(json.dumps(out))
 """
 
@@ -337,21 +346,23 @@ _KNOB_DIGESTS = {}
 
 @pytest.mark.parametrize("pdl", ["1", "0"])
 def test_scheduling_knobs_change_speed_never_results(pdl):
-    """Threshold hints, the static / dynamically claimed tile schedule, the pipeline depth and programmatic dependent
-    launch are speed knobs: the candidate keys must be bit-identical under every combination (own process: the
-    library reads its knobs at the first launch)."""
+    """Threshold hints, the static / dynamically claimed tile schedule, the pipeline depth, hint pruning in the CTA merge,
+    early TMA issue and programmatic dependent launch are speed knobs: the candidate keys — and the packed result of the
+    one-launch request path, which must also equal the two-kernel form bit for bit — are identical under every combination
+    (own process: the library reads its knobs at the first launch)."""
     import json
     import os
     import subprocess
     import sys
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, REBERT_PDL=pdl)
-    r = subprocess.run([sys.executable, "-c", _KNOB_SCRIPT, repo], capture_output=True, text=True, timeout=300, env=env)
+    r = subprocess.run([sys.executable, "-c", _KNOB_SCRIPT, repo], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert len(res) == 4
     for case, v in res.items():
         assert v["identical"] and v["filled"] == v["kc"], (case, v)
+        assert v["fused_identical"] and v["fused_equals_two_kernel"], (case, v)
         assert _KNOB_DIGESTS.setdefault(case, v["digest"]) == v["digest"], case      # ... and with PDL on or off
 
 
@@ -397,3 +408,90 @@ def test_int8_prefilter_falls_back_when_its_bound_cannot_prove_the_result():
     want_rows, want_scores = ora.query_rows(_stored_f64(store), q.astype(np.float64), None, k)
     np.testing.assert_array_equal(rows, want_rows)
     np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL)
+
+
+def test_one_workspace_serves_every_candidate_count():
+    """A thread's host scratch is zero-filled ONCE and then reused for every kc (k = 10 -> 32 candidates, k = 100 -> 128,
+    forced 256): the kernel's control words must not move with kc.  Regression test for stale candidates after a kc change:
+    same query, DIFFERENT exclusions per call, every answer checked against the independent dense kernel."""
+    n, d = 1_000_000, 1536
+    store = CatalogStore.synthetic(0, n, d, "bf16")
+    q = synth.query_f32(1, d)
+    qn = (q.astype(np.float64) / np.linalg.norm(q.astype(np.float64)))
+    q32 = torch.zeros((1, store.ld), dtype=torch.float32, device=store.device)
+    q32[0, :d] = torch.from_numpy(qn.astype(np.float32)).to(store.device)
+    dense = store.scores_dense(q32)[0]
+
+    def expect(excl, k):
+        sc = dense.clone()
+        sc[torch.from_numpy(excl).to(store.device)] = -float("inf")
+        cand = torch.topk(sc, k + 8).indices.cpu().numpy()
+        exact = np.array([float(row @ qn / np.linalg.norm(row)) for row in
+                          (synth.quantise(synth.catalog_rows_f32(0, int(r), 1, d), "bf16")[0] for r in cand)])
+        order = np.lexsort((cand, -exact))[:k]
+        return cand[order], exact[order]
+
+    first_rows, _ = store.recommend(query=q, k=10)
+    for i, (k, forced_kc) in enumerate([(10, None), (100, None), (10, None), (10, 256), (10, None), (50, None), (10, None)]):
+        excl = np.unique(np.concatenate([first_rows[:i % 4], np.random.default_rng(i).choice(n, size=133, replace=False)]))
+        if forced_kc:
+            rows, scores, info = store._recommend_host(q, None, None, excl, k, forced_kc, None)
+        else:
+            rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True)
+        want_rows, want_scores = expect(excl, k)
+        np.testing.assert_array_equal(rows, want_rows)
+        np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL)
+        assert info["proven_exact"] and not set(rows.tolist()) & set(excl.tolist())
+        assert info["attempts"] == 1 and info["kc"] == (forced_kc or (32 if k <= 16 else 128)), info     # never a silent widening
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("n,d", [(2269, 32), (2264, 50), (700, 150), (8000, 16), (85, 1536), (3, 32), (5000, 1)])
+def test_tiny_catalog_kernel_equals_the_general_path_and_the_oracle(dtype, n, d, monkeypatch):
+    """Catalogs that fit one CTA (the reference's production 2269 x 32) are served by ONE kernel that scores every row in
+    fp64.  Its answers must equal the oracle's and, bit for bit, the general path's (REBERT_SMALL=0)."""
+    import os
+    store = CatalogStore.synthetic(0, n, d, dtype, scale_rows=True)
+    m = _stored_f64(store)
+    users = synth.user_ratings(2, n, 4)
+    q = synth.query_f32(1, d)
+    excl = np.arange(0, n, 7)
+    monkeypatch.setenv("REBERT_GEMV_TUNE", "1")                  # knobs are re-read on every call
+    got = {}
+    for small in ("1", "0"):
+        monkeypatch.setenv("REBERT_SMALL", small)
+        res = []
+        for k in (1, 10, 50, 240):
+            with np.errstate(all="ignore"):
+                rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True)
+            assert info["proven_exact"] and (info["kc"] == 0) == (small == "1"), info
+            want_rows, want_scores = ora.query_rows(m, q.astype(np.float64), excl, k)
+            np.testing.assert_array_equal(rows, want_rows)
+            np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=1e-300)
+            res.append((rows, scores))
+        for rated, rts in users:
+            liked = rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1]
+            with np.errstate(all="ignore"):
+                rows, scores = store.recommend(liked_rows=liked, exclude_rows=rated, k=10)
+            want_rows, want_scores = ora.recommend_rows(m, liked, rated, 10)
+            np.testing.assert_array_equal(rows, want_rows)
+            np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=1e-300)
+            res.append((rows, scores))
+        got[small] = res
+    if d > 1:                                                    # d = 1: mass ties take the sweep route on the general path
+        for (r1, s1), (r0, s0) in zip(got["1"], got["0"]):
+            np.testing.assert_array_equal(r1, r0)
+            np.testing.assert_array_equal(s1, s0)                # same exact-score function, same bits
+
+
+def test_unprovable_result_raises_instead_of_returning(monkeypatch):
+    """Fail closed: when neither a candidate list nor the exhaustive routes can prove the ids, recommend() raises."""
+    n = 3000
+    m = synth.catalog_rows_f32(0, 0, n, 1, scale_rows=True)      # d = 1: every cosine is +-1, thousands of exact ties
+    store = CatalogStore.from_host(None, m, "fp32")
+    monkeypatch.setenv("REBERT_GEMV_TUNE", "1")
+    monkeypatch.setenv("REBERT_SMALL", "0")
+    monkeypatch.setattr(CatalogStore, "_exact_sweep", lambda self, *a, **k: None)
+    monkeypatch.setattr(CatalogStore, "_recommend_large_k", lambda self, *a, **k: (_ for _ in ()).throw(RuntimeError("sweep overflow")))
+    with pytest.raises(RuntimeError, match="cannot be proven exact"):
+        store.recommend(query=np.ones(1, dtype=np.float32), k=10)
