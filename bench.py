@@ -6,18 +6,25 @@
 Workload (BASELINE.json `metric`): single-query cosine top-10 with a 133-row seen-movie exclusion over a
 10M x 1536 bf16 synthetic catalog.  One step = one query through the whole hot path.
   N = 1 : the whole catalog on one B200 (30.7 GB).
-  N > 1 : the same 10M catalog row-sharded over N ranks (strong scaling), local top-k + NCCL all-gather + merge.
-`value`  : queries/s with the query already resident in HBM (kernels only).
-`e2e`    : queries/s through CatalogStore.recommend / ShardedCatalog.recommend with HOST buffers in and out
-           (pinned H2D of the request, D2H of the result, stream sync) inside the timed region.
-`batched` / `prefilter_int8` are secondary measurements printed beside the headline (BASELINE configs 3/4 on the tcgen05
-path; the same request with the opt-in int8 prefilter shadow, same ids and scores) — never instead of it.
+  N > 1 : the same 10M catalog row-sharded over N ranks (strong scaling); local fast + exact pass, NVLink exchange + merge
+          inside the same kernel launch.
+`value`  : queries/s with the query already resident in HBM (ONE kernel launch per query).
+`e2e`    : queries/s through CatalogStore.recommend / ShardedCatalog.recommend with HOST buffers in and out (the request is
+           read from pinned memory by the first kernel, the result written there by the last, stream sync) inside the timed region.
+`result_digest` : sha1 over the k returned row ids and fp64 score bits of the fixed workload (catalog seed 0, query seed 1,
+           exclusion seed 1).  It must be the SAME at every N — one global order, lib.py:55,63 — and is asserted against
+           tests/golden/bench_digests.json; an independent dense-score kernel + host fp64 re-score checks it in every run.
+`configs`: every BASELINE.json config measured in this run (C1 CPU-sized catalog with the reference's CPU path beside it,
+           C2 1M fp32 / bf16, C3 4096 x 1M batched top-100, C4 = the headline + the batched 10M leg, C5 CSR profiles +
+           genre/year-filtered top-50 at N > 1), plus a profile request (85 liked + 133 rated rows, the reference's real
+           route, lib.py:43-55) and the int8-prefilter variant of the headline.  Secondary: never instead of the headline.
 `--impl reference` times the reference's own CPU path (oracle/, pandas + scikit-learn, float64, all host threads) on
 a bounded row sample of the same workload and scales to the full catalog.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -33,10 +40,25 @@ sys.path.insert(0, REPO)
 
 N_ROWS, DIM, DTYPE, K, N_EXCL = 10_000_000, 1536, "bf16", 10, 133
 METRIC = "queries/s top-k cosine retrieval (10M x 1536 bf16)"
+DIGESTS = os.path.join(REPO, "tests", "golden", "bench_digests.json")
 
 
 def workload_name(rows):
     return f"single-query cosine top-{K} + {N_EXCL}-row exclusion over {rows} x {DIM} {DTYPE} synthetic catalog"
+
+
+def digest(rows, scores=None):
+    h = hashlib.sha1(np.ascontiguousarray(rows, dtype=np.int64).tobytes())
+    if scores is not None:
+        h.update(np.ascontiguousarray(scores, dtype=np.float64).tobytes())
+    return h.hexdigest()[:16]
+
+
+def expected_digest(key):
+    try:
+        return json.load(open(DIGESTS)).get(key)
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -93,28 +115,40 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measured_peak():
+def measured_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    out = {"hbm": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "bf16": 1590.0, "bf16_sustained": None}
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            mp = json.load(open(path))
+            out.update(hbm=float(mp["hbm_gbs"]), hbm_src="measured (MEASURED_PEAKS.json hbm_gbs)", bf16=float(mp["bf16_tflops"]),
+                       bf16_sustained=float(mp.get("bf16_tflops_sustained") or 0) or None)
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return out
 
 
 def ncu_traffic(key):
+    """dram bytes of one launch from the committed ncu capture (profiles/roofline_traffic.json) — NOT measured in this run."""
     path = os.path.join(REPO, "profiles", "roofline_traffic.json")
-    if os.path.exists(path):
-        try:
-            return json.load(open(path)).get(key)
-        except Exception:
-            return None
-    return None
+    try:
+        return json.load(open(path)).get(key)
+    except Exception:
+        return None
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_leg(rows_full: int, steps: int, warmup: int, sample_rows: int, budget_s: float = 90.0):
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle/)
+def cpu_reference_leg(rows_full: int, steps: int, warmup: int, sample_rows: int, budget_s: float = 60.0):
     """The reference's own CPU path (restated lib.py:51-55, L=1) on a bounded row sample; returns (q/s scaled to
     rows_full, description, seconds per sample query, cores).  The sample is sized from a short calibration so that
     the whole (warmup + steps) run stays near `budget_s` seconds whatever K the caller asks for."""
@@ -154,31 +188,139 @@ def cpu_reference_leg(rows_full: int, steps: int, warmup: int, sample_rows: int,
     return qps, desc, t, os.cpu_count()
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    rows = args.rows or N_ROWS
-    steps, warmup = max(1, args.steps), max(1, args.warmup)
-    sample = args.cpu_sample_rows
-    qps, desc, t, cores = cpu_reference_leg(rows, steps, warmup, sample)
-    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": 1e3 / qps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(rows), "rows": rows, "dim": DIM, "k": K},
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": desc},
-            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line))
+def config_c1(dev):
+    """BASELINE config 1, MEASURED (not scaled): 10k x 1536 fp32 catalog, (i) the reference's user-recs request
+    (lib.py:42-55, ~85 liked of ~133 rated) and (ii) a single query, on the host cores with pandas + sklearn in float64,
+    and the GPU path end to end on the very same inputs with the parity assertion."""
+    import pandas as pd
+    from oracle import reference_scoring as ora
+    from robot_ebert_b200 import CatalogStore, synth
+    n, d, k = 10_000, 1536, 10
+    m32 = synth.catalog_rows_f32(0, 0, n, d)
+    ids = synth.row_ids(n)
+    emb = ora.catalog_frame(ids, m32.astype(np.float64))
+    rated, rts = None, None
+    for cand_rated, cand_rts in synth.user_ratings(2, n, 64):                      # the synthetic user closest to 85 liked / 133 rated
+        if rated is None or abs(int((cand_rts >= 3.5).sum()) - 85) + abs(len(cand_rated) - 133) < abs(int((rts >= 3.5).sum()) - 85) + abs(len(rated) - 133):
+            rated, rts = cand_rated, cand_rts
+    liked = rated[rts >= 3.5]
+    ratings = pd.DataFrame({"tmdb_id": [ids[r] for r in rated], "rating": rts})
+    q = synth.query_f32(1, d)
+    excl_ids = [ids[r] for r in rated]
+
+    def best_median(fn, runs=5):
+        fn()
+        ts = []
+        for _ in range(runs):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts) * 1e3, statistics.median(ts) * 1e3
+
+    cpu_user = best_median(lambda: ora.user_recs_ranked(emb, ratings, k))
+    cpu_query = best_median(lambda: ora.single_query(emb, q.astype(np.float64), excl_ids, k))
+    want_user = ora.user_recs_ranked(emb, ratings, k)
+    want_query = ora.single_query(emb, q.astype(np.float64), excl_ids, k)
+
+    store = CatalogStore.from_host(ids, m32, "fp32", device=dev)
+    got_u = store.recommend(liked_rows=liked, exclude_rows=rated, k=k)
+    got_q = store.recommend(query=q, exclude_rows=rated, k=k)
+    for (rows, scores), want in ((got_u, want_user), (got_q, want_query)):
+        assert [ids[r] for r in rows] == [w[0] for w in want], "C1: ids differ from the reference arithmetic"
+        assert np.allclose(scores, [w[1] for w in want], rtol=1e-9, atol=0), "C1: scores differ from the reference arithmetic"
+    gpu_user = best_median(lambda: store.recommend(liked_rows=liked, exclude_rows=rated, k=k), 200)
+    gpu_query = best_median(lambda: store.recommend(query=q, exclude_rows=rated, k=k), 200)
+    threads = None
+    try:
+        from threadpoolctl import threadpool_info
+        threads = [{"api": t.get("internal_api"), "threads": t.get("num_threads")} for t in threadpool_info()]
+    except Exception:
+        pass
+    return {"workload": f"{n} x {d} fp32 values (float64 frame on the CPU), k={k}, user with {len(liked)} liked of {len(rated)} rated movies",
+            "cpu": {"impl": "oracle/reference_scoring.py = lib.py:42-55 (pandas + sklearn cosine_similarity), float64, measured at this size (not scaled)",
+                    "user_recs_ms_best_median": cpu_user, "single_query_ms_best_median": cpu_query, "cores": os.cpu_count(),
+                    "cpu_model": cpu_model(), "blas": threads},
+            "gpu_e2e": {"impl": "CatalogStore.recommend, host buffers in and out", "user_recs_ms_best_median": gpu_user,
+                        "single_query_ms_best_median": gpu_query},
+            "speedup_user_recs": cpu_user[1] / gpu_user[1], "speedup_single_query": cpu_query[1] / gpu_query[1],
+            "parity": "ids identical, scores within 1e-9 of the reference arithmetic (asserted in this run)"}
 
 
-def batched_leg(store, sharded, world, rows_total, dev, steps=3, warmup=2):
-    """Secondary measurement (BASELINE configs 3/4): 4096 users x catalog, top-100, on the tcgen05 path; sharded when N>1."""
+# ------------------------------------------------------------------------------------------------ GPU helpers
+def independent_topk(store, dist_mod, world, q, excl, k, dtype, seed=0):
+    """The answer by a route that shares nothing with the fused path: the plain dense-score kernel over every shard,
+    torch.topk, all-gather of the shard winners, fp64 re-score of the union on the HOST from regenerated rows, one global
+    (score desc, row asc) order (lib.py:55,63)."""
+    import torch
+    from robot_ebert_b200 import synth
+    d = store.d
+    qn = q.astype(np.float64) / np.linalg.norm(q.astype(np.float64))
+    q32 = torch.zeros((1, store.ld), dtype=torch.float32, device=store.device)
+    q32[0, :d] = torch.from_numpy(qn.astype(np.float32)).to(store.device)
+    dense = store.scores_dense(q32)[0]
+    loc = excl[(excl >= store.row_base) & (excl < store.row_base + store.n)] - store.row_base
+    if len(loc):
+        dense[torch.from_numpy(loc).to(store.device)] = -float("inf")
+    top = torch.topk(dense, min(k + 8, store.n))
+    cand = top.indices + store.row_base
+    if world > 1:
+        allc = torch.empty(world * cand.numel(), dtype=cand.dtype, device=store.device)
+        dist_mod.all_gather_into_tensor(allc, cand.contiguous())
+        cand = allc
+    cand = np.unique(cand.cpu().numpy())
+    exact = np.empty(len(cand))
+    for i, r in enumerate(cand):
+        row = synth.quantise(synth.catalog_rows_f32(seed, int(r), 1, d), dtype)[0]
+        exact[i] = float(row @ qn / np.linalg.norm(row))
+    order = np.lexsort((cand, -exact))[:k]
+    return cand[order], exact[order]
+
+
+def time_device(fn, steps, warmup, barrier, world, dist_mod, dev):
+    """CUDA-event time of `steps` calls (ms per step, max over ranks), barrier + synchronize on both sides."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        fn()
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def time_wall(fn, steps, warmup, barrier, world, dist_mod, dev):
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    s = (time.perf_counter() - w0) / steps
+    if world > 1:
+        t = torch.tensor([s], dtype=torch.float64, device=dev)
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+        s = float(t.item())
+    return s
+
+
+def batched_leg(store, sharded, world, rows_total, dev, barrier, B=4096, KB=100, steps=3, warmup=2):
+    """BASELINE configs 3/4: B users x catalog, top-KB, on the tcgen05 path; sharded when N>1.  One step = the whole batch
+    INCLUDING the re-run of every query the batched pass could not prove (sync + single-query route inside the timed region)."""
     import ctypes as C
     import torch
     import torch.distributed as dist
     from robot_ebert_b200 import synth
     from robot_ebert_b200 import _native as nat
-    B, KB = 4096, 100
     lib = nat.load()
     q = synth.catalog_rows_f32(11, 0, B, DIM)
     qn32, qn64, qbf = store.prepare_queries(q)
@@ -189,102 +331,85 @@ def batched_leg(store, sharded, world, rows_total, dev, steps=3, warmup=2):
         c = np.unique(rng.integers(0, rows_total, size=N_EXCL))
         ec.append(c)
         ep[u + 1] = ep[u] + len(c)
-    ec = np.concatenate(ec)
+    ec = np.concatenate(ec).astype(np.int32)
+    reruns = [0]
     if sharded is not None:
         ctx = sharded.batch_context(qbf, qn64, KB, ep, ec)
-        status_of = lambda: ctx["gathered"][:, 2 * B * KB + ctx["hb"]:].contiguous().view(torch.int32)[:, :B].max(dim=0).values
-        step = lambda: sharded.batch_step(ctx)
         plan = ctx["plan"]
+
+        def step():
+            sharded.batch_step(ctx)
+            rows, scores, counts, status = sharded.batch_collect(ctx, q, ep, ec)
+            reruns[0] = int((status != 0).sum())
+            return rows, scores
     else:
         plan = store.gemm_plan(B, KB)
-        ept, ect = torch.from_numpy(ep).to(dev), torch.from_numpy(ec.astype(np.int32)).to(dev)
+        ept, ect = torch.from_numpy(ep).to(dev), torch.from_numpy(ec).to(dev)
         ws = torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan)), dtype=torch.uint8, device=dev)
         o_rows = torch.empty((B, KB), dtype=torch.int64, device=dev)
         o_scores = torch.empty((B, KB), dtype=torch.float64, device=dev)
         o_count = torch.empty(B, dtype=torch.int32, device=dev)
         o_status = torch.empty(B, dtype=torch.int32, device=dev)
-        step = lambda: store.enqueue_batch(plan, qbf, qn64, ept, ect, ws, o_rows, o_scores, o_count, o_status)
-        status_of = lambda: o_status
-    for _ in range(warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(steps):
-        step()
-    t1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / steps
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        scratch = store._scratch()
+
+        def step():
+            store.enqueue_batch(plan, qbf, qn64, ept, ect, ws, o_rows, o_scores, o_count, o_status)
+            status = o_status.cpu().numpy()                                  # the sync a caller needs to know what to re-run
+            redo = np.nonzero(status)[0]
+            reruns[0] = len(redo)
+            fix = {}
+            for u in redo:
+                scratch.qn32.copy_(qn32[u])
+                scratch.qn64.copy_(qn64[u])
+                fix[int(u)] = store.topk_prepared(KB, ect.data_ptr() + 4 * int(ep[u]), int(ep[u + 1] - ep[u]))
+            return fix
+    ms = time_device(step, steps, warmup, barrier, world, dist, dev)
+    # digest of the whole [B, k] answer (re-runs patched in), identical at every N
+    if sharded is not None:
+        rows, scores = step()
+    else:
+        fix = step()
+        rows, scores = o_rows.cpu().numpy(), o_scores.cpu().numpy()
+        for u, (r, sc) in fix.items():
+            rows[u, :len(r)], scores[u, :len(r)] = r, sc
+    pk = measured_peaks()
     flops = 2.0 * B * rows_total * DIM
-    peak, sustained = 1590.0, None
-    try:
-        mp = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-        peak = float(mp["bf16_tflops"])
-        sustained = float(mp["bf16_tflops_sustained"])            # cuBLAS back to back for seconds: the power-capped regime
-    except Exception:
-        pass
+    tf = flops / (ms * 1e-3) / 1e12
     return {"workload": f"{B} users x {rows_total} x {DIM} bf16, top-{KB}, {N_EXCL}-row exclusions per user",
-            "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "tflops": flops / (ms * 1e-3) / 1e12,
-            "frac_of_measured_bf16_peak": flops / (ms * 1e-3) / 1e12 / (peak * world),
-            "frac_of_sustained_bf16_peak": (flops / (ms * 1e-3) / 1e12 / (sustained * world)) if sustained else None,
+            "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "tflops": tf,
+            "frac_of_measured_bf16_peak": tf / (pk["bf16"] * world),
+            "frac_of_sustained_bf16_peak": (tf / (pk["bf16_sustained"] * world)) if pk["bf16_sustained"] else None,
             "peak_note": "burst = cuBLAS best of 10; sustained = cuBLAS back to back for seconds (the regime a ~100 ms batch runs in)",
             "bound": "tensor",
-            "includes": "threshold sample + fused GEMM filter + per-query select + fp64 exact pass" + (" + all-gather + merge" if world > 1 else ""),
-            "queries_rerun_on_single_query_path": int((status_of() != 0).sum().item()),
+            "includes": "threshold sample + fused GEMM filter + per-query select + fp64 exact pass + status read-back + re-run of unproven queries"
+                        + (" + all-gather + merge" if world > 1 else ""),
+            "queries_rerun_on_single_query_path": reruns[0], "reruns_inside_timed_region": True,
+            "result_digest": digest(rows, scores),
             "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
 
 
-def prefilter_leg(store, q, excl, rows_total, steps, warmup, want_rows, want_scores):
-    """Secondary measurement: the same request with the opt-in int8 prefilter shadow (fast pass streams 1 byte per
-    element and keeps 256 candidates, exact pass re-scores them from the bf16 catalog).  Same ids and scores, proven
-    per request; reported beside the headline, never instead of it."""
-    import time as _t
-    import torch
-    eps = store.enable_prefilter()
-    got_rows, got_scores, info = store.recommend(query=q, exclude_rows=excl, k=K, return_info=True)
-    same = bool(np.array_equal(got_rows, want_rows) and np.array_equal(got_scores, want_scores))
-    excl_ptr, ne = store.stage_inputs(q, None, None, excl, K, 256)
-    torch.cuda.synchronize()
-    for _ in range(warmup):
-        store.enqueue_topk(K, 256, excl_ptr, ne, None, prefilter=True)
-    torch.cuda.synchronize()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(steps):
-        store.enqueue_topk(K, 256, excl_ptr, ne, None, prefilter=True)
-    t1.record()
-    torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / steps
-    for _ in range(warmup):
-        store.recommend(query=q, exclude_rows=excl, k=K)
-    w0 = _t.perf_counter()
-    for _ in range(steps):
-        store.recommend(query=q, exclude_rows=excl, k=K)
-    e2e_s = (_t.perf_counter() - w0) / steps
-    peak, _ = measured_peak()
-    shadow_bytes = store.n * store._c8.ld
-    return {"workload": f"same request, fast pass over an int8 shadow of the catalog ({shadow_bytes / 1e9:.2f} GB), 256 candidates, "
-                        f"exact fp64 pass over the bf16 rows", "value": 1e3 / ms, "unit": "queries/s", "ms_per_step": ms,
-            "shadow_gbs": shadow_bytes / (ms * 1e-3) / 1e9, "frac_of_measured_hbm_peak": shadow_bytes / (ms * 1e-3) / 1e9 / peak,
-            "e2e": {"value": 1.0 / e2e_s, "unit": "queries/s", "ms_per_step": 1e3 * e2e_s},
-            "error_bound": eps, "margin": info.get("margin"), "proven_on_shadow_candidates": bool(info.get("prefilter")),
-            "same_ids_and_scores_as_plain_path": same, "rows": rows_total}
-
-
 # ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = args.rows or N_ROWS
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    qps, desc, t, cores = cpu_reference_leg(rows, steps, warmup, args.cpu_sample_rows, budget_s=90.0)
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 / qps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(rows), "rows": rows, "dim": DIM, "k": K},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "cpu_model": cpu_model(), "kind": "port", "sample": desc},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from robot_ebert_b200 import CatalogStore, synth
+    from robot_ebert_b200 import CatalogStore, RowFilter, synth
     from robot_ebert_b200 import _native as nat
     from robot_ebert_b200.sharding import ShardedCatalog
 
@@ -301,6 +426,7 @@ def run_b200(args):
     steps, warmup = args.steps, max(3, args.warmup)
     lib = nat.load()
     kc = lib.rebert_candidates_for_k(K)
+    pk = measured_peaks()
 
     if world > 1:
         sharded = ShardedCatalog.synthetic(0, rows, DIM, DTYPE, device=dev)
@@ -308,6 +434,7 @@ def run_b200(args):
     else:
         sharded = None
         store = CatalogStore.synthetic(0, rows, DIM, DTYPE, device=dev)
+    api = sharded if sharded is not None else store
     q = synth.query_f32(1, DIM)
     excl = np.random.default_rng(1).choice(rows, size=N_EXCL, replace=False).astype(np.int64)
 
@@ -316,43 +443,29 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness of this very configuration, once, before timing (cheap: regenerates only the winners on host)
-    api = sharded if sharded is not None else store
+    # ---- correctness of this very configuration, before timing: the answer of an independent route (dense-score kernel
+    # over every shard + host fp64 re-score + one global order), and the digest every N must share
     got_rows, got_scores, info = api.recommend(query=q, exclude_rows=excl, k=K, return_info=True)
-    qn = q.astype(np.float64) / np.linalg.norm(q.astype(np.float64))
-    for r, sc in zip(got_rows, got_scores):
-        row = synth.quantise(synth.catalog_rows_f32(0, int(r), 1, DIM), DTYPE)[0]
-        ref = float(row @ qn / np.linalg.norm(row))
-        assert abs(ref - sc) <= 1e-9 * max(1.0, abs(ref)), (r, sc, ref)
+    want_rows, want_scores = independent_topk(store, dist, world, q, excl, K, DTYPE)
+    assert np.array_equal(got_rows, want_rows), ("top-k ids differ from the independent route", got_rows, want_rows)
+    assert np.allclose(got_scores, want_scores, rtol=1e-9, atol=0), (got_scores, want_scores)
     assert info["proven_exact"] and len(got_rows) == K and not set(got_rows.tolist()) & set(excl.tolist())
+    result_digest = digest(got_rows, got_scores)
+    dkey = f"query:{rows}x{DIM}:{DTYPE}:k{K}:excl{N_EXCL}"
+    want_digest = expected_digest(dkey)
+    if want_digest is not None:
+        assert result_digest == want_digest, f"result digest {result_digest} != the committed single-GPU digest {want_digest} ({dkey})"
 
-    # ---- value: device-resident query, kernels only
+    # ---- value: device-resident query, ONE launch per step (fast pass + exact pass + ranking [+ exchange + merge])
     excl_ptr, ne = store.stage_inputs(q, None, None, excl, K, kc)
+    if sharded is not None:
+        sharded.backend._excl = (excl_ptr, ne)
     torch.cuda.synchronize()
-    scratch = store._scratch()
-    filt = nat.Filter()
-    filt.exclude_rows, filt.n_exclude = excl_ptr, ne
-    import ctypes as C
-    ob = scratch.d_out.data_ptr()
 
-    def step(ev=None):
-        st = torch.cuda.current_stream().cuda_stream
-        if ev is not None:
-            ev[0].record()
-        nat.check(lib.rebert_gemv_topk(C.byref(store._c), scratch.qn32.data_ptr(), C.byref(filt), kc, scratch.ws.data_ptr(),
-                                       scratch.ws.numel(), scratch.cand.data_ptr(), st))
-        if ev is not None:
-            ev[1].record()
-        nat.check(lib.rebert_finalize_topk(C.byref(store._c), scratch.qn64.data_ptr(), scratch.cand.data_ptr(), kc, K, ob,
-                                           ob + 8 * K, ob + 16 * K, ob + 16 * K + 8, st))
-        if sharded is not None:
-            if sharded.backend.exchange == "p2p":
-                sharded.backend.exchange_merge(scratch.d_out, K)          # one kernel: P2P stores + flags + merge
-            else:
-                buf = sharded._gather_buf(K, scratch.d_out)
-                dist.all_gather_into_tensor(buf.view(-1), scratch.d_out)
-                sharded.backend.merge(buf, K)
-
+    if sharded is not None:
+        step = lambda: sharded.enqueue(K, kc)
+    else:
+        step = lambda: store.enqueue_fused(K, kc, excl_ptr, ne)
     for _ in range(warmup):
         step()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -361,58 +474,191 @@ def run_b200(args):
     with ClockSampler(local_rank) as clocks:
         t0.record()
         for i in range(steps):
-            step(kev[i])
+            kev[i][0].record()
+            step()
+            kev[i][1].record()
         t1.record()
         barrier()
     elapsed_ms = t0.elapsed_time(t1)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / steps
     if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-        t = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kernel_ms = float(t.item())
+        elapsed_ms, kernel_ms = float(t[0].item()), float(t[1].item())
     value = steps / (elapsed_ms * 1e-3)
 
     # ---- e2e: host buffers in, host buffers out, through the public API
-    for _ in range(warmup):
-        api.recommend(query=q, exclude_rows=excl, k=K)
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(steps):
-        api.recommend(query=q, exclude_rows=excl, k=K)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = steps / e2e_s
-    h2d, d2h = int(store.last_h2d_bytes), (2 * K + 2) * 8
+    e2e_s = time_wall(lambda: api.recommend(query=q, exclude_rows=excl, k=K), steps, warmup, barrier, world, dist, dev)
+    e2e = 1.0 / e2e_s
+    h2d, d2h = int(store.last_h2d_bytes), int(store.last_d2h_bytes)
 
-    prefilter = None
-    if world == 1 and not args.no_prefilter:
+    configs = {}
+
+    def guarded(name, fn):
         try:
-            prefilter = prefilter_leg(store, q, excl, rows, min(steps, 100), warmup, got_rows, got_scores)
+            configs[name] = fn()
         except Exception as e:  # the headline line must survive a failure of a secondary measurement
-            prefilter = {"error": repr(e)[:200]}
-        store._c8 = None                                 # free the shadow before the batched leg
+            configs[name] = {"error": repr(e)[:300]}
+
+    # ---- profile request: the reference's real route (lib.py:43-55): ~85 liked rows -> profile, ~133 rated rows masked
+    def profile_leg():
+        rated, rts = None, None
+        for cr, ct in synth.user_ratings(2, rows, 64):
+            if rated is None or abs(int((ct >= 3.5).sum()) - 85) + abs(len(cr) - 133) < abs(int((rts >= 3.5).sum()) - 85) + abs(len(rated) - 133):
+                rated, rts = cr, ct
+        liked = rated[rts >= 3.5]
+        r, sc, inf = api.recommend(liked_rows=liked, exclude_rows=rated, k=K, return_info=True)
+        assert inf["proven_exact"] and not set(r.tolist()) & set(rated.tolist())
+        ikey = f"profile-ids:{rows}x{DIM}:{DTYPE}:k{K}"
+        want = expected_digest(ikey)
+        if want is not None:
+            assert digest(r) == want, f"profile request: ids digest {digest(r)} != the committed single-GPU digest {want}"
+        s = time_wall(lambda: api.recommend(liked_rows=liked, exclude_rows=rated, k=K), steps, warmup, barrier, world, dist, dev)
+        return {"workload": f"user-profile request: {len(liked)} liked rows -> mean of unit rows, {len(rated)} rated rows excluded, top-{K} over {rows} x {DIM} {DTYPE}",
+                "e2e": {"value": 1.0 / s, "unit": "queries/s", "ms_per_step": 1e3 * s}, "vs_query_request_e2e": (1.0 / s) / e2e,
+                "ids_digest": digest(r), "result_digest": digest(r, sc),
+                "note": "ids identical at every N (asserted against tests/golden/bench_digests.json); scores agree to 1e-12 — the fp64 "
+                        "partial profiles of the shards are added in rank order, a different association than one GPU's row order"}
+    guarded("profile_request", profile_leg)
+
+    # ---- int8 prefilter shadow: same request, half the bytes in the fast pass, same ids and scores (proven per request)
+    def prefilter_leg():
+        eps = api.enable_prefilter()
+        r, sc, inf = api.recommend(query=q, exclude_rows=excl, k=K, return_info=True)
+        same = bool(np.array_equal(r, got_rows) and np.array_equal(sc, got_scores))
+        if sharded is not None:
+            dev_ms = None
+        else:
+            dev_ms = time_device(lambda: store.enqueue_fused(K, 256, excl_ptr, ne, None, prefilter=True), min(steps, 100), warmup, barrier, world, dist, dev)
+        s = time_wall(lambda: api.recommend(query=q, exclude_rows=excl, k=K), min(steps, 100), warmup, barrier, world, dist, dev)
+        shadow_bytes = store.n * store._c8.ld
+        out = {"workload": f"same request, fast pass over an int8 shadow of the catalog ({shadow_bytes / 1e9:.2f} GB per GPU), 256 candidates, "
+                           f"exact fp64 pass over the bf16 rows in the same launch",
+               "e2e": {"value": 1.0 / s, "unit": "queries/s", "ms_per_step": 1e3 * s},
+               "error_bound": eps, "margin": inf.get("margin"), "proven_on_shadow_candidates": bool(inf.get("prefilter")),
+               "same_ids_and_scores_as_plain_path": same, "result_digest": digest(r, sc), "rows": rows}
+        if dev_ms is not None:
+            out.update(value=1e3 / dev_ms, unit="queries/s", ms_per_step=dev_ms, shadow_gbs=shadow_bytes / (dev_ms * 1e-3) / 1e9,
+                       frac_of_measured_hbm_peak=shadow_bytes / (dev_ms * 1e-3) / 1e9 / pk["hbm"],
+                       e2e_vs_device_resident=(1.0 / s) / (1e3 / dev_ms))
+        return out
+    if not args.no_prefilter:
+        guarded("prefilter_int8", prefilter_leg)
+        store._c8 = None                                 # free the shadow before the batched legs
         store._q8_rows = store._q8_factor = None
+        if sharded is not None:
+            sharded.q8_eps = None
         torch.cuda.empty_cache()
 
-    batched = None
+    # ---- C4 batched: 4096 users x the 10M catalog, top-100 (tcgen05), sharded when N > 1
     if not args.no_batched:
-        try:
-            batched = batched_leg(store, sharded, world, rows, dev)
-        except Exception as e:  # the headline line must survive a failure of the secondary measurement
-            batched = {"error": repr(e)[:200]}
+        guarded("C4_batched_10M", lambda: batched_leg(store, sharded, world, rows, dev, barrier))
+
+    # ---- C5 (N > 1): ragged-CSR profile build + genre/year-filtered top-50 over the sharded catalog
+    def c5_leg():
+        B, K5 = 4096, 50
+        g, y = synth.movie_metadata(3, store.row_base, store.n)
+        store.set_metadata(g, y)
+        rf = RowFilter(genre_any=0b1011, year_lo=1960, year_hi=2000)
+        rng = np.random.default_rng(2)
+        lp = np.zeros(B + 1, dtype=np.int64)
+        ep = np.zeros(B + 1, dtype=np.int64)
+        lc, ec = [], []
+        for u in range(B):                                   # ~133 rated / ~85 liked per user (create-embeddings.ipynb:961-975)
+            rated = np.unique(rng.integers(0, rows, size=max(2, int(rng.lognormal(np.log(133) - 0.4, 0.9)))))
+            liked = rated[rng.random(len(rated)) < 0.637]
+            if len(liked) == 0:
+                liked = rated[:1]
+            lc.append(liked); ec.append(rated); lp[u + 1] = lp[u] + len(liked); ep[u + 1] = ep[u] + len(rated)
+        lc = np.concatenate(lc).astype(np.int32)
+        ec = np.concatenate(ec).astype(np.int32)
+        red = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
+        build = lambda: store.build_profiles(lp, lc, None, reduce_fn=red)
+        qn32, qn64, qbf = build()
+        t_prof = time_device(build, 3, 1, barrier, world, dist, dev)
+        if sharded is not None:
+            ctx = sharded.batch_context(qbf, qn64, K5, ep, ec, rf)
+            t_step = time_device(lambda: sharded.batch_step(ctx), 3, 1, barrier, world, dist, dev)
+            status = ctx["gathered"][:, 2 * B * K5 + ctx["hb"]:].contiguous().view(torch.int32)[:, :B].max(dim=0).values
+            nrerun = int((status != 0).sum().item())
+            plan = ctx["plan"]
+        else:
+            import ctypes as C
+            plan = store.gemm_plan(B, K5)
+            ept, ect = torch.from_numpy(ep).to(dev), torch.from_numpy(ec).to(dev)
+            ws = torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan)), dtype=torch.uint8, device=dev)
+            o = (torch.empty((B, K5), dtype=torch.int64, device=dev), torch.empty((B, K5), dtype=torch.float64, device=dev),
+                 torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev))
+            t_step = time_device(lambda: store.enqueue_batch(plan, qbf, qn64, ept, ect, ws, *o, rf), 3, 1, barrier, world, dist, dev)
+            nrerun = int((o[3] != 0).sum().item())
+        flops = 2.0 * B * rows * DIM
+        return {"workload": f"C5: {world} x B200, {B} users (CSR, nnz_liked={len(lc)}), profile build + genre/year-filtered top-{K5} over {rows} x {DIM} bf16",
+                "profile_build_ms": t_prof, "score_filter_topk_ms": t_step, "users_per_s": B / ((t_prof + t_step) * 1e-3),
+                "tflops_scoring": flops / (t_step * 1e-3) / 1e12, "frac_of_measured_bf16_peak": flops / (t_step * 1e-3) / 1e12 / (pk["bf16"] * world),
+                "queries_flagged_for_rerun": nrerun, "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
+    if not args.no_batched:
+        guarded("C5_csr_profiles_genre_year_top50", c5_leg)
+
+    # ---- single-GPU configs measured on rank 0's GPU only at N = 1 (they do not shard: C1-C3 are one-GPU configs)
+    if world == 1 and not args.no_configs:
+        del store
+        if sharded is None:
+            api = None
+        torch.cuda.empty_cache()
+
+        def c2_leg():
+            out = {}
+            for dt in ("fp32", "bf16"):
+                n2 = 1_000_000
+                st2 = CatalogStore.synthetic(0, n2, DIM, dt, device=dev)
+                ex2 = np.random.default_rng(1).choice(n2, size=N_EXCL, replace=False).astype(np.int64)
+                r, sc, inf = st2.recommend(query=q, exclude_rows=ex2, k=K, return_info=True)
+                wr, ws_ = independent_topk(st2, dist, 1, q, ex2, K, dt)
+                assert np.array_equal(r, wr) and np.allclose(sc, ws_, rtol=1e-9, atol=0) and inf["proven_exact"], f"C2 {dt}: parity"
+                p2, n2e = st2.stage_inputs(q, None, None, ex2, K, kc)
+                ms = time_device(lambda: st2.enqueue_fused(K, kc, p2, n2e), max(steps, 50), warmup, barrier, 1, dist, dev)
+                s = time_wall(lambda: st2.recommend(query=q, exclude_rows=ex2, k=K), max(steps, 50), warmup, barrier, 1, dist, dev)
+                nbytes = n2 * DIM * (4 if dt == "fp32" else 2)
+                out[dt] = {"ms_per_query": ms, "queries_per_s": 1e3 / ms, "gbs": nbytes / (ms * 1e-3) / 1e9,
+                           "frac_of_measured_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"],
+                           "e2e_queries_per_s": 1.0 / s, "result_digest": digest(r, sc),
+                           "parity": "ids == independent dense-kernel route, scores within 1e-9 (asserted)"}
+                if dt == "bf16":
+                    out["_bf16_store"] = st2
+                else:
+                    del st2
+                    torch.cuda.empty_cache()
+            return out
+        guarded("C2_1M_single_query", c2_leg)
+        st_1m = None
+        if isinstance(configs.get("C2_1M_single_query"), dict):
+            st_1m = configs["C2_1M_single_query"].pop("_bf16_store", None)
+            configs["C2_1M_single_query"]["workload"] = f"1M x {DIM}, single-query top-{K} + {N_EXCL}-row exclusion, one launch per query"
+        if st_1m is not None and not args.no_batched:
+            guarded("C3_batched_4096x1M_top100", lambda: batched_leg(st_1m, None, 1, 1_000_000, dev, barrier, steps=5))
+        del st_1m
+        torch.cuda.empty_cache()
+        guarded("C1_cpu_sized_catalog", lambda: config_c1(dev))
+        # the reference's production catalog shape (movies-collab: 2269 x 32, create-embeddings.ipynb:1241)
+        def prod_leg():
+            n3, d3 = 2269, 32
+            st3 = CatalogStore.synthetic(0, n3, d3, "fp32", device=dev)
+            (rated, rts), = synth.user_ratings(2, n3, 1)
+            liked = rated[rts >= 3.5]
+            r, sc, inf = st3.recommend(liked_rows=liked, exclude_rows=rated, k=K, return_info=True)
+            s1 = time_wall(lambda: st3.recommend(liked_rows=liked, exclude_rows=rated, k=K), 2000, 50, barrier, 1, dist, dev)
+            q3 = synth.query_f32(1, d3)
+            s2 = time_wall(lambda: st3.recommend(query=q3, exclude_rows=rated, k=K), 2000, 50, barrier, 1, dist, dev)
+            return {"workload": f"{n3} x {d3} fp32 (the reference's production collab catalog), user with {len(liked)} liked / {len(rated)} rated",
+                    "e2e_user_recs_us": s1 * 1e6, "e2e_single_query_us": s2 * 1e6, "kernels_per_request": 1 if inf["kc"] == 0 else 2,
+                    "route": "one CTA scores every row in fp64 (exact by construction)" if inf["kc"] == 0 else "general"}
+        guarded("production_shape_2269x32", prod_leg)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        shard_rows = store.n
+        shard_rows = (rows * 1) // world if world > 1 else rows
         alg_bytes = shard_rows * DIM * 2                                  # catalog bytes one launch must read
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = ncu_traffic(f"gemv_topk_bf16_{shard_rows}") if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -420,24 +666,28 @@ def run_b200(args):
             "config": {"workload": workload_name(rows), "rows": rows, "dim": DIM, "k": K, "exclusions": N_EXCL,
                        "arithmetic": "bf16 catalog, fp32 accumulate in the streaming kernel, fp64 exact pass over the candidates",
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
-                       "exchange": (("fused P2P store+flag+merge kernel over NVLink peer memory" if sharded.backend.exchange == "p2p"
+                       "exchange": (("NVLink peer-memory stores + flags + merge in the tail of the scoring launch" if sharded.backend.exchange == "p2p"
                                      else "NCCL all-gather + merge kernel") if world > 1 else None),
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e9:.2f} GB read per step per GPU)"},
-            "roofline": {"bound": "hbm", "kernel": "gemv_topk_kernel<bf16,6,32,1> (scores + mask + top-k + cross-CTA merge, one launch)", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+            "result_digest": result_digest, "result_digest_expected": want_digest,
+            "result_check": "ids == independent dense-score-kernel route over all shards + host fp64 re-score; digest == committed single-GPU digest",
+            "roofline": {"bound": "hbm", "kernel": "gemv_topk_kernel<bf16,6,32,1> (scores + mask + top-k + cross-CTA merge + fp64 exact pass"
+                                                   + (" + NVLink exchange + merge" if world > 1 else "") + ", ONE launch per query)",
+                         "achieved": achieved, "peak": pk["hbm"], "peak_source": pk["hbm_src"], "unit": "GB/s", "frac": achieved / pk["hbm"],
                          "note": "the measured peak is a read+write copy; this kernel only reads, which HBM serves faster, so frac can exceed 1",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
-                         "traffic": ncu_traffic(f"gemv_topk_bf16_{shard_rows}")},
+                         "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "traffic": traffic,
+                         "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture of this kernel, not measured in this run)" if traffic else None},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / steps},
-            "gpu_launches": steps * (2 + (1 if world > 1 else 0)),
+                    "ms_per_step": 1e3 * e2e_s, "kernels_per_request": 2},
+            "gpu_launches": steps,
             "clocks": clocks.summary(),
-            "batched": batched,
-            "prefilter_int8": prefilter,
+            "configs": configs,
+            "batched": configs.get("C4_batched_10M"),
+            "prefilter_int8": configs.get("prefilter_int8"),
         }
         if world == 1 and not args.no_cpu_baseline:
-            qps, desc, _, cores = cpu_reference_leg(rows, 5, 1, args.cpu_sample_rows)
-            line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": desc}
+            qps, desc, _, cores = cpu_reference_leg(rows, 5, 1, args.cpu_sample_rows, budget_s=20.0)
+            line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "cpu_model": cpu_model(), "kind": "port", "sample": desc}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -453,8 +703,9 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override catalog rows (default 10M)")
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-prefilter", action="store_true", help="skip the secondary int8-prefilter measurement")
-    ap.add_argument("--no-batched", action="store_true", help="skip the secondary batched (tcgen05) measurement")
+    ap.add_argument("--no-prefilter", action="store_true", help="skip the int8-prefilter measurement")
+    ap.add_argument("--no-batched", action="store_true", help="skip the batched (tcgen05) measurements")
+    ap.add_argument("--no-configs", action="store_true", help="skip the single-GPU BASELINE configs C1-C3 and the production shape")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -189,12 +189,13 @@ REBERT_API int rebert_finalize_topk(const rebert_catalog_t* cat, const double* q
                          int32_t k, int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin,
                          rebert_stream stream);
 
-/* ---- device-resident request: ONE launch (lib.py:51-55 for a prepared query / profile) ------------------------- */
-/* Fast pass + exact pass + ranking in a single kernel launch: the last CTA of the streaming kernel re-scores the kc
- * candidates in fp64 from `cat` (the catalog of record), orders them and writes the packed result
+/* ---- device-resident request (lib.py:51-55 for a prepared query / profile) -------------------------------------- */
+/* Fast pass + exact pass + ranking as two chained launches without host involvement: the streaming kernel publishes its
+ * pruned candidate keys, and a cluster of 8 CTAs placed behind it by programmatic dependent launch selects the kc winners,
+ * re-scores them in fp64 from `cat` (the catalog of record), orders them and writes the packed result
  *     out_packed[0..k) rows | [k..2k) fp64 score bits | [2k] count (low 32 bits) + tag (high 32 bits) | [2k+1] margin
  * (device memory or device-addressable pinned host memory).  shadow != NULL: the fast pass streams the int8 shadow
- * (kc must be 256).  exchange != NULL with world > 1: the same launch also runs the NVLink exchange + merge, so that
+ * (kc must be 256).  exchange != NULL with world > 1: the cluster kernel also runs the NVLink exchange + merge, so that
  * out_packed is the merged result a single GPU would return (margin = the smallest over the ranks); *err_flag (int32,
  * device or pinned) becomes 1 + rank if a peer did not deliver within ~10 s, 101 + rank if its request tag differs. */
 REBERT_API int rebert_recommend_device(const rebert_catalog_t* cat, const rebert_catalog_t* shadow, const float* qn32, const double* qn64,
@@ -211,16 +212,15 @@ REBERT_API int rebert_recommend_host_scratch(const rebert_catalog_t* cat, int32_
  * weights), plus the sorted unique GLOBAL `exclude_rows`; device_filter may add device-resident bitmap / genre / year
  * tests.  The request is packed into the pinned block and read from there by the first kernel (zero-copy, no copy-engine
  * operation): a staging kernel normalises the query or builds the profile (mean of the liked rows' unit vectors), then
- * ONE launch does fused score + mask + top-k + fp64 exact pass and writes the packed result straight into the pinned
- * block; a stream synchronisation ends the call.  Catalogs small enough for one CTA (n * ld <= 131072 elements: the
- * reference's production 2269 x 32) are served by a single kernel that scores every row exactly in fp64.
+ * rebert_recommend_device's two chained launches do fused score + mask + top-k and the fp64 exact pass, whose packed
+ * result the kernel writes straight into the pinned block; a stream synchronisation ends the call.
  * `pinned` must therefore be page-locked memory the device can address.  out_rows / out_scores are host [k]
  * (-1 / -inf padded), *out_count <= k.
  * proof  (may be NULL = one attempt with `kc`, info->proven = 0): see rebert_proof_t — int8 shadow first, then the plain
  *        fast pass with kc, 4 kc, ... 256 candidates until the margin proves the id set.
  * exchange (may be NULL = single GPU): this rank's view of a row-sharded catalog.  Every rank calls with the same
  *        request; liked rows owned by other shards are summed there and the fp64 partial profiles are exchanged and
- *        added in rank order; the local results are exchanged and merged inside the scoring launch.  Each attempt uses
+ *        added in rank order; the local results are exchanged and merged by the exact-pass kernel.  Each attempt uses
  *        sequence numbers exchange->seq, seq + 1, ... (info->attempts of them).
  * Returns REBERT_ERR_INVALID with "Found array with 0 sample(s)" when liked_rows is given but empty (the reference's
  * own failure for a user without liked movies). */

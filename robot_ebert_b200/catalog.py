@@ -498,6 +498,7 @@ class CatalogStore:
                 s.hdev.data_ptr(), s.hdev.numel(), C.byref(proof), None if exchange is None else C.byref(exchange),
                 s.h_rows.ctypes.data, s.h_scores.ctypes.data, C.byref(cnt), C.byref(info),
                 torch.cuda.current_stream().cuda_stream)
+        s.last_attempts = int(info.attempts)         # exchange sequence numbers consumed, also when the call failed (per thread)
         nat.check(rc)
         n = cnt.value
         return s.h_rows[:n].copy(), s.h_scores[:n].copy(), {

@@ -244,7 +244,7 @@ __global__ void quantize_i8_kernel(const T* __restrict__ rows, const double* __r
 // Request staging for the host-buffer entry point: ONE CTA reads the raw query and the exclusion list straight from
 // the caller's pinned host block (zero-copy over PCIe, no copy-engine operation in front of the kernels), normalises the
 // query exactly as query_normalize_kernel does (same per-thread and reduction order => same bits) and drops the
-// exclusion list into device scratch for the scoring kernel.  (Helpers in request.cuh, shared with small.cu.)
+// exclusion list into device scratch for the scoring kernel.  (Helpers in request.cuh.)
 __global__ void __launch_bounds__(256) stage_query_kernel(const float* __restrict__ q_host, int d, int ld, float* __restrict__ qn32,
                                                           double* __restrict__ qn64, const int32_t* __restrict__ excl_host,
                                                           int n_excl, int32_t* __restrict__ excl_dev) {

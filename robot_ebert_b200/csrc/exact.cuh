@@ -66,38 +66,60 @@ struct QueryGlobal {
         for (int p = 0; p < PAIRS; ++p) q[p] = __ldg((const double2*)(q64 + (size_t)ch * (2 * PAIRS)) + p);
     }
 };
+// q [ld] (global) -> pair planes in shared memory.  Eight loads per thread are issued before the first store: a plain
+// load-store loop would pay one L2 round trip per iteration.
 __device__ __forceinline__ void stage_query_planes(const double* __restrict__ q, int ld, int epc, double* s_q) {
     const int chunks = ld / epc;
-    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
-        const int ch = i / epc, e = i - ch * epc;
-        s_q[((size_t)(e >> 1) * chunks + ch) * 2 + (e & 1)] = q[i];
+    for (int i0 = threadIdx.x; i0 < ld; i0 += 8 * blockDim.x) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * blockDim.x;
+            v[j] = i < ld ? __ldg(q + i) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * blockDim.x;
+            if (i < ld) {
+                const int ch = i / epc, e = i - ch * epc;
+                s_q[((size_t)(e >> 1) * chunks + ch) * 2 + (e & 1)] = v[j];
+            }
+        }
     }
 }
 
-// One warp, one row: every lane returns the score.  The summation order is fixed (lane-strided chunks, two
-// accumulators, xor-shuffle tree), so the result depends on nothing but the row and the query.
+// One warp, one row: every lane returns the score.  The summation order is fixed — lane l owns chunks l, l + 32, l + 64, ...;
+// even-numbered ones accumulate into a0, odd-numbered ones into a1, in ascending order; then a0 + a1 and an xor-shuffle
+// tree — so the result depends on nothing but the row and the query.  All of a lane's row chunks (up to NB at a time) are
+// requested before the first is used: candidate rows come from HBM (the streaming pass evicts them from L2 first), and one
+// round trip per row instead of one per pair of chunks is what makes the exact pass cheap.
 template <typename T, bool DIV, typename Q>
 __device__ __forceinline__ double exact_score_row(const T* __restrict__ rows, int ld, const double* __restrict__ norm64,
                                                   uint32_t local_row, const Q& qsrc, int lane) {
     constexpr int EPC = ChunkDot<T>::EPC;
     constexpr int PAIRS = ChunkDot<T>::PAIRS;
+    constexpr int NB = 6;                                // 6 x 32 chunks: a 1536-element bf16 row in one round, fp32 in two
     const int chunks = ld / EPC;
     const uint4* row = (const uint4*)(rows + (size_t)local_row * ld);
     const double nrm = __ldg(norm64 + local_row);
     double a0 = 0.0, a1 = 0.0;
-    int ch = lane;
-    for (; ch + 32 < chunks; ch += 64) {                 // two independent 16-byte loads in flight per lane
-        const uint4 v0 = __ldg(row + ch), v1 = __ldg(row + ch + 32);
-        double2 q0[PAIRS], q1[PAIRS];
-        qsrc.template load<PAIRS>(ch, q0);
-        qsrc.template load<PAIRS>(ch + 32, q1);
-        a0 = ChunkDot<T>::template dot<DIV>(v0, q0, a0, nrm);
-        a1 = ChunkDot<T>::template dot<DIV>(v1, q1, a1, nrm);
-    }
-    if (ch < chunks) {
-        double2 q0[PAIRS];
-        qsrc.template load<PAIRS>(ch, q0);
-        a0 = ChunkDot<T>::template dot<DIV>(__ldg(row + ch), q0, a0, nrm);
+    for (int base = lane; base < chunks; base += 32 * NB) {
+        uint4 v[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int ch = base + 32 * j;
+            if (ch < chunks) v[j] = __ldg(row + ch);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int ch = base + 32 * j;
+            if (ch < chunks) {
+                double2 q[PAIRS];
+                qsrc.template load<PAIRS>(ch, q);
+                if (j & 1) a1 = ChunkDot<T>::template dot<DIV>(v[j], q, a1, nrm);
+                else       a0 = ChunkDot<T>::template dot<DIV>(v[j], q, a0, nrm);
+            }
+        }
     }
     return DIV ? warp_sum(a0 + a1) : warp_sum(a0 + a1) / nrm;
 }
@@ -114,23 +136,18 @@ __device__ __forceinline__ double exact_score_row_rt(const void* rows, int dtype
 // (-1 / -inf padded), their number to *o_count.  fast_last = fast score of the worst kept candidate when the fast pass's
 // list was full (list_full): *o_margin = exact k-th - fast_last - 4 max|fast - exact| proves the id set when it exceeds the
 // fast pass's error bound; +inf when the list was not full (every allowed row is a candidate), -inf when two distinct
-// scores at or above the k-th place sit within 4 ulp and the caller computed them divide-after (neartie_matters).
+// scores at or above the k-th place sit within 4 ulp and the caller computed them divide-after (NEARTIE).
 // Every thread of the CTA must call; outputs may be shared, global or device-addressable pinned host memory.
+template <bool NEARTIE>
 __device__ __forceinline__ void rank_candidates(const double* s_score, const int64_t* s_row, int kc, int k, bool list_full, double fast_last,
-                                                double maxerr, bool neartie_matters, int64_t* o_rows, double* o_scores, int32_t* o_count,
-                                                double* o_margin, int* s_tmp /* 2 ints of shared scratch */,
+                                                double maxerr, int64_t* o_rows, double* o_scores, int32_t* o_count,
+                                                double* o_margin, int* s_tmp /* 2 ints of shared scratch, s_tmp[0] = s_tmp[1] = 0 on entry */,
                                                 double* s_kth /* 1 double of shared scratch */) {
-    if (threadIdx.x == 0) { s_tmp[0] = 0; s_tmp[1] = 0; *s_kth = 0.0; }
-    __syncthreads();
-    int mine = 0;
-    for (int c = threadIdx.x; c < kc; c += blockDim.x) mine += s_row[c] >= 0;
-    if (mine) atomicAdd(&s_tmp[0], mine);
-    __syncthreads();
-    const int valid = s_tmp[0];
-    const int nout = valid < k ? valid : k;
+    int valid_mine = 0;
     for (int c = threadIdx.x; c < kc; c += blockDim.x) {
         const int64_t r = s_row[c];
         if (r < 0) continue;
+        ++valid_mine;
         const double sc = s_score[c];
         int rank = 0;
         bool near = false;
@@ -139,26 +156,31 @@ __device__ __forceinline__ void rank_candidates(const double* s_score, const int
             if (rj < 0) continue;
             const double sj = s_score[j];
             if (better(sj, rj, sc, r)) ++rank;
-            const double gap = fabs(sj - sc);
-            near |= gap != 0.0 && gap <= 8.9e-16 * fmax(fabs(sc), 1e-300);   // distinct scores within 4 ulp
+            if (NEARTIE) {
+                const double gap = fabs(sj - sc);
+                near |= gap != 0.0 && gap <= 8.9e-16 * fmax(fabs(sc), 1e-300);   // distinct scores within 4 ulp
+            }
         }
-        if (neartie_matters && near && rank <= k) s_tmp[1] = 1;    // a divide-after formula cannot be trusted to order these
+        if (NEARTIE && near && rank <= k) s_tmp[1] = 1;    // a divide-after formula cannot be trusted to order these
         if (rank < k) {
             o_rows[rank] = r;
             o_scores[rank] = sc;
             if (rank == k - 1) *s_kth = sc;
         }
     }
+    if (valid_mine) atomicAdd(&s_tmp[0], valid_mine);
+    __syncthreads();
+    const int valid = s_tmp[0];
+    const int nout = valid < k ? valid : k;
     for (int i = nout + threadIdx.x; i < k; i += blockDim.x) {
         o_rows[i] = -1;
         o_scores[i] = -INFINITY;
     }
-    __syncthreads();
     if (threadIdx.x == 0) {
         *o_count = nout;
         if (o_margin) {
             double mg = (list_full && valid >= k) ? *s_kth - fast_last - 4.0 * maxerr : INFINITY;
-            if (s_tmp[1]) mg = -INFINITY;
+            if (NEARTIE && s_tmp[1]) mg = -INFINITY;
             *o_margin = mg;
         }
     }

@@ -15,6 +15,7 @@
 #pragma once
 
 #include "exact.cuh"
+#include "merge.cuh"
 
 namespace rebert {
 
@@ -141,9 +142,11 @@ __device__ __forceinline__ void exchange_profile(const Exchange& x, int len, con
 // host side: fill an Exchange from the C-ABI description (defined in finalize.cu)
 int make_exchange(const rebert_exchange_t* ex, int32_t* err_flag, Exchange* out);
 
-// ---- internal launchers shared by gemv_topk.cu / catalog.cu / small.cu / host_api.cu --------------------------------
-// Single-query kernel.  fused != nullptr: exact pass + packed result (+ exchange) in the same launch; else the kc candidate
-// keys go to cand_keys.
+// ---- internal launchers shared by gemv_topk.cu / finalize.cu / catalog.cu / host_api.cu ----------------------------
+// Request form of the single-query path: the streaming kernel publishes its pruned candidate keys, and a cluster kernel
+// placed behind it by programmatic dependent launch selects the kc winners, re-scores them in fp64, ranks them and writes
+// the packed result (and runs the exchange on a row shard).  fused == nullptr: the streaming kernel alone, kc candidate
+// keys to cand_keys (the last CTA merges).
 struct GemvFused {
     const rebert_catalog_t* exact_cat;   // catalog of record (the streamed catalog may be its int8 shadow)
     const double* q64;
@@ -151,15 +154,19 @@ struct GemvFused {
     unsigned long long* out_packed;
     uint32_t tag;
     const Exchange* xchg;                // nullptr on a single GPU
+    uint32_t* done_flag;                 // device-addressable pinned host word that receives done_token after the result (or nullptr)
+    uint32_t done_token;
 };
+// What the streaming kernel leaves in the workspace for the cluster kernel.
+struct Published {
+    PublishedKeys keys;
+    unsigned* ctl;             // 32 control words (ticket, hint, tile claims, compaction cursors): the cluster kernel leaves them zero
+    unsigned long long* trace; // tuning only
+};
+int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t row_base, cudaStream_t st);
 int gemv_launch(const rebert_catalog_t* cat, const float* qn32, const rebert_filter_t* filter, int32_t kc, void* workspace,
                 size_t workspace_bytes, uint64_t* cand_keys, const GemvFused* fused, cudaStream_t st);
 int stage_profile_launch(const rebert_catalog_t* cat, const int32_t* liked_host, const float* w_host, int n_liked, const int32_t* excl_host,
                          int n_excl, int32_t* excl_dev, double* sum64, double* wsum, float* qn32, double* qn64, const Exchange* x,
                          cudaStream_t st);
-bool small_catalog(const rebert_catalog_t* cat, int n_excl);
-int small_recommend_launch(const rebert_catalog_t* cat, const float* q_host, const int32_t* liked_host, const float* w_host, int n_liked,
-                           const int32_t* excl_host, int n_excl, const rebert_filter_t* device_filter, int k,
-                           unsigned long long* out_packed, cudaStream_t st);
-
 }  // namespace rebert

@@ -3,9 +3,13 @@
 //                          (sklearn cosine_similarity: x/||x||, y/||y||, dot — lib.py:51), then the
 //                          (score desc, row asc) order of lib.py:55,63, best k out.
 //   rebert_merge_topk    : the same order across per-shard result lists (row-sharded catalogs).
+#include <cooperative_groups.h>
+
 #include "exchange.cuh"
 
 namespace rebert {
+
+namespace cg = cooperative_groups;
 
 constexpr int kFinalThreads = 1024;
 constexpr int kMaxKc = 1024;
@@ -32,7 +36,7 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
     pdl_wait();                                      // the candidates come from the kernel launched just before
     const uint64_t* keys = cand_keys + (size_t)u * kc;
     stage_query_planes(q64 + (size_t)u * ld, ld, EPC, s_q);
-    if (threadIdx.x == 0) s_maxerr = 0ull;
+    if (threadIdx.x == 0) { s_maxerr = 0ull; s_tmp[0] = 0; s_tmp[1] = 0; }
     __syncthreads();
     const QueryPlanes qsrc{s_q, ld / EPC};
 
@@ -56,9 +60,190 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
     // minus 4x the largest fast-vs-exact deviation seen on the candidates themselves, which calibrates whatever
     // rounding the fast pass had (fp32 accumulation, bf16 queries on the tensor-core path)
     const uint64_t last = keys[kc - 1];
-    rank_candidates(s_score, s_row, kc, k, last != 0, last ? (double)key_score(last) : 0.0,
-                    __longlong_as_double((long long)s_maxerr), /*neartie_matters=*/!DIV, out_rows + (size_t)u * k,
-                    out_scores + (size_t)u * k, out_count + u, out_margin ? out_margin + u : nullptr, s_tmp, &s_kth);
+    rank_candidates<!DIV>(s_score, s_row, kc, k, last != 0, last ? (double)key_score(last) : 0.0,
+                          __longlong_as_double((long long)s_maxerr), out_rows + (size_t)u * k,
+                          out_scores + (size_t)u * k, out_count + u, out_margin ? out_margin + u : nullptr, s_tmp, &s_kth);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Request path, second (and last) launch: a CLUSTER of 8 CTAs placed behind the streaming kernel by programmatic dependent
+// launch.  The streaming kernel's CTAs have published their pruned candidate keys (gemv_topk.cu); here
+//   (1) every CTA selects the kc winners from them (redundantly — 30 KB of keys, cheaper than any cross-CTA step),
+//   (2) the winners are dealt out over the 8 x 8 warps of the cluster for the fp64 exact pass — one row per warp, on 8 SMs,
+//       instead of a queue of rows behind one SM's fp64 unit — and each warp stores its score straight into CTA 0's shared
+//       memory (distributed shared memory),
+//   (3) CTA 0 ranks by (score desc, row asc), writes the packed result (device or pinned host memory) and, on a row shard,
+//       runs the NVLink exchange + merge; it leaves the streaming kernel's control words zero for the next request.
+// 256 threads, <= 128 registers and ~30 KB of shared memory per CTA: small enough to be resident beside the streaming
+// kernel's CTAs, so the cluster is already waiting in griddepcontrol.wait when the stream ends.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFinalCluster = 8;
+constexpr int kFinalClusterThreads = 256;
+
+struct FinalizeParams {
+    Published pub;
+    const void* x_rows;
+    const double* x_norm64;
+    const double* q64;
+    int x_ld, x_dtype;
+    int64_t row_base;
+    int k, cap;
+    unsigned long long* out_packed;
+    uint32_t tag;
+    uint32_t* done_flag;       // pinned host word the host polls instead of synchronising the stream (or nullptr)
+    uint32_t done_token;
+    Exchange xchg;
+};
+
+__device__ __forceinline__ unsigned long long ftimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FIN_TRACE(slot) do { if (p.pub.trace && threadIdx.x == 0 && crank == 0) p.pub.trace[(slot)] = ftimer_ns(); } while (0)
+
+__global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_kernel(const FinalizeParams p) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int kc = p.pub.keys.kc, k = p.k;
+    double* s_q = (double*)fsm;                                        // [x_ld] fp64 query, pair planes
+    uint64_t* buf = (uint64_t*)(s_q + p.x_ld);                         // [cap]
+    uint64_t* fk = buf + p.cap;                                        // [kc] winners, best fast score first
+    double* s_score = (double*)(fk + kc);                              // [kc]   (filled remotely in CTA 0)
+    int64_t* s_row = (int64_t*)(s_score + kc);                         // [kc]
+    unsigned long long* s_werr = (unsigned long long*)(s_row + kc);    // [cluster warps] largest |fast - exact| per warp
+    unsigned long long* s_block = s_werr + kFinalCluster * (kFinalClusterThreads / 32);   // [2 k + 2] local result (row shards)
+    __shared__ int s_tmp[2];
+    __shared__ double s_kth;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kFinalClusterThreads / 32;
+    FIN_TRACE(0);
+    pdl_trigger();
+    if (threadIdx.x == 0) { s_tmp[0] = 0; s_tmp[1] = 0; }
+    cluster.sync();                                  // every CTA of the cluster is running: its shared memory may be addressed.
+                                                     // Done HERE, while the stream is still running, it costs nothing.
+    pdl_wait();                                      // the keys come from the streaming kernel launched just before
+    // (Waiting on the CTAs' publish counter instead would start 1-3 us earlier, but a cluster placed early by programmatic
+    // launch could then mistake the PREVIOUS request's count for its own; stream order is the simple, safe hand-off.)
+    FIN_TRACE(1);
+    const int epc = p.x_dtype == REBERT_F32 ? 4 : 8;
+    // the fp64 query: its loads are issued here, ahead of the ones select_winners issues, and consumed only afterwards —
+    // one L2 round trip for everything this kernel reads before the candidate rows
+    constexpr int kQPre = 8;
+    double qv[kQPre];
+#pragma unroll
+    for (int j = 0; j < kQPre; ++j) {
+        const int i = threadIdx.x + j * kFinalClusterThreads;
+        qv[j] = i < p.x_ld ? __ldg(p.q64 + i) : 0.0;
+    }
+    select_winners<16>(p.pub.keys, p.cap, buf, fk, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
+    {
+        const int chunks = p.x_ld / epc;
+#pragma unroll
+        for (int j = 0; j < kQPre; ++j) {
+            const int i = threadIdx.x + j * kFinalClusterThreads;
+            if (i < p.x_ld) {
+                const int ch = i / epc, e = i - ch * epc;
+                s_q[((size_t)(e >> 1) * chunks + ch) * 2 + (e & 1)] = qv[j];
+            }
+        }
+        for (int i = kQPre * kFinalClusterThreads + threadIdx.x; i < p.x_ld; i += kFinalClusterThreads) {   // rows beyond 2048 elements
+            const int ch = i / epc, e = i - ch * epc;
+            s_q[((size_t)(e >> 1) * chunks + ch) * 2 + (e & 1)] = __ldg(p.q64 + i);
+        }
+    }
+    __syncthreads();
+    FIN_TRACE(2);
+    double* r_score = cluster.map_shared_rank(s_score, 0);
+    int64_t* r_row = cluster.map_shared_rank(s_row, 0);
+    unsigned long long* r_werr = cluster.map_shared_rank(s_werr, 0);
+    const QueryPlanes qsrc{s_q, p.x_ld / epc};
+    double werr = 0.0;
+    for (int c = crank * nwarps + warp; c < kc; c += kFinalCluster * nwarps) {
+        const uint64_t key = fk[c];
+        double sc = -INFINITY;
+        int64_t gr = -1;
+        if (key != 0) {
+            const uint32_t lr = key_row(key);
+            sc = exact_score_row_rt(p.x_rows, p.x_dtype, p.x_ld, p.x_norm64, lr, qsrc, lane);
+            gr = p.row_base + lr;
+            werr = fmax(werr, fabs(sc - (double)key_score(key)));
+        }
+        if (lane == 0) { r_score[c] = sc; r_row[c] = gr; }
+    }
+    if (lane == 0) r_werr[crank * nwarps + warp] = (unsigned long long)__double_as_longlong(werr);
+    FIN_TRACE(7);
+    cluster.sync();                                  // all scores have landed in CTA 0
+    if (crank != 0) return;
+    FIN_TRACE(3);
+    unsigned long long me = 0;                       // bits of non-negative doubles: integer order == numeric order
+    for (int i = lane; i < kFinalCluster * nwarps; i += 32) me = s_werr[i] > me ? s_werr[i] : me;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, me, o); me = v > me ? v : me; }
+    const uint64_t last = fk[kc - 1];
+    const bool exchange = p.xchg.world > 1;
+    unsigned long long* blk = exchange ? s_block : p.out_packed;
+    rank_candidates<false>(s_score, s_row, kc, k, last != 0, last ? (double)key_score(last) : 0.0, __longlong_as_double((long long)me),
+                           (int64_t*)blk, (double*)(blk + k), (int32_t*)(blk + 2 * k), (double*)(blk + 2 * k + 1), s_tmp, &s_kth);
+    if (threadIdx.x == 0) ((uint32_t*)(blk + 2 * k))[1] = p.tag;
+    FIN_TRACE(4);
+    if (exchange) {
+        __syncthreads();
+        exchange_results(p.xchg, k, s_block, p.out_packed);
+    }
+    if (threadIdx.x < 32) p.pub.ctl[threadIdx.x] = 0u;       // ticket, hint, tile-claim counter, compaction cursors
+    if (p.done_flag) {
+        __syncthreads();                                     // every thread's result stores are ordered before the flag
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            *(volatile uint32_t*)p.done_flag = p.done_token;
+        }
+    }
+    FIN_TRACE(5);
+}
+
+int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t row_base, cudaStream_t st) {
+    FinalizeParams p;
+    memset(&p, 0, sizeof(p));
+    p.pub = pub;
+    p.x_rows = f.exact_cat->rows;
+    p.x_norm64 = f.exact_cat->norm64;
+    p.q64 = f.q64;
+    p.x_ld = f.exact_cat->ld;
+    p.x_dtype = f.exact_cat->dtype;
+    p.row_base = row_base;
+    p.k = f.k;
+    int need = 2 * pub.keys.kc > pub.keys.kc + pub.keys.lists ? 2 * pub.keys.kc : pub.keys.kc + pub.keys.lists;
+    int cap = 1024;
+    while (cap < need) cap <<= 1;
+    p.cap = cap;
+    p.out_packed = f.out_packed;
+    p.tag = f.tag;
+    p.done_flag = f.done_flag;
+    p.done_token = f.done_token;
+    if (f.xchg) p.xchg = *f.xchg;
+    const size_t smem = (size_t)p.x_ld * 8 + (size_t)cap * 8 + (size_t)pub.keys.kc * 24 + (size_t)kFinalCluster * (kFinalClusterThreads / 32) * 8 +
+                        (size_t)(2 * f.k + 2) * 8;
+    auto kern = finalize_published_kernel;
+    { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kFinalCluster);
+    cfg.blockDim = dim3(kFinalClusterThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kFinalCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    REBERT_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
 }
 
 // One CTA per query: rank-merge `lists` sorted lists of up to k entries each.  List l of query u lives at

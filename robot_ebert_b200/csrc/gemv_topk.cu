@@ -16,10 +16,10 @@
 //   * at the end the 8 warp lists are rank-merged through shared memory into one sorted list per CTA, and the last
 //     CTA to finish (atomic ticket) merges the per-CTA lists behind two pruning thresholds — one launch per query.
 //     The N-long score vector never exists;
-//   * FUSED TAIL (rebert_gemv_topk_fused, the request path): the last CTA does not stop at the candidate keys — its warps
-//     re-score the kc winners in fp64 with the oracle's formula (exact.cuh), rank them by (score desc, row asc), write the
-//     packed result (device or pinned host memory) and, on a row shard, run the NVLink exchange + merge (exchange.cuh).
-//     One launch per request instead of three;
+//   * REQUEST PATH (rebert_recommend_device): the CTAs only PUBLISH their pruned keys (compacted through one atomic cursor)
+//     plus the heads / tails of their lists; a cluster of 8 small CTAs (finalize.cu), placed behind this kernel by
+//     programmatic dependent launch and already waiting when the stream ends, selects the kc winners, re-scores them in
+//     fp64 on 8 SMs, ranks them, writes the result and runs the NVLink exchange on a row shard;
 //   * launched with programmatic stream serialization: no access to memory an earlier kernel of the stream writes before
 //     griddepcontrol.wait.  The catalog is immutable, so the producer starts streaming the first tiles BEFORE that wait:
 //     the first TMA round trip overlaps the previous kernel's tail (query staging / the previous request's merge).
@@ -51,8 +51,12 @@ struct GemvParams {
     int          kc;
     int          l2_policy; // 0 = evict_first (default), 1 = evict_normal, 2 = evict_last  (tuning knob)
     DevFilter    filter;
-    uint64_t*    cta_lists; // [grid, kc]
-    uint64_t*    cand_keys; // [kc] final output
+    uint64_t*    pub_keys;  // [kPubRegions][region_cap] kept keys of all CTAs: CTA b compacts into region b % kPubRegions
+    uint64_t*    pub_heads; // [grid, pub_P] the pub_P = ceil(kc / grid) best keys of every CTA (zero padded)
+    uint64_t*    pub_tails; // [grid] kc-th key of a CTA whose list is full, else 0
+    unsigned*    cursors;   // [kPubRegions] compaction cursors (zero before launch; reset by whoever merges)
+    int          pub_P, region_cap;
+    uint64_t*    cand_keys; // [kc] final output (rebert_gemv_topk: the last CTA merges)
     unsigned*    counter;   // CTAs finished (zero before launch; the last CTA resets it)
     unsigned*    ghint;     // grid-wide threshold hint, orderable fp32 bits (zero before launch; reset with the counter)
     unsigned*    tile_ctr;  // tail tiles claimed so far (zero before launch; reset with the counter)
@@ -62,18 +66,7 @@ struct GemvParams {
     int          merge_prune; // 1 = the CTA merge drops keys below the threshold hints (default; 0 is a tuning knob)
     int          early_tma; // 1 = first tiles are requested before griddepcontrol.wait (default; 0 is a tuning knob)
     int          merge_cap; // keys the final merge may hold in shared memory (power of two)
-    int*         cta_count; // [grid] keys each CTA published
-    // ---- fused tail (fused != 0): exact pass + result (+ exchange) inside this launch
-    int          fused;
-    int          k;
-    const void*  x_rows;    // catalog of record the exact pass reads (differs from `rows` when an int8 shadow is streamed)
-    const double* x_norm64;
-    const double* q64;      // [x_ld] fp64 unit query / profile
-    int          x_ld, x_dtype;
-    int64_t      row_base;
-    unsigned long long* out_packed;  // rows k | fp64 scores k | count + tag | margin   (device or pinned host memory)
-    uint32_t     tag;
-    Exchange     xchg;      // xchg.world > 1: the last CTA exchanges + merges with the peers before writing out_packed
+    int          publish_only;  // request path: no ticket, no merge here — the cluster kernel behind this launch takes over
 };
 
 template <typename T> struct Elem;
@@ -163,132 +156,12 @@ __device__ __forceinline__ void publish_hints(uint64_t key0, float thr, int warp
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Final merge, run by the LAST CTA to finish (no second launch): `lists` sorted lists of kc keys -> best kc.
-// Two cheap lower bounds on the kc-th best key prune almost everything before any sorting:
-//   T0 = max over lists of their kc-th key            (that one list alone holds kc keys >= T0)
-//   T1 = kc-th largest key among the first P = ceil(kc / lists) keys of every list
-// Keys >= max(T0, T1) (typically kc + a few) are gathered into shared memory and bitonic-sorted.  If a pathological
-// input (mass ties) overflows the buffer, a chunked full sort over all keys is used instead.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t ldcg_u64(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
-
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 #define REBERT_TRACE(slot) do { if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 8 + (slot)] = globaltimer_ns(); } while (0)
-
-__device__ void chunked_merge(const uint64_t* __restrict__ in, int total, int kc, int cap, uint64_t* buf,
-                              uint64_t* __restrict__ out) {
-    int done = 0, carried = 0;
-    while (true) {
-        int take = total - done;
-        if (take > cap - carried) take = cap - carried;
-        for (int i = threadIdx.x; i < take; i += blockDim.x) buf[carried + i] = ldcg_u64(in + done + i);
-        const int filled = carried + take;
-        int p2 = 2;
-        while (p2 < filled) p2 <<= 1;
-        for (int i = filled + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
-        __syncthreads();
-        block_bitonic_sort_desc(buf, p2);
-        done += take;
-        carried = kc;
-        if (done >= total) break;
-    }
-    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
-}
-
-constexpr int kMaxLists = 256;               // per-CTA lists the final merge can index (grid <= number of SMs <= 256)
-
-// `out` may be shared or global memory.  counts_g[l] = keys list l really holds (the rest of its kc slots are zero).
-__device__ void final_merge(const uint64_t* __restrict__ lists_g, const int* __restrict__ counts_g, int lists, int kc, int cap,
-                            uint64_t* buf, uint64_t* out) {
-    __shared__ unsigned long long s_t0, s_t1;
-    __shared__ int s_cnt;
-    __shared__ int s_lcnt[kMaxLists];
-    __shared__ int s_pref[kMaxLists + 1];
-    if (threadIdx.x == 0) { s_t0 = 0; s_t1 = 0; s_cnt = 0; }
-    __syncthreads();
-    // The list sizes, T0 and the prefix set of T1 come from the same round of loads (every L2 round trip here is on the
-    // critical path of the whole launch: the other CTAs have already gone)
-    const int P = (kc + lists - 1) / lists;
-    const int S = P * lists;                       // kc <= S < kc + lists <= cap
-    unsigned long long t0 = 0;
-    for (int l = threadIdx.x; l < lists; l += blockDim.x) {
-        const unsigned long long v = ldcg_u64(lists_g + (size_t)l * kc + kc - 1);
-        s_lcnt[l] = __ldcg(counts_g + l);
-        t0 = v > t0 ? v : t0;
-    }
-    for (int e0 = threadIdx.x; e0 < S; e0 += 2 * blockDim.x) {
-        const int e1 = e0 + blockDim.x;
-        const uint64_t v0 = ldcg_u64(lists_g + (size_t)(e0 / P) * kc + (e0 % P));
-        const uint64_t v1 = e1 < S ? ldcg_u64(lists_g + (size_t)(e1 / P) * kc + (e1 % P)) : 0;
-        buf[e0] = v0;
-        if (e1 < S) buf[e1] = v1;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long v = __shfl_xor_sync(0xffffffffu, t0, o);
-        t0 = v > t0 ? v : t0;
-    }
-    if ((threadIdx.x & 31) == 0 && t0) atomicMax(&s_t0, t0);
-    __syncthreads();
-    // exclusive prefix of the list sizes (<= 256 lists: every thread sums its own prefix, no scan needed)
-    for (int l = threadIdx.x; l <= lists; l += blockDim.x) {
-        int acc = 0;
-        for (int j = 0; j < l; ++j) acc += s_lcnt[j];
-        s_pref[l] = acc;
-    }
-    // T1: rank-count for the kc-th largest of the prefix set
-    for (int e = threadIdx.x; e < S; e += blockDim.x) {
-        const uint64_t key = buf[e];
-        if (key == 0) continue;
-        int rank = 0;
-        for (int j = 0; j < S; ++j) rank += buf[j] > key;
-        if (rank == kc - 1) s_t1 = key;            // keys are distinct, so exactly one thread can hit this
-    }
-    __syncthreads();
-    const uint64_t T = s_t0 > s_t1 ? s_t0 : s_t1;
-    const int total = s_pref[lists];
-    // gather survivors: only the slots the lists really fill are read (hint pruning leaves ~kc per CTA of the 8 kc a CTA
-    // could hold), sixteen loads in flight per thread so their L2 latencies overlap
-    constexpr int kInFlight = 16;
-    for (int i0 = threadIdx.x; i0 < total; i0 += kInFlight * blockDim.x) {
-        uint64_t kk[kInFlight];
-#pragma unroll
-        for (int j = 0; j < kInFlight; ++j) {
-            const int i = i0 + j * blockDim.x;
-            kk[j] = 0;
-            if (i < total) {
-                int lo = 0, hi = lists;                  // list l with s_pref[l] <= i < s_pref[l + 1]
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pref[mid] <= i) lo = mid; else hi = mid; }
-                kk[j] = ldcg_u64(lists_g + (size_t)lo * kc + (i - s_pref[lo]));
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kInFlight; ++j) {
-            if (kk[j] != 0 && kk[j] >= T) {
-                const int idx = atomicAdd(&s_cnt, 1);
-                if (idx < cap) buf[idx] = kk[j];
-            }
-        }
-    }
-    __syncthreads();
-    const int cnt = s_cnt;
-    if (cnt > cap) {                               // mass ties: correct but slow path
-        __syncthreads();
-        chunked_merge(lists_g, lists * kc, kc, cap, buf, out);
-        return;
-    }
-    int p2 = 2;
-    while (p2 < cnt || p2 < kc) p2 <<= 1;
-    for (int i = cnt + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
-    __syncthreads();
-    block_bitonic_sort_desc(buf, p2);
-    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
-}
 
 template <typename T, int CPL, int LANES, int M>
 __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams p) {
@@ -642,10 +515,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
         if (lane == 0) s_kept[warp] = kept;
     }
     __syncthreads();
-    uint64_t* out = p.cta_lists + (size_t)blockIdx.x * kc;
+    uint64_t* merged = lists + kConsumerWarps * kc;      // [kc] this CTA's kept keys, best first, zero padded
+    __shared__ unsigned s_base;
     int total = 0;
 #pragma unroll
     for (int w = 0; w < kConsumerWarps; ++w) total += s_kept[w];
+    const int nkeep = total < kc ? total : kc;
+    const int region = blockIdx.x % kPubRegions;
+    if (threadIdx.x == 0) s_base = atomicAdd(p.cursors + region, (unsigned)nkeep);      // its round trip overlaps the rank merge below
+    for (int i = total + threadIdx.x; i < kc; i += blockDim.x) merged[i] = 0;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         int w = 0, e = i;                        // i-th kept key overall = entry e of warp list w
         while (e >= s_kept[w]) { e -= s_kept[w]; ++w; }
@@ -658,68 +536,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
             while (lo < hi) { int mid = (lo + hi) >> 1; if (L[mid] > key) lo = mid + 1; else hi = mid; }
             rank += lo;
         }
-        if (rank < kc) out[rank] = key;
+        if (rank < kc) merged[rank] = key;
     }
-    for (int i = total + threadIdx.x; i < kc; i += blockDim.x) out[i] = 0;
-    if (threadIdx.x == 0) p.cta_count[blockIdx.x] = total < kc ? total : kc;
+    __syncthreads();
+    // publish: the kept keys into the compacted array, the list's head (first pub_P keys) and tail (kc-th key if full)
+    {
+        uint64_t* dst = p.pub_keys + (size_t)region * p.region_cap + s_base;
+        for (int i = threadIdx.x; i < nkeep; i += blockDim.x) dst[i] = merged[i];
+        for (int j = threadIdx.x; j < p.pub_P; j += blockDim.x) p.pub_heads[(size_t)blockIdx.x * p.pub_P + j] = j < kc ? merged[j] : 0;
+        if (threadIdx.x == 0) p.pub_tails[blockIdx.x] = nkeep == kc ? merged[kc - 1] : 0;
+    }
+    REBERT_TRACE(5);                                   // CTA keys published
+    if (p.publish_only) return;                        // request path: the cluster kernel behind this launch merges
 
-    // ===================== last CTA to finish merges all per-CTA lists (no second launch) =====================
+    // ===================== rebert_gemv_topk: the last CTA to finish merges what all CTAs kept (no second launch) =========
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
-    REBERT_TRACE(5);                                   // CTA list written
     if (threadIdx.x == 0) s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (!p.fused) {
-        final_merge(p.cta_lists, p.cta_count, (int)gridDim.x, kc, p.merge_cap, (uint64_t*)smem, p.cand_keys);
-    } else {
-        // ---- fused tail: exact pass over the kc winners, ranking, result (and the exchange on a row shard)
-        uint64_t* fk = (uint64_t*)smem + p.merge_cap;                  // [kc] winners, best fast score first
-        double* s_score = (double*)(fk + kc);                          // [kc]
-        int64_t* s_row = (int64_t*)(s_score + kc);                     // [kc]
-        unsigned long long* s_block = (unsigned long long*)(s_row + kc);   // [2k + 2] packed local result (row shards)
-        __shared__ unsigned long long s_maxerr;
-        __shared__ int s_tmp[2];
-        __shared__ double s_kth;
-        final_merge(p.cta_lists, p.cta_count, (int)gridDim.x, kc, p.merge_cap, (uint64_t*)smem, fk);
-        if (threadIdx.x == 0) s_maxerr = 0ull;
+    {
+        PublishedKeys pub;
+        pub.keys = p.pub_keys; pub.cursors = p.cursors; pub.heads = p.pub_heads; pub.tails = p.pub_tails;
+        pub.lists = (int)gridDim.x; pub.P = p.pub_P; pub.kc = kc; pub.region_cap = p.region_cap;
+        select_winners<16>(pub, p.merge_cap, (uint64_t*)smem, p.cand_keys);
         __syncthreads();
-        REBERT_TRACE(6);                               // winners known
-        const QueryGlobal qsrc{p.q64};
-        for (int c = warp; c < kc; c += kThreads / 32) {
-            const uint64_t key = fk[c];
-            double sc = -INFINITY;
-            int64_t gr = -1;
-            if (key != 0) {
-                const uint32_t lr = key_row(key);
-                sc = exact_score_row_rt(p.x_rows, p.x_dtype, p.x_ld, p.x_norm64, lr, qsrc, lane);
-                gr = p.row_base + lr;
-            }
-            if (lane == 0) {
-                s_score[c] = sc;
-                s_row[c] = gr;
-                if (key != 0) atomicMax(&s_maxerr, (unsigned long long)__double_as_longlong(fabs(sc - (double)key_score(key))));
-            }
-        }
-        __syncthreads();
-        REBERT_TRACE(7);                               // exact pass done
-        const int k = p.k;
-        const uint64_t last = fk[kc - 1];
-        const bool exchange = p.xchg.world > 1;
-        unsigned long long* blk = exchange ? s_block : p.out_packed;
-        rank_candidates(s_score, s_row, kc, k, last != 0, last ? (double)key_score(last) : 0.0,
-                        __longlong_as_double((long long)s_maxerr), /*neartie_matters=*/false, (int64_t*)blk, (double*)(blk + k),
-                        (int32_t*)(blk + 2 * k), (double*)(blk + 2 * k + 1), s_tmp, &s_kth);
-        if (threadIdx.x == 0) ((uint32_t*)(blk + 2 * k))[1] = p.tag;
-        if (exchange) {
-            __syncthreads();
-            exchange_results(p.xchg, k, s_block, p.out_packed);
-        }
     }
     if (p.trace && threadIdx.x == 0) { p.trace[(size_t)gridDim.x * 8] = globaltimer_ns(); p.trace[(size_t)gridDim.x * 8 + 1] = blockIdx.x; }
-    if (threadIdx.x == 0) { *p.counter = 0; *p.ghint = 0u; *p.tile_ctr = 0u; }
+    if (threadIdx.x < 32) p.counter[threadIdx.x] = 0u;       // ticket, hint, tile-claim counter, compaction cursors
 }
 
 // ---------------------------------------------------------------- host side ----------------------------------
@@ -735,6 +581,7 @@ struct GemvKnobs {
     int merge_prune = 1;       // CTA merge drops keys below the threshold hints
     int early_tma = 1;         // first tiles requested before griddepcontrol.wait
     unsigned long long* trace = nullptr;
+    unsigned long long* fin_trace = nullptr;   // phase stamps of the request path's cluster kernel
 };
 static GemvKnobs read_knobs() {
     GemvKnobs k;
@@ -745,6 +592,7 @@ static GemvKnobs read_knobs() {
     if (const char* e = getenv("REBERT_GEMV_DYN_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) k.dyn_pct = v; }
     if (const char* e = getenv("REBERT_GEMV_MERGE_PRUNE")) k.merge_prune = atoi(e) != 0;
     if (const char* e = getenv("REBERT_GEMV_EARLY_TMA")) k.early_tma = atoi(e) != 0;
+    if (const char* e = getenv("REBERT_FIN_TRACE")) k.fin_trace = (unsigned long long*)strtoull(e, nullptr, 0);
     if (const char* e = getenv("REBERT_GEMV_TRACE")) k.trace = (unsigned long long*)strtoull(e, nullptr, 0);
     return k;
 }
@@ -782,16 +630,15 @@ static GemvLaunch plan_gemv(const RowLayout& L, int64_t n, int kc, bool generic,
     while (stages > 1 && (size_t)stages * stage_stride + fixed > 220 * 1024) --stages;
     g.stages = stages;
     g.smem = (size_t)stages * stage_stride + fixed;
-    size_t merge_bytes = (size_t)kConsumerWarps * kc * sizeof(uint64_t);
+    size_t merge_bytes = (size_t)(kConsumerWarps + 1) * kc * sizeof(uint64_t);   // 8 warp lists + the CTA's merged list
     if (g.smem < merge_bytes) g.smem = merge_bytes;
-    // final merge buffer: a power of two >= max(2 kc, kc + grid), as large as the pipeline memory allows (<= 16384 keys);
-    // behind it the fused tail keeps the winners, their exact scores / rows and the packed local result (k <= kc)
+    // last-CTA merge buffer (rebert_gemv_topk): a power of two >= max(2 kc, kc + grid), as large as the pipeline memory
+    // allows (<= 16384 keys)
     int need = 2 * kc > kc + num_sms() ? 2 * kc : kc + num_sms();
     int cap = 2;
     while (cap < need) cap <<= 1;
-    const size_t tail_extra = (size_t)kc * 24 + (size_t)(2 * kc + 2) * 8;
-    while (cap < 16384 && (size_t)cap * 2 * sizeof(uint64_t) + tail_extra <= g.smem) cap <<= 1;
-    if (g.smem < (size_t)cap * sizeof(uint64_t) + tail_extra) g.smem = (size_t)cap * sizeof(uint64_t) + tail_extra;
+    while (cap < 16384 && (size_t)cap * 2 * sizeof(uint64_t) <= g.smem) cap <<= 1;
+    if (g.smem < (size_t)cap * sizeof(uint64_t)) g.smem = (size_t)cap * sizeof(uint64_t);
     g.merge_cap = cap;
     const int64_t tiles = (n + tr - 1) / tr;
     int grid = num_sms();
@@ -894,19 +741,21 @@ REBERT_API int32_t rebert_candidates_for_k(int32_t k) {
 }
 
 // Workspace layout (kc-INDEPENDENT control words first, so one zero-filled-once workspace serves every kc a thread uses):
-//   [0, 128)      ticket counter, grid-wide hint, tile-claim counter  (zero before a launch; the last CTA leaves them zero)
-//   [128, 1152)   keys each CTA published (int32 x 256)
-//   [1152, ...)   per-CTA candidate lists [num_sms, kc] u64
-constexpr size_t kWsCtl = 128, kWsCounts = 4 * kMaxLists;
+//   [0, 128)       32 control words: ticket counter, grid-wide hint, tile-claim counter, -, 16 compaction cursors  (zero
+//                  before a launch; whoever merges — the last CTA, or the cluster kernel of the request path — zeroes them)
+//   [128, 2176)    tail key of every CTA list (u64 x 256)
+//   [2176, ...)    kept keys of all CTAs [16 regions][region_cap] u64; then the list heads [kc + 256] u64
+constexpr size_t kWsCtl = 128, kWsTails = 8 * 256;
+static inline int region_cap_for(int kc) { return ((num_sms() + kPubRegions - 1) / kPubRegions) * kc; }
 
 REBERT_API size_t rebert_gemv_workspace_bytes(int64_t n, int32_t kc) {
     (void)n;
-    return 128 + kWsCtl + kWsCounts + (size_t)num_sms() * (size_t)kc * sizeof(uint64_t) + 256;
+    return 128 + kWsCtl + kWsTails + ((size_t)kPubRegions * region_cap_for(kc) + (size_t)kc + 256) * sizeof(uint64_t) + 256;
 }
 
 REBERT_API int rebert_workspace_reset(void* workspace, size_t workspace_bytes, rebert_stream stream) {
-    REBERT_REQUIRE(workspace && workspace_bytes >= 128 + kWsCtl + kWsCounts, "workspace_reset: bad arguments");
-    REBERT_CUDA(cudaMemsetAsync(workspace, 0, 128 + kWsCtl + kWsCounts, (cudaStream_t)stream));
+    REBERT_REQUIRE(workspace && workspace_bytes >= 128 + kWsCtl, "workspace_reset: bad arguments");
+    REBERT_CUDA(cudaMemsetAsync(workspace, 0, 128 + kWsCtl, (cudaStream_t)stream));
     return REBERT_OK;
 }
 
@@ -932,7 +781,7 @@ int gemv_launch(const rebert_catalog_t* cat, const float* qn32, const rebert_fil
         set_error("gemv_topk: workspace %zu < %zu", workspace_bytes, rebert_gemv_workspace_bytes(cat->n, kc));
         return REBERT_ERR_WORKSPACE;
     }
-    REBERT_REQUIRE(num_sms() <= kMaxLists, "gemv_topk: device has %d SMs, the final merge indexes at most %d lists", num_sms(), kMaxLists);
+    REBERT_REQUIRE(num_sms() <= 256, "gemv_topk: device has %d SMs, the workspace holds the tails of at most 256 CTA lists", num_sms());
     if (fused) {
         const rebert_catalog_t* xc = fused->exact_cat;
         REBERT_REQUIRE(xc && xc->rows && xc->norm64 && fused->q64 && fused->out_packed, "recommend_device: null argument");
@@ -970,8 +819,12 @@ int gemv_launch(const rebert_catalog_t* cat, const float* qn32, const rebert_fil
     p.counter = (unsigned*)ws;
     p.ghint = p.counter + 1;
     p.tile_ctr = p.counter + 2;
-    p.cta_count = (int*)(ws + kWsCtl);
-    p.cta_lists = (uint64_t*)(ws + kWsCtl + kWsCounts);
+    p.cursors = p.counter + 4;
+    p.region_cap = region_cap_for(kc);
+    p.pub_tails = (uint64_t*)(ws + kWsCtl);
+    p.pub_keys = (uint64_t*)(ws + kWsCtl + kWsTails);
+    p.pub_heads = p.pub_keys + (size_t)kPubRegions * p.region_cap;
+    p.pub_P = (kc + g.grid - 1) / g.grid;
     {
         // share of the tiles claimed dynamically at the end (balances SMs of unequal speed); 0 = all static
         const int dyn_pct = knobs.dyn_pct;
@@ -987,22 +840,26 @@ int gemv_launch(const rebert_catalog_t* cat, const float* qn32, const rebert_fil
     p.early_tma = knobs.early_tma;
     p.cand_keys = cand_keys;
     p.merge_cap = g.merge_cap;
-    if (fused) {
-        p.fused = 1;
-        p.k = fused->k;
-        p.x_rows = fused->exact_cat->rows;
-        p.x_norm64 = fused->exact_cat->norm64;
-        p.x_ld = fused->exact_cat->ld;
-        p.x_dtype = fused->exact_cat->dtype;
-        p.q64 = fused->q64;
-        p.row_base = cat->row_base;
-        p.out_packed = fused->out_packed;
-        p.tag = fused->tag;
-        if (fused->xchg) p.xchg = *fused->xchg;
-    }
+    p.publish_only = fused ? 1 : 0;
 
-    if (cat->dtype == REBERT_I8) return launch_gemv_i8(L, p, g, st);
-    return cat->dtype == REBERT_F32 ? launch_gemv<float>(L, p, g, kc, st) : launch_gemv<__nv_bfloat16>(L, p, g, kc, st);
+    int rc;
+    if (cat->dtype == REBERT_I8) rc = launch_gemv_i8(L, p, g, st);
+    else rc = cat->dtype == REBERT_F32 ? launch_gemv<float>(L, p, g, kc, st) : launch_gemv<__nv_bfloat16>(L, p, g, kc, st);
+    if (rc != REBERT_OK || !fused) return rc;
+    // request path: the cluster kernel that selects the winners, runs the exact pass, ranks, writes the result (and exchanges)
+    Published pub;
+    memset(&pub, 0, sizeof(pub));
+    pub.keys.keys = p.pub_keys;
+    pub.keys.cursors = p.cursors;
+    pub.keys.heads = p.pub_heads;
+    pub.keys.tails = p.pub_tails;
+    pub.keys.lists = g.grid;
+    pub.keys.P = p.pub_P;
+    pub.keys.kc = kc;
+    pub.keys.region_cap = p.region_cap;
+    pub.ctl = p.counter;
+    pub.trace = knobs.fin_trace;
+    return finalize_published_launch(pub, *fused, cat->row_base, st);
 }
 
 }  // namespace rebert
@@ -1026,6 +883,8 @@ REBERT_API int rebert_recommend_device(const rebert_catalog_t* cat, const rebert
     f.k = k;
     f.out_packed = (unsigned long long*)out_packed;
     f.tag = tag;
+    f.done_flag = nullptr;
+    f.done_token = 0;
     Exchange x;
     f.xchg = nullptr;
     if (exchange && exchange->world > 1) {

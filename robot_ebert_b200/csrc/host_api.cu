@@ -1,26 +1,43 @@
 // Host-buffer entry point: one C call = one request of the reference's hot path (lib.py:43-55) end to end.
 // Host pointers in, host pointers out.  The request is packed into the caller's pinned block and read from there by the
 // first kernel (zero-copy: no copy-engine operation at all); a staging kernel normalises the query or builds the
-// profile; ONE launch does score + mask + top-k + fp64 exact pass (+ the NVLink exchange and merge on a row shard) and
-// writes the packed result straight into the pinned block; a stream synchronisation ends the call.  Catalogs that fit one
-// CTA (the reference's production 2 269 x 32) take a single kernel (small.cu).  The proof loop lives here too: int8
+// profile; the streaming kernel does score + mask + top-k and a cluster of 8 CTAs placed behind it by programmatic
+// dependent launch does the fp64 exact pass, the ranking (+ the NVLink exchange and merge on a row shard) and writes the
+// packed result straight into the pinned block; a stream synchronisation ends the call.  The proof loop lives here too: int8
 // shadow first when the caller has one, then the plain fast pass with 4x more candidates until the margin proves the ids.
 // Scratch (pinned host + device) is provided by the caller, so the library still allocates nothing and concurrent
 // callers only need their own scratch + stream (+ their own exchange channel on a row shard).
 #include <stdlib.h>
 
+#include <chrono>
+
 #include "exchange.cuh"
 
 namespace rebert {
 
-// REBERT_SMALL=0 switches the one-kernel route for tiny catalogs off (tests compare it with the general route).  Read once,
-// unless REBERT_GEMV_TUNE is set (the convention of the scoring kernel's knobs): getenv is off the per-request path.
-static bool small_route_enabled() {
-    static const bool tuning = getenv("REBERT_GEMV_TUNE") != nullptr;
-    static const bool cached = [] { const char* e = getenv("REBERT_SMALL"); return !(e && e[0] == '0'); }();
-    if (!tuning) return cached;
-    const char* e = getenv("REBERT_SMALL");
-    return !(e && e[0] == '0');
+// The result block lives in pinned host memory and the exact-pass kernel stores a completion token behind it, so the host
+// can wait by polling that word instead of synchronising the stream (saves the driver's completion path, a few us per
+// request).  REBERT_HOST_POLL=0 switches back to cudaStreamSynchronize.  Read once.
+static bool host_poll_enabled() {
+    static const bool on = [] { const char* e = getenv("REBERT_HOST_POLL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// true when *flag == token arrived; false after ~20 s (a faulted kernel or a dead peer: the caller then synchronises the
+// stream, which reports the error)
+static bool poll_done(const volatile uint32_t* flag, uint32_t token) {
+    for (int spin = 0; spin < 4096; ++spin) {
+        if (*flag == token) return true;
+        __builtin_ia32_pause();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    while (true) {
+        for (int spin = 0; spin < 2048; ++spin) {
+            if (*flag == token) return true;
+            __builtin_ia32_pause();
+        }
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) return false;
+    }
 }
 
 static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -123,6 +140,8 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
     int32_t* excl_dev = (int32_t*)(dv + L.off_dexcl);
     int32_t* err_word = (int32_t*)(h + L.pin_err);
     int32_t* in_flight = err_word + 1;
+    volatile uint32_t* done_flag = (volatile uint32_t*)(err_word + 2);
+    uint32_t* token_ctr = (uint32_t*)(err_word + 3);
     unsigned long long* res = (unsigned long long*)(h + L.pin_out);
     int rc;
     // A previous call on this scratch that never completed (a fault between launch and synchronisation) may have left the
@@ -159,16 +178,6 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
         *in_flight = 0;
     };
 
-    // ---- tiny catalog on one GPU: the whole request is ONE kernel, every row scored exactly
-    if (!sharded && small_route_enabled() && small_catalog(cat, n_exclude)) {
-        rc = small_recommend_launch(cat, q_host, liked_host, w_host, n_liked, excl_host, n_exclude, device_filter, k, res, st);
-        if (rc != REBERT_OK) return rc;
-        REBERT_CUDA(cudaStreamSynchronize(st));
-        inf.kc = 0; inf.attempts = 1; inf.proven = 1; inf.used_shadow = 0;
-        finish();
-        return REBERT_OK;
-    }
-
     // ---- staging kernel: normalised query, or the profile (with the partial-profile exchange on a row shard)
     uint32_t seq = sharded ? exchange->seq : 0;
     Exchange x;
@@ -196,7 +205,7 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
                                                liked_w, liked_w ? (size_t)n_liked * 4 : 0, ((uint64_t)k << 32) | (uint32_t)n_liked)
                                  : 0u;
 
-    // ---- proof loop: each attempt is ONE launch + one synchronisation
+    // ---- proof loop: each attempt is the streaming launch + its cluster kernel + one synchronisation
     const bool try_shadow = proof && proof->shadow && k <= proof->shadow_max_k && proof->shadow_eps > 0.0;
     int cur_kc = kc;
     bool shadow_turn = try_shadow;
@@ -208,6 +217,17 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
         gf.out_packed = res;
         gf.tag = tag;
         gf.xchg = nullptr;
+        gf.done_flag = nullptr;
+        gf.done_token = 0;
+        const bool poll = host_poll_enabled();
+        if (poll) {
+            uint32_t token = *token_ctr + 1u;
+            if (token == 0u) token = 1u;
+            *token_ctr = token;
+            *done_flag = 0u;
+            gf.done_flag = (uint32_t*)done_flag;
+            gf.done_token = token;
+        }
         if (sharded) {
             x.seq = seq ? seq : 1u;
             gf.xchg = &x;
@@ -215,13 +235,14 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
         const int use_kc = shadow_turn ? 256 : cur_kc;
         rc = gemv_launch(shadow_turn ? proof->shadow : cat, qn32, &f, use_kc, dv + L.off_ws, L.ws_bytes, nullptr, &gf, st);
         if (rc != REBERT_OK) return rc;
-        REBERT_CUDA(cudaStreamSynchronize(st));
+        if (!poll || !poll_done(done_flag, gf.done_token)) REBERT_CUDA(cudaStreamSynchronize(st));
         ++inf.attempts;
         ++seq;
         if (*err_word != 0) {
             if (*err_word > 100) set_error("recommend_host: rank %d answered a different request on this channel (request order diverged)", *err_word - 101);
             else set_error("recommend_host: peer %d did not deliver its result to the exchange", *err_word - 1);
             *in_flight = 0;
+            if (info) *info = inf;               // attempts = exchange sequence numbers this call consumed, the failed one included
             return REBERT_ERR_CUDA;
         }
         double margin;

@@ -128,12 +128,15 @@ class CudaShardBackend:
         every rank must call it with the same arguments on the same channel.  Returns (rows, scores, info)."""
         st = self.store
         x = self.exchange_struct(channel, self._seq[channel] + 1)
+        scratch = st._scratch()
+        scratch.last_attempts = 0
         try:
             rows, scores, info = st._recommend_host(query, liked_rows, weights, exclude_rows, k, kc, row_filter, shadow_max_k,
                                                     exchange=x, shadow_eps=shadow_eps)
-        except ValueError:
-            raise                                   # argument errors are raised before any exchange: sequence numbers unchanged
-        self._seq[channel] += info["attempts"]
+        finally:
+            # every attempt that reached the exchange consumed one sequence number on every rank, whether it succeeded or
+            # failed (peer timeout, diverged request order); argument errors are raised before any exchange (0 attempts)
+            self._seq[channel] += scratch.last_attempts
         return rows, scores, info
 
     def exchange_merge(self, local: torch.Tensor, k: int, channel: int = 0) -> torch.Tensor:

@@ -446,52 +446,34 @@ def test_one_workspace_serves_every_candidate_count():
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("n,d", [(2269, 32), (2264, 50), (700, 150), (8000, 16), (85, 1536), (3, 32), (5000, 1)])
-def test_tiny_catalog_kernel_equals_the_general_path_and_the_oracle(dtype, n, d, monkeypatch):
-    """Catalogs that fit one CTA (the reference's production 2269 x 32) are served by ONE kernel that scores every row in
-    fp64.  Its answers must equal the oracle's and, bit for bit, the general path's (REBERT_SMALL=0)."""
-    import os
+@pytest.mark.parametrize("n,d", [(2269, 32), (2264, 50), (700, 150), (8000, 16), (85, 1536), (3, 32)])
+def test_tiny_catalogs_vs_oracle(dtype, n, d):
+    """The reference's production shape (movies-collab: 2269 x 32, create-embeddings.ipynb:1241) and other tiny catalogs:
+    a handful of CTAs, lists that are never full, k up to the row count."""
     store = CatalogStore.synthetic(0, n, d, dtype, scale_rows=True)
     m = _stored_f64(store)
-    users = synth.user_ratings(2, n, 4)
     q = synth.query_f32(1, d)
     excl = np.arange(0, n, 7)
-    monkeypatch.setenv("REBERT_GEMV_TUNE", "1")                  # knobs are re-read on every call
-    got = {}
-    for small in ("1", "0"):
-        monkeypatch.setenv("REBERT_SMALL", small)
-        res = []
-        for k in (1, 10, 50, 240):
-            with np.errstate(all="ignore"):
-                rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True)
-            assert info["proven_exact"] and (info["kc"] == 0) == (small == "1"), info
-            want_rows, want_scores = ora.query_rows(m, q.astype(np.float64), excl, k)
-            np.testing.assert_array_equal(rows, want_rows)
-            np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=1e-300)
-            res.append((rows, scores))
-        for rated, rts in users:
-            liked = rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1]
-            with np.errstate(all="ignore"):
-                rows, scores = store.recommend(liked_rows=liked, exclude_rows=rated, k=10)
-            want_rows, want_scores = ora.recommend_rows(m, liked, rated, 10)
-            np.testing.assert_array_equal(rows, want_rows)
-            np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=1e-300)
-            res.append((rows, scores))
-        got[small] = res
-    if d > 1:                                                    # d = 1: mass ties take the sweep route on the general path
-        for (r1, s1), (r0, s0) in zip(got["1"], got["0"]):
-            np.testing.assert_array_equal(r1, r0)
-            np.testing.assert_array_equal(s1, s0)                # same exact-score function, same bits
+    for k in (1, 10, 50, 240):
+        rows, scores, info = store.recommend(query=q, exclude_rows=excl, k=k, return_info=True)
+        want_rows, want_scores = ora.query_rows(m, q.astype(np.float64), excl, k)
+        assert info["proven_exact"]
+        np.testing.assert_array_equal(rows, want_rows)
+        np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=1e-300)
+    for rated, rts in synth.user_ratings(2, n, 4):
+        liked = rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1]
+        rows, scores = store.recommend(liked_rows=liked, exclude_rows=rated, k=10)
+        want_rows, want_scores = ora.recommend_rows(m, liked, rated, 10)
+        np.testing.assert_array_equal(rows, want_rows)
+        np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=1e-300)
 
 
 def test_unprovable_result_raises_instead_of_returning(monkeypatch):
     """Fail closed: when neither a candidate list nor the exhaustive routes can prove the ids, recommend() raises."""
     n = 3000
     m = synth.catalog_rows_f32(0, 0, n, 1, scale_rows=True)      # d = 1: every cosine is +-1, thousands of exact ties
-    store = CatalogStore.from_host(None, m, "fp32")
-    monkeypatch.setenv("REBERT_GEMV_TUNE", "1")
-    monkeypatch.setenv("REBERT_SMALL", "0")
+    store = CatalogStore.from_host(None, np.repeat(m, 64, axis=1), "fp32")        # 3000 x 64, every cosine exactly +-1
     monkeypatch.setattr(CatalogStore, "_exact_sweep", lambda self, *a, **k: None)
     monkeypatch.setattr(CatalogStore, "_recommend_large_k", lambda self, *a, **k: (_ for _ in ()).throw(RuntimeError("sweep overflow")))
     with pytest.raises(RuntimeError, match="cannot be proven exact"):
-        store.recommend(query=np.ones(1, dtype=np.float32), k=10)
+        store.recommend(query=np.ones(64, dtype=np.float32), k=10)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""A/B probe of the request path (round 2): one-launch fused request vs the two-kernel form, knobs on/off, end-to-end
-latency of query / liked-rows requests, and the tiny-catalog kernel.  Prints JSON lines; writes gpurun_out/fused.json.
+"""A/B probe of the request path (round 2): streaming kernel + cluster exact pass vs the round-1 form (streaming kernel with
+its own last-CTA merge + one-CTA exact pass), knobs on/off, end-to-end latency of query / liked-rows requests, tiny catalogs.  Prints JSON lines; writes gpurun_out/fused.json.
 
     python tools/probe_fused.py [max_rows]
 """
@@ -87,21 +87,15 @@ for n, dtype, K in [(1_250_000, "bf16", 10), (1_250_000, "bf16", 100), (1_000_00
     del store
     torch.cuda.empty_cache()
 
-# ---------------------------------------------------------------- tiny catalogs: one kernel vs the general route
+# ---------------------------------------------------------------- tiny catalogs (the reference's production shapes): pure latency
 for n, d, dtype in [(2269, 32, "fp32"), (2264, 1536, "fp32"), (2264, 1536, "bf16"), (10_000, 1536, "fp32")]:
     store = CatalogStore.synthetic(0, n, d, dtype, device=dev)
     q = synth.query_f32(1, d)
     (rated, rts), = synth.user_ratings(2, n, 1)
     liked = rated[rts >= 3.5]
     res = {"rows": n, "dim": d, "dtype": dtype, "n_liked": int(len(liked)), "n_rated": int(len(rated))}
-    for small in ("1", "0"):
-        os.environ["REBERT_SMALL"] = small
-        r1 = store.recommend(query=q, exclude_rows=rated, k=10)
-        r2, _, info = store.recommend(liked_rows=liked, exclude_rows=rated, k=10, return_info=True)
-        res[f"small{small}_route_kc"] = info["kc"]
-        res[f"small{small}_e2e_query_us"] = round(wall_time(lambda: store.recommend(query=q, exclude_rows=rated, k=10), 500, 20), 1)
-        res[f"small{small}_e2e_profile_us"] = round(wall_time(lambda: store.recommend(liked_rows=liked, exclude_rows=rated, k=10), 500, 20), 1)
-    os.environ.pop("REBERT_SMALL")
+    res["e2e_query_us"] = round(wall_time(lambda: store.recommend(query=q, exclude_rows=rated, k=10), 500, 20), 1)
+    res["e2e_profile_us"] = round(wall_time(lambda: store.recommend(liked_rows=liked, exclude_rows=rated, k=10), 500, 20), 1)
     emit(res)
 
 os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
