@@ -52,11 +52,14 @@ class _Scratch:
         self.wsum = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def ensure_host(self, n_liked: int, n_excl: int, k: int):
-        """Pinned + device scratch of rebert_recommend_host, grown geometrically."""
+        """Pinned + device scratch of rebert_recommend_host.  Sized once for any k of the single-request path (256) and lists
+        of 4096 entries; longer lists grow it geometrically.  (Growing allocates, and CUDA allocations may synchronise the
+        device — harmless on one GPU, but on a row shard a kernel waiting for a peer may be running: the sharding layer
+        therefore pre-allocates its channels' scratch while no request is in flight.)"""
         if n_liked > self.nl_cap or n_excl > self.ne_cap or k > self.hk_cap:
-            self.nl_cap = max(self.nl_cap, 1024, 1 << max(n_liked - 1, 0).bit_length())
-            self.ne_cap = max(self.ne_cap, 1024, 1 << max(n_excl - 1, 0).bit_length())
-            self.hk_cap = max(self.hk_cap, 16, 1 << (k - 1).bit_length())
+            self.nl_cap = max(self.nl_cap, 4096, 1 << max(n_liked - 1, 0).bit_length())
+            self.ne_cap = max(self.ne_cap, 4096, 1 << max(n_excl - 1, 0).bit_length())
+            self.hk_cap = max(self.hk_cap, 256, 1 << (k - 1).bit_length())
             self.hpin, self.hdev = self._host_scratch(self.nl_cap, self.ne_cap, self.hk_cap)
             self.h_rows = np.empty(self.hk_cap, dtype=np.int64)
             self.h_scores = np.empty(self.hk_cap, dtype=np.float64)
@@ -456,11 +459,12 @@ class CatalogStore:
         return sub.cpu().numpy().astype(np.int64), exact[0].cpu().numpy()
 
     def _recommend_host(self, query, liked_rows, weights, exclude_rows, k, kc, row_filter, shadow_max_k=0, exchange=None,
-                        shadow_eps=None):
+                        shadow_eps=None, scratch=None):
         """One rebert_recommend_host call: host buffers in, host buffers out; staging, kernels, proof loop and stream sync
-        inside.  exchange: a nat.Exchange for one rank of a row-sharded catalog (sharding.py).  Returns (rows, scores, info)."""
+        inside.  exchange: a nat.Exchange for one rank of a row-sharded catalog (sharding.py); scratch: an explicit _Scratch
+        instead of the calling thread's own (the sharding layer pre-allocates one per exchange channel).
+        Returns (rows, scores, info)."""
         lib = nat.load()
-        s = self._scratch()
         d = self.d
         q = lk = w = ex = None
         nl = ne = 0
@@ -478,7 +482,6 @@ class CatalogStore:
         if exclude_rows is not None and len(exclude_rows):
             ex = sorted_unique_i32(exclude_rows)
             ne = int(ex.shape[0])
-        s.ensure_host(nl, ne, k)
         f = self._filter_struct(row_filter)
         proof = nat.Proof()
         proof.fast_eps, proof.widen = self.fast_eps, 1
@@ -490,7 +493,9 @@ class CatalogStore:
         # bytes the kernels fetch from / write to the pinned block over PCIe (zero-copy: no copy-engine operation)
         self.last_h2d_bytes = (4 * d if lk is None else 4 * nl * (2 if w is not None else 1)) + 4 * ne
         self.last_d2h_bytes = 8 * (2 * k + 2)
-        with _on_device(self.device):
+        with _on_device(self.device):                 # a serving thread's current device is 0 until it says otherwise
+            s = scratch if scratch is not None else self._scratch()
+            s.ensure_host(nl, ne, k)
             rc = lib.rebert_recommend_host(
                 C.byref(self._c), None if q is None else q.ctypes.data, None if lk is None else lk.ctypes.data,
                 None if w is None else w.ctypes.data, nl, None if ex is None else ex.ctypes.data, ne,

@@ -297,13 +297,15 @@ __global__ void __launch_bounds__(256) stage_profile_kernel(const T* __restrict_
                                                             const int32_t* __restrict__ excl_host, int n_excl, int32_t* __restrict__ excl_dev,
                                                             double* __restrict__ sum64, double* __restrict__ wsum,
                                                             float* __restrict__ qn32, double* __restrict__ qn64, Exchange x) {
-    pdl_trigger();
+    // a kernel that waits for a peer lets its dependents in only after that wait (see finalize_published_kernel)
+    if (x.world <= 1) pdl_trigger();
     pdl_wait();
     copy_list_zero_copy(excl_host, n_excl, excl_dev);
     profile_accumulate_cta<T, true, 16>(rows, norm64, n, row_base, ld, liked_host, w_host, n_liked, sum64, wsum);
     __syncthreads();
     if (x.world > 1) {
         exchange_profile(x, ld, sum64, sum64);
+        pdl_trigger();
         __syncthreads();
     }
     const double ws = wsum[0];

@@ -27,7 +27,8 @@ struct Exchange {
     int words_cap, prof_cap;               // 2 * k_max + 2, prof_len + 1
     unsigned seq;                          // call number on this channel (same on every rank), never 0
     long long timeout_cycles;
-    int* err;                              // int32, device or device-addressable pinned: 1 + rank = no delivery, 101 + rank = tag mismatch
+    int* err;                              // int32, device or device-addressable pinned: 1 + rank = result not delivered, 51 + rank = partial
+                                           // profile not delivered, 101 + rank = tag mismatch
 };
 
 __host__ __device__ __forceinline__ size_t xchg_channel_words(int world, int words_cap, int prof_cap) {
@@ -46,7 +47,7 @@ __device__ __forceinline__ size_t xchg_pflag_off(const Exchange& x, int parity, 
 
 // publish `seq` in every peer's flag slot for my rank, then wait until every rank's flag in MY buffer shows `seq`.
 // Called by all threads of the CTA after the payload stores (and a __threadfence_system + __syncthreads by the caller).
-__device__ __forceinline__ void xchg_publish_and_wait(const Exchange& x, size_t my_flag_off_in_peer, size_t flag0_off_in_mine) {
+__device__ __forceinline__ void xchg_publish_and_wait(const Exchange& x, size_t my_flag_off_in_peer, size_t flag0_off_in_mine, int err_base = 1) {
     if ((int)threadIdx.x < x.world) {
         unsigned long long* f = x.peer[threadIdx.x] + my_flag_off_in_peer;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)x.seq) : "memory");
@@ -56,7 +57,7 @@ __device__ __forceinline__ void xchg_publish_and_wait(const Exchange& x, size_t 
         while (true) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
             if (v == (unsigned long long)x.seq) break;
-            if (clock64() - t0 > x.timeout_cycles) { *(volatile int*)x.err = 1 + threadIdx.x; break; }   // plain store: err may live in pinned host memory
+            if (clock64() - t0 > x.timeout_cycles) { *(volatile int*)x.err = err_base + threadIdx.x; break; }   // plain store: err may live in pinned host memory
             __nanosleep(64);
         }
     }
@@ -84,7 +85,8 @@ __device__ __forceinline__ void exchange_results(const Exchange& x, int k, const
         total += min((int)(unsigned)L[2 * k], k);
         margin = fmin(margin, __longlong_as_double((long long)L[2 * k + 1]));
         // every rank must be serving the SAME request on this channel: a differing tag means the callers' request order diverged
-        if ((unsigned)(L[2 * k] >> 32) != my_tag && threadIdx.x == 0) *(volatile int*)x.err = 101 + l;
+        // (a peer that never delivered has already been reported and leaves a stale block here: do not relabel that)
+        if ((unsigned)(L[2 * k] >> 32) != my_tag && threadIdx.x == 0 && *(volatile int*)x.err == 0) *(volatile int*)x.err = 101 + l;
     }
     const int nout = total < k ? total : k;
     for (int i = threadIdx.x; i < x.world * k; i += blockDim.x) {
@@ -130,7 +132,7 @@ __device__ __forceinline__ void exchange_profile(const Exchange& x, int len, con
     }
     __threadfence_system();
     __syncthreads();
-    xchg_publish_and_wait(x, xchg_pflag_off(x, parity, x.rank), xchg_pflag_off(x, parity, 0));
+    xchg_publish_and_wait(x, xchg_pflag_off(x, parity, x.rank), xchg_pflag_off(x, parity, 0), 51);
     const unsigned long long* g = x.peer[x.rank] + xchg_prof_off(x, parity, 0);
     for (int c = threadIdx.x; c < len; c += blockDim.x) {
         double s = 0.0;

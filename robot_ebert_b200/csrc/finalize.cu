@@ -4,6 +4,7 @@
 //                          (score desc, row asc) order of lib.py:55,63, best k out.
 //   rebert_merge_topk    : the same order across per-shard result lists (row-sharded catalogs).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "exchange.cuh"
 
@@ -118,7 +119,13 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     const int crank = (int)cluster.block_rank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kFinalClusterThreads / 32;
     FIN_TRACE(0);
-    pdl_trigger();
+    // Programmatic dependent launch lets the NEXT kernel of the stream place its CTAs early.  A kernel that will wait for
+    // a PEER must not do that before the wait is over: the next request's streaming CTAs would sit resident on every SM,
+    // blocked behind this kernel, while the peer — in the mirrored state on another channel — needs exactly those SMs to
+    // produce what this kernel waits for (deadlock across ranks with concurrent channels).  So on a row shard the trigger
+    // comes after the exchange.
+    const bool exchange = p.xchg.world > 1;
+    if (!exchange) pdl_trigger();
     if (threadIdx.x == 0) { s_tmp[0] = 0; s_tmp[1] = 0; }
     cluster.sync();                                  // every CTA of the cluster is running: its shared memory may be addressed.
                                                      // Done HERE, while the stream is still running, it costs nothing.
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
         const int i = threadIdx.x + j * kFinalClusterThreads;
         qv[j] = i < p.x_ld ? __ldg(p.q64 + i) : 0.0;
     }
-    select_winners<16>(p.pub.keys, p.cap, buf, fk, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
+    select_winners<24>(p.pub.keys, p.cap, buf, fk, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
     {
         const int chunks = p.x_ld / epc;
 #pragma unroll
@@ -181,7 +188,6 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, me, o); me = v > me ? v : me; }
     const uint64_t last = fk[kc - 1];
-    const bool exchange = p.xchg.world > 1;
     unsigned long long* blk = exchange ? s_block : p.out_packed;
     rank_candidates<false>(s_score, s_row, kc, k, last != 0, last ? (double)key_score(last) : 0.0, __longlong_as_double((long long)me),
                            (int64_t*)blk, (double*)(blk + k), (int32_t*)(blk + 2 * k), (double*)(blk + 2 * k + 1), s_tmp, &s_kth);
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     if (exchange) {
         __syncthreads();
         exchange_results(p.xchg, k, s_block, p.out_packed);
+        pdl_trigger();
     }
     if (threadIdx.x < 32) p.pub.ctl[threadIdx.x] = 0u;       // ticket, hint, tile-claim counter, compaction cursors
     if (p.done_flag) {
@@ -292,17 +299,17 @@ __global__ void merge_topk_kernel(const int64_t* __restrict__ rows, const double
 // own tail (gemv_topk.cu); these kernels serve callers that hold a packed local result / a partial profile already.
 __global__ void __launch_bounds__(256) exchange_merge_kernel(Exchange x, int k, const unsigned long long* __restrict__ local,
                                                              unsigned long long* __restrict__ out) {
-    pdl_trigger();
     pdl_wait();                                      // `local` is written by the kernel launched just before
     exchange_results(x, k, local, out);
+    pdl_trigger();                                   // only now: see finalize_published_kernel
 }
 
 // sum64 [ld] partial -> exchanged, summed in rank order, divided by wsum: p32 / p64 (profile_finalize fused in).
 __global__ void __launch_bounds__(256) profile_exchange_kernel(Exchange x, int ld, double* __restrict__ sum64, const double* __restrict__ wsum,
                                                                float* __restrict__ p32, double* __restrict__ p64) {
-    pdl_trigger();
     pdl_wait();
     exchange_profile(x, ld, sum64, sum64);           // every element is read (pushed) before the barrier inside, written after it
+    pdl_trigger();                                   // only now: see finalize_published_kernel
     __syncthreads();
     const double ws = wsum[0];
     for (int c = threadIdx.x; c < ld; c += blockDim.x) {
@@ -325,8 +332,13 @@ int make_exchange(const rebert_exchange_t* ex, int32_t* err_flag, Exchange* out)
     out->prof_cap = ex->prof_len + 1;
     out->seq = ex->seq;
     // ~10 s of SM clocks at 2 GHz: only a dead peer gets here.  (A constant: querying the clock rate is a slow driver
-    // call and this function sits on the per-request path.)
-    out->timeout_cycles = 20000000000ll;
+    // call and this function sits on the per-request path.)  REBERT_EXCHANGE_TIMEOUT_MS overrides it (read once; tests).
+    static const long long timeout_cycles = [] {
+        const char* e = getenv("REBERT_EXCHANGE_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 0;
+        return ms > 0 ? ms * 2000000ll : 20000000000ll;
+    }();
+    out->timeout_cycles = timeout_cycles;
     out->err = err_flag;
     const size_t ch_words = xchg_channel_words(ex->world, out->words_cap, out->prof_cap);
     for (int i = 0; i < ex->world; ++i)

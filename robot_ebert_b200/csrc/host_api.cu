@@ -240,6 +240,7 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
         ++seq;
         if (*err_word != 0) {
             if (*err_word > 100) set_error("recommend_host: rank %d answered a different request on this channel (request order diverged)", *err_word - 101);
+            else if (*err_word > 50) set_error("recommend_host: peer %d did not deliver its partial profile to the exchange", *err_word - 51);
             else set_error("recommend_host: peer %d did not deliver its result to the exchange", *err_word - 1);
             *in_flight = 0;
             if (info) *info = inf;               // attempts = exchange sequence numbers this call consumed, the failed one included

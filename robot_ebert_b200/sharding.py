@@ -103,6 +103,17 @@ class CudaShardBackend:
         if self.exchange == "p2p":
             self.channels = channels
             self._seq = [0] * channels
+            # One request scratch (pinned + device) per channel, allocated NOW, while no request is in flight: a CUDA
+            # allocation may synchronise the device, and a device synchronisation while another channel's kernel is waiting
+            # for a peer — whose own progress may hang on the mirrored allocation — stalls both ranks until the timeout.
+            from .catalog import _Scratch
+            self._chan_scratch = []
+            with torch.cuda.device(self.device):
+                for _ in range(channels):
+                    sc = _Scratch(self.store)
+                    sc.ensure_host(1, 1, 1)
+                    self._chan_scratch.append(sc)
+                torch.cuda.synchronize(self.device)
         log.info("rank %d/%d: row-shard exchange path = %s%s", rank, world, self.exchange,
                  f" ({channels} channels)" if self.exchange == "p2p" else " (all-gather + merge kernel; requests are serialised)")
         return self.exchange == "p2p"
@@ -128,11 +139,11 @@ class CudaShardBackend:
         every rank must call it with the same arguments on the same channel.  Returns (rows, scores, info)."""
         st = self.store
         x = self.exchange_struct(channel, self._seq[channel] + 1)
-        scratch = st._scratch()
+        scratch = self._chan_scratch[channel]                      # pre-allocated; the caller holds the channel's lock
         scratch.last_attempts = 0
         try:
             rows, scores, info = st._recommend_host(query, liked_rows, weights, exclude_rows, k, kc, row_filter, shadow_max_k,
-                                                    exchange=x, shadow_eps=shadow_eps)
+                                                    exchange=x, shadow_eps=shadow_eps, scratch=scratch)
         finally:
             # every attempt that reached the exchange consumed one sequence number on every rank, whether it succeeded or
             # failed (peer timeout, diverged request order); argument errors are raised before any exchange (0 attempts)
@@ -249,7 +260,9 @@ class ShardedCatalog:
         store = CatalogStore.synthetic(seed, n, d, dtype, scale_rows=scale_rows, device=device, row0=row0)
         backend = CudaShardBackend(store)
         backend.setup_p2p(group)
-        return cls(backend, n_total, group)
+        sc = cls(backend, n_total, group)
+        sc.warm_up()
+        return sc
 
     @classmethod
     def from_host(cls, ids: Optional[Sequence[str]], matrix: np.ndarray, dtype: str = "fp32", device=None, group=None,
@@ -276,7 +289,32 @@ class ShardedCatalog:
         store = CatalogStore.from_host(None, matrix[row0:row0 + cnt], dtype, device=device, row_base=row0)
         backend = CudaShardBackend(store)
         backend.setup_p2p(group)
-        return cls(backend, n, group, ids)
+        sc = cls(backend, n, group, ids)
+        sc.warm_up()
+        return sc
+
+    def warm_up(self) -> None:
+        """Run one request through every kernel variant the request path can take (candidate lists of 32 / 64 / 128 / 256
+        keys, query / liked rows / weighted liked rows) on every channel's scratch.  Collective; called by the constructors,
+        BEFORE any serving thread exists.  Why: the first launch of a kernel loads its module (CUDA lazy loading) and the
+        first use of a scratch allocates — both may synchronise the device, and a device synchronisation while another
+        channel's kernel is waiting for a peer (whose progress may hang on the mirrored event) stalls both ranks until the
+        exchange times out.  After the warm-up the request path makes no such call."""
+        if getattr(self.backend, "exchange", "nccl") != "p2p":
+            return
+        st = self.backend.store
+        n = self.plan.n_total
+        q = np.ones(st.d, dtype=np.float32)
+        liked = np.arange(min(3, n), dtype=np.int64)
+        for k in (10, 40, 100, 200):
+            kk = max(1, min(k, n))
+            self.recommend(query=q, k=kk)
+            self.recommend(liked_rows=liked, exclude_rows=liked, k=kk)
+        self.recommend(liked_rows=liked, weights=np.ones(len(liked), dtype=np.float32), k=max(1, min(10, n)))
+        for ch in range(1, self.backend.channels):          # every channel's flags and scratch have been through one request
+            self.recommend(query=q, k=max(1, min(10, n)), channel=ch)
+        torch.cuda.synchronize(self.backend.device)
+        dist.barrier(group=self.group)
 
     # ------------------------------------------------------------------ id map (global rows) ----
     def row_of(self, tmdb_id: str) -> Optional[int]:
@@ -310,6 +348,10 @@ class ShardedCatalog:
         t = torch.tensor([eps], dtype=torch.float64, device=self.backend.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         self.q8_eps = float(t.item())
+        if getattr(self.backend, "exchange", "nccl") == "p2p":          # warm the shadow's kernel variants up too (see warm_up)
+            self.recommend(query=np.ones(self.backend.store.d, dtype=np.float32), k=max(1, min(10, self.plan.n_total)), prefilter=True)
+            torch.cuda.synchronize(self.backend.device)
+            dist.barrier(group=self.group)
         return self.q8_eps
 
     def _gather_buf(self, k: int, like: torch.Tensor) -> torch.Tensor:

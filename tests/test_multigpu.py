@@ -275,6 +275,7 @@ def _requests(n, d, count):
 
 def _threads_worker(rank, world, port, n, d, nthreads, per_thread, out_q):
     import threading
+    os.environ["REBERT_EXCHANGE_TIMEOUT_MS"] = "3000"        # fail fast if a peer never delivers
     dist = _init(rank, world, port)
     from robot_ebert_b200.sharding import ShardedCatalog
     try:
@@ -285,6 +286,7 @@ def _threads_worker(rank, world, port, n, d, nthreads, per_thread, out_q):
 
         def serve(t):                                   # thread t of every rank serves the same requests on channel t
             try:
+                torch.cuda.set_device(rank)             # a new thread starts on device 0
                 with torch.cuda.stream(torch.cuda.Stream()):
                     for j in range(per_thread):
                         i = t * per_thread + j
@@ -298,8 +300,7 @@ def _threads_worker(rank, world, port, n, d, nthreads, per_thread, out_q):
             x.start()
         for x in th:
             x.join()
-        assert not errors, errors
-        out_q.put((rank, results))
+        out_q.put((rank, results, errors))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -314,9 +315,10 @@ def test_sharded_serving_threads_on_their_own_channels():
     from robot_ebert_b200 import CatalogStore
     n, d, nthreads, per_thread = 120_001, 256, 8, 12
     results = _spawn("_threads_worker", world, n, d, nthreads, per_thread)
+    assert not any(errs for _, _, errs in results), [(rank, errs) for rank, _, errs in results]
     store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True, device="cuda:0")
     want = [store.recommend(**r) for r in _requests(n, d, nthreads * per_thread)]
-    for rank, got in results:
+    for rank, got, _ in results:
         for i, ((rows, scores), (wr, ws)) in enumerate(zip(got, want)):
             assert rows == wr.tolist(), (rank, i)
             np.testing.assert_allclose(scores, ws, rtol=1e-12)
