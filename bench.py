@@ -313,7 +313,7 @@ def time_wall(fn, steps, warmup, barrier, world, dist_mod, dev):
     return s
 
 
-def batched_leg(store, sharded, world, rows_total, dev, barrier, B=4096, KB=100, steps=3, warmup=2):
+def batched_leg(store, sharded, world, rows_total, dev, barrier, B=4096, KB=100, steps=3, warmup=2, int8=False):
     """BASELINE configs 3/4: B users x catalog, top-KB, on the tcgen05 path; sharded when N>1.  One step = the whole batch
     INCLUDING the re-run of every query the batched pass could not prove (sync + single-query route inside the timed region)."""
     import ctypes as C
@@ -333,8 +333,11 @@ def batched_leg(store, sharded, world, rows_total, dev, barrier, B=4096, KB=100,
         ep[u + 1] = ep[u] + len(c)
     ec = np.concatenate(ec).astype(np.int32)
     reruns = [0]
+    if int8 and not store.batch_shadow_ok:
+        raise RuntimeError("int8 operands need enable_prefilter() and rows of whole 128-byte k-blocks")
     if sharded is not None:
-        ctx = sharded.batch_context(qbf, qn64, KB, ep, ec)
+        ctx = sharded.batch_context(qbf, qn64, KB, ep, ec, qn32=qn32 if int8 else None)
+        assert (ctx["shadow"] is not None) == int8
         plan = ctx["plan"]
 
         def step():
@@ -343,7 +346,8 @@ def batched_leg(store, sharded, world, rows_total, dev, barrier, B=4096, KB=100,
             reruns[0] = int((status != 0).sum())
             return rows, scores
     else:
-        plan = store.gemm_plan(B, KB)
+        plan = store.gemm_plan(B, KB, shadow=int8)
+        shadow = store.quantize_queries(qn32) if int8 else None
         ept, ect = torch.from_numpy(ep).to(dev), torch.from_numpy(ec).to(dev)
         ws = torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan)), dtype=torch.uint8, device=dev)
         o_rows = torch.empty((B, KB), dtype=torch.int64, device=dev)
@@ -353,7 +357,7 @@ def batched_leg(store, sharded, world, rows_total, dev, barrier, B=4096, KB=100,
         scratch = store._scratch()
 
         def step():
-            store.enqueue_batch(plan, qbf, qn64, ept, ect, ws, o_rows, o_scores, o_count, o_status)
+            store.enqueue_batch(plan, qbf, qn64, ept, ect, ws, o_rows, o_scores, o_count, o_status, shadow=shadow)
             status = o_status.cpu().numpy()                                  # the sync a caller needs to know what to re-run
             redo = np.nonzero(status)[0]
             reruns[0] = len(redo)
@@ -376,7 +380,9 @@ def batched_leg(store, sharded, world, rows_total, dev, barrier, B=4096, KB=100,
     flops = 2.0 * B * rows_total * DIM
     tf = flops / (ms * 1e-3) / 1e12
     return {"workload": f"{B} users x {rows_total} x {DIM} bf16, top-{KB}, {N_EXCL}-row exclusions per user",
+            "operands": "int8 shadow (tcgen05 kind::i8), exact fp64 pass over the bf16 rows" if int8 else "bf16 (tcgen05 kind::f16)",
             "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "tflops": tf,
+            "tflops_note": "2*B*N*D / time: the work of the bf16 GEMM the path replaces, whatever the operand type",
             "frac_of_measured_bf16_peak": tf / (pk["bf16"] * world),
             "frac_of_sustained_bf16_peak": (tf / (pk["bf16_sustained"] * world)) if pk["bf16_sustained"] else None,
             "peak_note": "burst = cuBLAS best of 10; sustained = cuBLAS back to back for seconds (the regime a ~100 ms batch runs in)",
@@ -384,7 +390,10 @@ def batched_leg(store, sharded, world, rows_total, dev, barrier, B=4096, KB=100,
             "includes": "threshold sample + fused GEMM filter + per-query select + fp64 exact pass + status read-back + re-run of unproven queries"
                         + (" + all-gather + merge" if world > 1 else ""),
             "queries_rerun_on_single_query_path": reruns[0], "reruns_inside_timed_region": True,
-            "result_digest": digest(rows, scores),
+            "ids_digest": digest(rows), "result_digest": digest(rows, scores), "_rows": rows, "_scores": scores,
+            "digest_note": "ids_digest (sha1 over the [B, k] row ids) is the same at every N and for either operand type; score bits may "
+                           "differ in the last ulp for queries that were re-run (the single-query exact pass divides element-wise "
+                           "first, the batched one once per row)",
             "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
 
 
@@ -494,6 +503,13 @@ def run_b200(args):
 
     configs = {}
 
+    def compare_batched(a, b_, what):
+        """bf16 vs int8 operands: the ids must be identical, the scores equal to the last ulp or so (see digest_note)."""
+        if "_rows" in a and "_rows" in b_:
+            assert np.array_equal(a["_rows"], b_["_rows"]), f"{what}: int8 operands changed the ids"
+            assert np.allclose(a["_scores"], b_["_scores"], rtol=1e-12, atol=0, equal_nan=True), f"{what}: int8 operands changed the scores"
+            b_["same_ids_as_bf16_operands"] = True
+
     def guarded(name, fn):
         try:
             configs[name] = fn()
@@ -544,15 +560,22 @@ def run_b200(args):
         return out
     if not args.no_prefilter:
         guarded("prefilter_int8", prefilter_leg)
-        store._c8 = None                                 # free the shadow before the batched legs
-        store._q8_rows = store._q8_factor = None
-        if sharded is not None:
-            sharded.q8_eps = None
-        torch.cuda.empty_cache()
 
-    # ---- C4 batched: 4096 users x the 10M catalog, top-100 (tcgen05), sharded when N > 1
+    # ---- C4 batched: 4096 users x the 10M catalog, top-100 (tcgen05), sharded when N > 1; bf16 operands, then int8
     if not args.no_batched:
         guarded("C4_batched_10M", lambda: batched_leg(store, sharded, world, rows, dev, barrier))
+        if store.batch_shadow_ok:
+            guarded("C4_batched_10M_int8", lambda: batched_leg(store, sharded, world, rows, dev, barrier, int8=True))
+            compare_batched(configs.get("C4_batched_10M", {}), configs.get("C4_batched_10M_int8", {}), "C4")
+        for name in ("C4_batched_10M", "C4_batched_10M_int8"):
+            want = expected_digest(f"batched-ids:{rows}x{DIM}:B4096:k100")
+            if want is not None and isinstance(configs.get(name), dict) and "ids_digest" in configs[name]:
+                assert configs[name]["ids_digest"] == want, f"{name}: ids digest {configs[name]['ids_digest']} != committed {want}"
+    store._c8 = None                                     # free the shadow
+    store._q8_rows = store._q8_factor = None
+    if sharded is not None:
+        sharded.q8_eps = None
+    torch.cuda.empty_cache()
 
     # ---- C5 (N > 1): ragged-CSR profile build + genre/year-filtered top-50 over the sharded catalog
     def c5_leg():
@@ -636,6 +659,12 @@ def run_b200(args):
             configs["C2_1M_single_query"]["workload"] = f"1M x {DIM}, single-query top-{K} + {N_EXCL}-row exclusion, one launch per query"
         if st_1m is not None and not args.no_batched:
             guarded("C3_batched_4096x1M_top100", lambda: batched_leg(st_1m, None, 1, 1_000_000, dev, barrier, steps=5))
+            if not args.no_prefilter:
+                def c3_int8():
+                    st_1m.enable_prefilter()
+                    return batched_leg(st_1m, None, 1, 1_000_000, dev, barrier, steps=5, int8=True)
+                guarded("C3_batched_4096x1M_top100_int8", c3_int8)
+                compare_batched(configs.get("C3_batched_4096x1M_top100", {}), configs.get("C3_batched_4096x1M_top100_int8", {}), "C3")
         del st_1m
         torch.cuda.empty_cache()
         guarded("C1_cpu_sized_catalog", lambda: config_c1(dev))
@@ -654,6 +683,10 @@ def run_b200(args):
                     "route": "one CTA scores every row in fp64 (exact by construction)" if inf["kc"] == 0 else "general"}
         guarded("production_shape_2269x32", prod_leg)
 
+    for v in configs.values():                               # arrays kept only for the comparisons above
+        if isinstance(v, dict):
+            v.pop("_rows", None)
+            v.pop("_scores", None)
     if rank == 0:
         shard_rows = (rows * 1) // world if world > 1 else rows
         alg_bytes = shard_rows * DIM * 2                                  # catalog bytes one launch must read

@@ -296,6 +296,32 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
                      size_t workspace_bytes,
                      int64_t* out_rows, double* out_scores, int32_t* out_count, int32_t* out_status,
                      rebert_stream stream);
+/* ---- the same batched path with INT8 OPERANDS: the filter GEMM streams the prefilter shadow (rebert_catalog_quantize_i8)
+ * with tcgen05 kind::i8 — half the bytes and twice the tensor rate of bf16 — and int8 queries; exact integer accumulation.
+ * Only the FILTER is approximate: candidates are re-scored in fp64 from the catalog of record exactly as in
+ * rebert_gemm_topk, and a query whose proof margin does not clear its bound gets out_status != 0 and is re-run by the
+ * caller on the single-query path, whose bound is rigorous.
+ *   rebert_gemm_plan_i8       as rebert_gemm_plan, with the wider candidate list the larger filter error needs
+ *   rebert_query_quantize_i8  qn32 [b, ld] unit queries / profiles -> q8 [b, ld8] int8, qscale [b] (dequantisation step),
+ *                             qeps [b] = the margin a result of that query must clear: 6 sigma of the score error under the
+ *                             random-direction model, sigma = sqrt(row_err^2 + rho_q^2) / sqrt(d) with row_err the shadow's
+ *                             measured worst relative row error (*out_max_err of rebert_catalog_quantize_i8) and rho_q
+ *                             the query's own, measured here.  The batched proof is statistical (as on the bf16 path, whose
+ *                             query rounding has no useful worst-case bound either); the margin is additionally reduced by
+ *                             2 x the largest |filter score - exact score| observed on the candidates.
+ *   rebert_gemm_topk_i8       cat = catalog of record (exact pass), shadow = its int8 shadow (operands of the GEMM);
+ *                             needs ld8 % 128 == 0. */
+REBERT_API int rebert_gemm_plan_i8(int64_t n, int32_t b, int32_t k, rebert_gemm_plan_t* plan);
+REBERT_API int rebert_query_quantize_i8(const float* qn32, int32_t b, int32_t d, int32_t ld, int32_t ld8, double row_err, void* q8,
+                                        float* qscale, double* qeps, rebert_stream stream);
+REBERT_API int rebert_gemm_topk_i8(const rebert_catalog_t* cat, const rebert_catalog_t* shadow, const void* q8, const float* qscale,
+                                   const double* qeps, const double* q64, const int64_t* excl_row_ptr, const int32_t* excl_col,
+                                   const rebert_filter_t* row_filter, const rebert_gemm_plan_t* plan, void* workspace,
+                                   size_t workspace_bytes, int64_t* out_rows, double* out_scores, int32_t* out_count,
+                                   int32_t* out_status, rebert_stream stream);
+/* out[u, j] = (sum_c q8[u, c] * shadow[j, c]) * factor[j] * qscale[u] for rows [row0, row0 + nrows), fp32 [b, nrows]. */
+REBERT_API int rebert_gemm_scores_i8(const rebert_catalog_t* shadow, const void* q8, const float* qscale, int32_t b, int64_t row0,
+                                     int64_t nrows, float* out, rebert_stream stream);
 /* Building block, also used by tests: out[u, j] = <q[u], row j> * inv_norm[j] for rows [row0, row0 + nrows) on the
  * tensor cores (bf16 catalog only), fp32 [b, nrows]. */
 REBERT_API int rebert_gemm_scores(const rebert_catalog_t* cat, const void* qbf16, int32_t b, int64_t row0, int64_t nrows,

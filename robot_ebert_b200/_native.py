@@ -90,6 +90,11 @@ _SIGS = {
     "rebert_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(Catalog), C.POINTER(GemmPlan)]),
     "rebert_gemm_topk": (C.c_int, [C.POINTER(Catalog), _P, _P, _P, _P, C.POINTER(Filter), C.POINTER(GemmPlan), _P, C.c_size_t, _P, _P, _P, _P, _P]),
     "rebert_gemm_scores": (C.c_int, [C.POINTER(Catalog), _P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
+    "rebert_gemm_plan_i8": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(GemmPlan)]),
+    "rebert_query_quantize_i8": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P]),
+    "rebert_gemm_topk_i8": (C.c_int, [C.POINTER(Catalog), C.POINTER(Catalog), _P, _P, _P, _P, _P, _P, C.POINTER(Filter), C.POINTER(GemmPlan),
+                                      _P, C.c_size_t, _P, _P, _P, _P, _P]),
+    "rebert_gemm_scores_i8": (C.c_int, [C.POINTER(Catalog), _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "rebert_synth_rows": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
 }
 

@@ -672,28 +672,58 @@ class CatalogStore:
                                              torch.cuda.current_stream().cuda_stream))
         return out
 
-    def gemm_plan(self, b: int, k: int) -> "nat.GemmPlan":
+    def gemm_plan(self, b: int, k: int, shadow: bool = False) -> "nat.GemmPlan":
         lib = nat.load()
         plan = nat.GemmPlan()
-        nat.check(lib.rebert_gemm_plan(self.n, b, k, C.byref(plan)))
+        nat.check((lib.rebert_gemm_plan_i8 if shadow else lib.rebert_gemm_plan)(self.n, b, k, C.byref(plan)))
         return plan
 
+    @property
+    def batch_shadow_ok(self) -> bool:
+        """True when the batched path can run on int8 operands: enable_prefilter() has built the shadow and its rows are
+        whole 128-byte k-blocks (tcgen05 kind::i8, K = 32 per instruction, 128-byte swizzled tiles)."""
+        return self._c8 is not None and self._c8.ld % 128 == 0
+
+    def quantize_queries(self, qn32: torch.Tensor):
+        """Unit queries / profiles [b, ld] fp32 -> (q8 int8 [b, ld8], qscale fp32 [b], qeps fp64 [b]) for the int8 batched path."""
+        lib = nat.load()
+        b, ld8 = qn32.shape[0], self._c8.ld
+        q8 = torch.empty((b, ld8), dtype=torch.int8, device=self.device)
+        qscale = torch.empty(b, dtype=torch.float32, device=self.device)
+        qeps = torch.empty(b, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(lib.rebert_query_quantize_i8(qn32.data_ptr(), b, self.d, self.ld, ld8, C.c_double(self.q8_row_err), q8.data_ptr(),
+                                                   qscale.data_ptr(), qeps.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return q8, qscale, qeps
+
     def enqueue_batch(self, plan, qbf16, q64, excl_ptr, excl_col, ws, out_rows, out_scores, out_count, out_status,
-                      row_filter: Optional[RowFilter] = None):
-        """Device-resident batched step (sample -> thresholds -> filtered GEMM -> select -> exact pass)."""
+                      row_filter: Optional[RowFilter] = None, shadow=None):
+        """Device-resident batched step (sample -> thresholds -> filtered GEMM -> select -> exact pass).
+        shadow = (q8, qscale, qeps) from quantize_queries: the GEMMs run on int8 operands over the prefilter shadow (plan
+        from gemm_plan(shadow=True)); the exact pass reads the catalog of record either way."""
         lib = nat.load()
         f = self._filter_struct(row_filter)
+        st = torch.cuda.current_stream().cuda_stream
+        if shadow is not None:
+            q8, qscale, qeps = shadow
+            nat.check(lib.rebert_gemm_topk_i8(C.byref(self._c), C.byref(self._c8), q8.data_ptr(), qscale.data_ptr(), qeps.data_ptr(),
+                                              q64.data_ptr(), _ptr(excl_ptr), _ptr(excl_col), None if f is None else C.byref(f),
+                                              C.byref(plan), ws.data_ptr(), ws.numel(), out_rows.data_ptr(), out_scores.data_ptr(),
+                                              out_count.data_ptr(), out_status.data_ptr(), st))
+            return
         nat.check(lib.rebert_gemm_topk(C.byref(self._c), qbf16.data_ptr(), q64.data_ptr(), _ptr(excl_ptr), _ptr(excl_col),
                                        None if f is None else C.byref(f),
                                        C.byref(plan), ws.data_ptr(), ws.numel(), out_rows.data_ptr(), out_scores.data_ptr(),
-                                       out_count.data_ptr(), out_status.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                       out_count.data_ptr(), out_status.data_ptr(), st))
 
     def recommend_batch(self, *, queries: Optional[np.ndarray] = None, liked_ptr: Optional[np.ndarray] = None,
                         liked_col: Optional[np.ndarray] = None, liked_w: Optional[np.ndarray] = None,
                         excl_ptr: Optional[np.ndarray] = None, excl_col: Optional[np.ndarray] = None, k: int = 10,
-                        row_filter: Optional[RowFilter] = None, return_info: bool = False):
+                        row_filter: Optional[RowFilter] = None, return_info: bool = False, prefilter: Optional[bool] = None):
         """Top-k for many users at once (lib.py:51-55 per user) on the tcgen05 path.
         row_filter: optional per-row predicate (genre / year / bitmap) shared by the whole batch.
+        prefilter: None = int8 operands (twice the tensor rate) when enable_prefilter() has built a shadow the GEMM can use;
+        True = require that; False = bf16 operands.  The result is the same either way.
 
         queries [b, d] fp32, OR a ragged CSR of liked rows (liked_ptr[b+1], liked_col, optional weights).
         excl_ptr/excl_col: per-user CSR of GLOBAL rows that must not be returned (sorted within a user).
@@ -713,13 +743,16 @@ class CatalogStore:
                     raise ValueError("Found array with 0 sample(s): a user has no liked movies in the catalog")
                 qn32, qn64, qbf = self.build_profiles(lp, liked_col, liked_w)
             b = qbf.shape[0]
+            if prefilter and not self.batch_shadow_ok:
+                raise ValueError("prefilter=True needs enable_prefilter() and rows of whole 128-byte int8 k-blocks")
+            use_shadow = self.batch_shadow_ok and prefilter is not False
             try:
-                plan = self.gemm_plan(b, k)
+                plan = self.gemm_plan(b, k, shadow=use_shadow)
             except nat.NativeError as e:
                 if e.code != nat.ERR_UNSUPPORTED:
                     raise
                 plan = None          # catalog too small for the sampled-threshold scheme: one fused GEMV per user instead
-            if plan is None or self.dtype != "bf16":
+            if plan is None or (self.dtype != "bf16" and not use_shadow):
                 return self._recommend_batch_loop(qn32, qn64, excl_ptr, excl_col, k, return_info, row_filter)
             ep = ec = None
             if excl_ptr is not None:
@@ -733,7 +766,8 @@ class CatalogStore:
             out_scores = torch.empty((b, k), dtype=torch.float64, device=dev)
             out_count = torch.empty(b, dtype=torch.int32, device=dev)
             out_status = torch.empty(b, dtype=torch.int32, device=dev)
-            self.enqueue_batch(plan, qbf, qn64, ep, ec, ws, out_rows, out_scores, out_count, out_status, row_filter)
+            self.enqueue_batch(plan, qbf, qn64, ep, ec, ws, out_rows, out_scores, out_count, out_status, row_filter,
+                               shadow=self.quantize_queries(qn32) if use_shadow else None)
             rows, scores = out_rows.cpu().numpy(), out_scores.cpu().numpy()
             counts, status = out_count.cpu().numpy(), out_status.cpu().numpy()
             redo = np.nonzero(status)[0]
@@ -750,7 +784,7 @@ class CatalogStore:
                     rows[u, :], scores[u, :] = -1, -np.inf
                     rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
         if return_info:
-            return rows, scores, counts, {"status": status, "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
+            return rows, scores, counts, {"status": status, "plan": {f: getattr(plan, f) for f, _ in plan._fields_}, "int8_operands": use_shadow}
         return rows, scores, counts
 
     def _recommend_batch_loop(self, qn32, qn64, excl_ptr, excl_col, k, return_info, row_filter=None):

@@ -134,7 +134,7 @@ __device__ __forceinline__ double exact_score_row_rt(const void* rows, int dtype
 
 // Rank `kc` re-scored candidates (s_row[c] < 0 = empty slot) by (score desc, row asc): the best k go to o_rows / o_scores
 // (-1 / -inf padded), their number to *o_count.  fast_last = fast score of the worst kept candidate when the fast pass's
-// list was full (list_full): *o_margin = exact k-th - fast_last - 4 max|fast - exact| proves the id set when it exceeds the
+// list was full (list_full): *o_margin = exact k-th - fast_last - err_mult (4) x max|fast - exact| proves the id set when it exceeds the
 // fast pass's error bound; +inf when the list was not full (every allowed row is a candidate), -inf when two distinct
 // scores at or above the k-th place sit within 4 ulp and the caller computed them divide-after (NEARTIE).
 // Every thread of the CTA must call; outputs may be shared, global or device-addressable pinned host memory.
@@ -142,7 +142,7 @@ template <bool NEARTIE>
 __device__ __forceinline__ void rank_candidates(const double* s_score, const int64_t* s_row, int kc, int k, bool list_full, double fast_last,
                                                 double maxerr, int64_t* o_rows, double* o_scores, int32_t* o_count,
                                                 double* o_margin, int* s_tmp /* 2 ints of shared scratch, s_tmp[0] = s_tmp[1] = 0 on entry */,
-                                                double* s_kth /* 1 double of shared scratch */) {
+                                                double* s_kth /* 1 double of shared scratch */, double err_mult = 4.0) {
     int valid_mine = 0;
     for (int c = threadIdx.x; c < kc; c += blockDim.x) {
         const int64_t r = s_row[c];
@@ -179,7 +179,7 @@ __device__ __forceinline__ void rank_candidates(const double* s_score, const int
     if (threadIdx.x == 0) {
         *o_count = nout;
         if (o_margin) {
-            double mg = (list_full && valid >= k) ? *s_kth - fast_last - 4.0 * maxerr : INFINITY;
+            double mg = (list_full && valid >= k) ? *s_kth - fast_last - err_mult * maxerr : INFINITY;
             if (NEARTIE && s_tmp[1]) mg = -INFINITY;
             *o_margin = mg;
         }

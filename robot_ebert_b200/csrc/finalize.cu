@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(kFinalThreads, 1)
 finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t row_base, int ld,
                      const double* __restrict__ q64, const uint64_t* __restrict__ cand_keys, int kc, int k,
                      int64_t* __restrict__ out_rows, double* __restrict__ out_scores, int32_t* __restrict__ out_count,
-                     double* __restrict__ out_margin) {
+                     double* __restrict__ out_margin, double err_mult) {
     constexpr int EPC = ChunkDot<T>::EPC;
     extern __shared__ __align__(16) double s_q[];   // [ld]
     __shared__ double s_score[kMaxKc];
@@ -63,7 +63,7 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
     const uint64_t last = keys[kc - 1];
     rank_candidates<!DIV>(s_score, s_row, kc, k, last != 0, last ? (double)key_score(last) : 0.0,
                           __longlong_as_double((long long)s_maxerr), out_rows + (size_t)u * k,
-                          out_scores + (size_t)u * k, out_count + u, out_margin ? out_margin + u : nullptr, s_tmp, &s_kth);
+                          out_scores + (size_t)u * k, out_count + u, out_margin ? out_margin + u : nullptr, s_tmp, &s_kth, err_mult);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -348,12 +348,12 @@ int make_exchange(const rebert_exchange_t* ex, int32_t* err_flag, Exchange* out)
 
 template <typename T, bool DIV>
 static int finalize_launch_t(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
-                             int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st) {
+                             int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st, double err_mult) {
     const size_t smem = (size_t)cat->ld * sizeof(double);
     auto kern = finalize_topk_kernel<T, DIV>;
     { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
     REBERT_CUDA(launch_pdl(kern, dim3(b), dim3(kFinalThreads), smem, st, (const T*)cat->rows, cat->norm64, cat->row_base, cat->ld, q64,
-                           cand_keys, kc, k, out_rows, out_scores, out_count, out_margin));
+                           cand_keys, kc, k, out_rows, out_scores, out_count, out_margin, err_mult));
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
 }
@@ -362,12 +362,12 @@ static int finalize_launch_t(const rebert_catalog_t* cat, const double* q64, con
 // exact_order = false: one division after the dot (within 1 ulp), near-ties flagged through the margin — the batched path.
 int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
                     int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st,
-                    bool exact_order) {
+                    bool exact_order, double err_mult = 4.0) {
     if (cat->dtype == REBERT_F32)
-        return exact_order ? finalize_launch_t<float, true>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st)
-                           : finalize_launch_t<float, false>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st);
-    return exact_order ? finalize_launch_t<__nv_bfloat16, true>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st)
-                       : finalize_launch_t<__nv_bfloat16, false>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st);
+        return exact_order ? finalize_launch_t<float, true>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st, err_mult)
+                           : finalize_launch_t<float, false>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st, err_mult);
+    return exact_order ? finalize_launch_t<__nv_bfloat16, true>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st, err_mult)
+                       : finalize_launch_t<__nv_bfloat16, false>(cat, q64, cand_keys, b, kc, k, out_rows, out_scores, out_count, out_margin, st, err_mult);
 }
 
 }  // namespace rebert

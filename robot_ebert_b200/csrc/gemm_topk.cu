@@ -37,7 +37,7 @@ namespace rebert {
 
 int finalize_launch(const rebert_catalog_t* cat, const double* q64, const uint64_t* cand_keys, int b, int kc, int k,
                     int64_t* out_rows, double* out_scores, int32_t* out_count, double* out_margin, cudaStream_t st,
-                    bool exact_order);
+                    bool exact_order, double err_mult = 4.0);
 
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
 constexpr int GEMM_STAGES = 4;
@@ -66,6 +66,7 @@ struct GemmParams {
     float* out;             // [b, out_ld], column = launch tile index * 256 + c
     int64_t out_ld;
     // MODE_FILTER
+    const float* qscale;    // [b] int8 operand path: dequantisation step of query q (scores = acc * factor[row] * qscale[q]); else nullptr
     const float* tau;       // [b]
     uint64_t* cand;         // [b, cand_cap]
     unsigned* cand_count;   // [b]
@@ -98,6 +99,17 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
         : "memory");
 }
+// int8 operands, int32 accumulators (sm_100a has kind::i8 at twice the bf16 rate; the shadow catalog of the prefilter supplies the rows)
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -126,6 +138,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), both K-major,
 // N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::i8: D = s32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major, K = 32 per instruction
+constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------------------
 // Epilogue of one 128 x 256 accumulator (shared by the 1-CTA and 2-CTA kernels).  Thread = one query row.
@@ -133,22 +147,29 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 // 32 independent FMULs, a max tree and ONE compare against the query's threshold; only a chunk that holds a winner
 // (2.5 % of thread-chunks) builds the pass mask and stages keys.  No per-element branches, no per-element LDS.
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, const float* inv_chunk, float tau, int q,
+// I8: the accumulators are int32 (kind::i8) and a score is acc * factor[row] * qs, qs = the query's dequantisation step.  The
+// filter compares acc * factor[row] against tau / qs (the caller passes that as `tau`), so the hot loop gains one I2F per
+// element and nothing else; only stored samples and staged winners are multiplied by qs.
+template <bool I8> __device__ __forceinline__ float acc_f32(uint32_t v) { return I8 ? __int2float_rn((int)v) : __uint_as_float(v); }
+
+template <int MODE, bool I8>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, const float* inv_chunk, float tau, float qs, int q,
                                                float* out_row, uint32_t row_chunk0, uint64_t* staging, int et, int& cnt) {
     float s[32];
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
         const float4 iv = ((const float4*)inv_chunk)[c4];
-        s[c4 * 4 + 0] = __uint_as_float(v[c4 * 4 + 0]) * iv.x;
-        s[c4 * 4 + 1] = __uint_as_float(v[c4 * 4 + 1]) * iv.y;
-        s[c4 * 4 + 2] = __uint_as_float(v[c4 * 4 + 2]) * iv.z;
-        s[c4 * 4 + 3] = __uint_as_float(v[c4 * 4 + 3]) * iv.w;
+        s[c4 * 4 + 0] = acc_f32<I8>(v[c4 * 4 + 0]) * iv.x;
+        s[c4 * 4 + 1] = acc_f32<I8>(v[c4 * 4 + 1]) * iv.y;
+        s[c4 * 4 + 2] = acc_f32<I8>(v[c4 * 4 + 2]) * iv.z;
+        s[c4 * 4 + 3] = acc_f32<I8>(v[c4 * 4 + 3]) * iv.w;
     }
     if (MODE == MODE_STORE) {
         if (q < p.b) {
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) *(float4*)(out_row + c) = make_float4(s[c], s[c + 1], s[c + 2], s[c + 3]);
+            for (int c = 0; c < 32; c += 4)
+                *(float4*)(out_row + c) = I8 ? make_float4(s[c] * qs, s[c + 1] * qs, s[c + 2] * qs, s[c + 3] * qs)
+                                             : make_float4(s[c], s[c + 1], s[c + 2], s[c + 3]);
         }
     } else {
         float m[16];
@@ -168,15 +189,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 float val = s[0];
 #pragma unroll
                 for (int j = 1; j < 32; ++j) val = (c == j) ? s[j] : val;       // register select, no local memory
-                if (cnt < STAGE_SLOTS) staging[cnt * 128 + et] = make_key(val, row_chunk0 + (uint32_t)c);
+                if (cnt < STAGE_SLOTS) staging[cnt * 128 + et] = make_key(I8 ? val * qs : val, row_chunk0 + (uint32_t)c);
                 ++cnt;
             }
         }
     }
 }
 
-template <int MODE>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, const float* inv, float tau, int q, int64_t row0,
+template <int MODE, bool I8>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, const float* inv, float tau, float qs, int q, int64_t row0,
                                               int64_t rt, uint64_t* staging, int et, int& cnt) {
     float* out_row = nullptr;
     if (MODE == MODE_STORE) out_row = p.out + (int64_t)q * p.out_ld + rt * BN;
@@ -186,17 +207,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 #pragma unroll
     for (int ch = 0; ch < BN / 32; ch += 2) {
         tc_ld32(taddr + (ch + 1) * 32, vb);                                     // in flight while chunk ch is processed
-        epilogue_chunk<MODE>(p, va, inv + ch * 32, tau, q, out_row + ch * 32, (uint32_t)(row0 + ch * 32), staging, et, cnt);
+        epilogue_chunk<MODE, I8>(p, va, inv + ch * 32, tau, qs, q, out_row + ch * 32, (uint32_t)(row0 + ch * 32), staging, et, cnt);
         tc_wait_ld();
         if (ch + 2 < BN / 32) tc_ld32(taddr + (ch + 2) * 32, va);
-        epilogue_chunk<MODE>(p, vb, inv + (ch + 1) * 32, tau, q, out_row + (ch + 1) * 32, (uint32_t)(row0 + (ch + 1) * 32), staging, et, cnt);
+        epilogue_chunk<MODE, I8>(p, vb, inv + (ch + 1) * 32, tau, qs, q, out_row + (ch + 1) * 32, (uint32_t)(row0 + (ch + 1) * 32), staging, et, cnt);
         if (ch + 2 < BN / 32) tc_wait_ld();
     }
 }
 
-template <int MODE>
+template <int MODE, bool I8>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_rows, const GemmParams p) {
+    constexpr int BKE = I8 ? 2 * BK : BK;             // elements per 128-byte k-block
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* stages = smem;
@@ -243,8 +265,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     mbar_wait(&empty_bar[s], ((it / GEMM_STAGES) & 1u) ^ 1u);
                     unsigned char* sa = stages + s * STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[s], pol_q);
-                    tma_load_2d(sa + A_BYTES, &map_rows, kb * BK, row0, &full_bar[s], pol_rows);
+                    tma_load_2d(sa, &map_q, kb * BKE, qt * BM, &full_bar[s], pol_q);
+                    tma_load_2d(sa + A_BYTES, &map_rows, kb * BKE, row0, &full_bar[s], pol_rows);
                 }
             }
         }
@@ -265,8 +287,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
-                        // advancing K by 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (>>4) address field
-                        tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
+                        // advancing K by 16 bf16 (32 int8) = 32 B inside the 128-B swizzle atom: +2 in the (>>4) address field
+                        if (I8) tc_mma_i8(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDescI8, (kb | k) ? 1u : 0u);
+                        else tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[s]);            // smem stage reusable once these MMAs have read it
                 }
@@ -293,14 +316,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 // rows beyond the shard, and rows the batch predicate filters out, get NaN: they can never pass tau
                 inv[c] = (r < p.n && (!p.has_pred || row_allowed(p.pred, (uint32_t)r))) ? __ldg(p.inv_norm + r) : __int_as_float(0x7FC00000);
             }
-            float tau = INFINITY;
-            if (MODE == MODE_FILTER && q < p.b) tau = __ldg(p.tau + q);
+            float tau = INFINITY, qs = 1.f;
+            if (I8 && q < p.b) qs = __ldg(p.qscale + q);
+            if (MODE == MODE_FILTER && q < p.b) tau = I8 ? __ldg(p.tau + q) / qs : __ldg(p.tau + q);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             int cnt = 0;
-            epilogue_tile<MODE>(p, taddr, inv, tau, q, row0, rt, staging, et, cnt);
+            epilogue_tile<MODE, I8>(p, taddr, inv, tau, qs, q, row0, rt, staging, et, cnt);
             // accumulator drained: hand it back to the MMA warp before the (slow) global appends
             tc_fence_before();
             __syncwarp();
@@ -336,6 +360,7 @@ constexpr int G2_STAGES = 6;
 constexpr int G2_A_BYTES = 128 * BK * 2, G2_B_BYTES = 128 * BK * 2, G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + SMEM_STAGING + SMEM_INV + 256 + 1024;
 constexpr uint32_t kInstrDesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t kInstrDesc2I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -369,9 +394,21 @@ __device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a
         : "memory");
 }
 
-template <int MODE>
+__device__ __forceinline__ void tc_mma_i8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
+template <int MODE, bool I8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_rows, const GemmParams p) {
+    constexpr int BKE = I8 ? 2 * BK : BK;             // elements per 128-byte k-block
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* stages = smem;
@@ -424,8 +461,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     unsigned char* sa = stages + s * G2_STAGE_BYTES;
                     const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);        // the leader's full barrier
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G2_STAGE_BYTES); // bytes of BOTH CTAs land on it
-                    tma_load_2d_2sm(sa, &map_q, kb * BK, q0, lbar, pol_q);
-                    tma_load_2d_2sm(sa + G2_A_BYTES, &map_rows, kb * BK, row0, lbar, pol_rows);
+                    tma_load_2d_2sm(sa, &map_q, kb * BKE, q0, lbar, pol_q);
+                    tma_load_2d_2sm(sa + G2_A_BYTES, &map_rows, kb * BKE, row0, lbar, pol_rows);
                 }
             }
         }
@@ -445,8 +482,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     const uint32_t sa = smem_u32(stages + s * G2_STAGE_BYTES);
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + G2_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k)
-                        tc_mma_bf16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc2, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / UK; ++k) {
+                        if (I8) tc_mma_i8_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc2I8, (kb | k) ? 1u : 0u);
+                        else tc_mma_bf16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc2, (kb | k) ? 1u : 0u);
+                    }
                     tc_commit_2sm(&empty_bar[s]);
                 }
                 tc_commit_2sm(&tfull_bar[acc]);
@@ -473,14 +512,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 // rows beyond the shard, and rows the batch predicate filters out, get NaN: they can never pass tau
                 inv[c] = (r < p.n && (!p.has_pred || row_allowed(p.pred, (uint32_t)r))) ? __ldg(p.inv_norm + r) : __int_as_float(0x7FC00000);
             }
-            float tau = INFINITY;
-            if (MODE == MODE_FILTER && q < p.b) tau = __ldg(p.tau + q);
+            float tau = INFINITY, qs = 1.f;
+            if (I8 && q < p.b) qs = __ldg(p.qscale + q);
+            if (MODE == MODE_FILTER && q < p.b) tau = I8 ? __ldg(p.tau + q) / qs : __ldg(p.tau + q);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             int cnt = 0;
-            epilogue_tile<MODE>(p, taddr, inv, tau, q, row0, rt, staging, et, cnt);
+            epilogue_tile<MODE, I8>(p, taddr, inv, tau, qs, q, row0, rt, staging, et, cnt);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc ? leader_tempty1 : leader_tempty0);
@@ -723,15 +763,15 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 tensor map over a row-major [rows, ld] matrix, box = [box_rows x 64 columns], 128-byte swizzle.
-static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int ld, int box_rows) {
+// 2-D tensor map over a row-major [rows, ld] matrix of bf16 (or int8: `i8`), box = [box_rows x 128 bytes], 128-byte swizzle.
+static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int ld, int box_rows, bool i8 = false) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable from the driver"); return REBERT_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (i8 ? 1 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(i8 ? 2 * BK : BK), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld ld=%d", (int)r, (long long)rows, ld); return REBERT_ERR_CUDA; }
@@ -740,8 +780,12 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int ld, i
 
 static int check_gemm_catalog(const rebert_catalog_t* cat, const char* who) {
     REBERT_REQUIRE(cat && cat->rows && cat->inv_norm, "%s: null catalog", who);
-    if (cat->dtype != REBERT_BF16) { set_error("%s: the tensor-core path needs a bf16 catalog", who); return REBERT_ERR_UNSUPPORTED; }
-    if (cat->ld % BK != 0) { set_error("%s: ld=%d is not a multiple of %d", who, cat->ld, BK); return REBERT_ERR_UNSUPPORTED; }
+    if (cat->dtype != REBERT_BF16 && cat->dtype != REBERT_I8) {
+        set_error("%s: the tensor-core path needs a bf16 catalog (or its int8 shadow)", who);
+        return REBERT_ERR_UNSUPPORTED;
+    }
+    const int kblock = cat->dtype == REBERT_I8 ? 2 * BK : BK;        // elements per 128-byte k-block
+    if (cat->ld % kblock != 0) { set_error("%s: ld=%d is not a multiple of %d", who, cat->ld, kblock); return REBERT_ERR_UNSUPPORTED; }
     REBERT_REQUIRE(cat->n > 0 && cat->n < (1ll << 31) - BN, "%s: shard rows %lld out of range", who, (long long)cat->n);
     REBERT_REQUIRE(((uintptr_t)cat->rows & 127) == 0, "%s: catalog rows must be 128-byte aligned", who);
     return REBERT_OK;
@@ -755,15 +799,17 @@ static void set_pred(GemmParams& p, const rebert_catalog_t* cat, const rebert_fi
     p.has_pred = (f.exclude_bitmap || f.genre_bits || f.year) ? 1 : 0;
 }
 
-template <int MODE>
-static int launch_gemm(const rebert_catalog_t* cat, const void* qbf16, GemmParams& p, cudaStream_t st) {
+// `cat` is the operand catalog the tensor cores stream: the bf16 catalog of record, or its int8 shadow (then qmat is int8
+// [b, ld8] and p.qscale holds the queries' dequantisation steps).
+template <int MODE, bool I8>
+static int launch_gemm_t(const rebert_catalog_t* cat, const void* qmat, GemmParams& p, cudaStream_t st) {
     const bool pair = p.b > BM && getenv("REBERT_GEMM_1CTA") == nullptr;   // cta_group::2 needs >= 2 query tiles to pay off
     CUtensorMap map_q, map_rows;
-    int rc = make_tmap(&map_q, qbf16, p.b, cat->ld, BM);
+    int rc = make_tmap(&map_q, qmat, p.b, cat->ld, BM, I8);
     if (rc != REBERT_OK) return rc;
-    rc = make_tmap(&map_rows, cat->rows, cat->n, cat->ld, pair ? 128 : BN);
+    rc = make_tmap(&map_rows, cat->rows, cat->n, cat->ld, pair ? 128 : BN, I8);
     if (rc != REBERT_OK) return rc;
-    p.kblocks = cat->ld / BK;
+    p.kblocks = cat->ld / (I8 ? 2 * BK : BK);
     p.n = cat->n;
     p.inv_norm = cat->inv_norm;
     p.num_qt = (p.b + BM - 1) / BM;
@@ -771,19 +817,76 @@ static int launch_gemm(const rebert_catalog_t* cat, const void* qbf16, GemmParam
         const int64_t tiles = (int64_t)p.num_rt * ((p.b + 255) / 256);
         int grid = num_sms() & ~1;
         if (tiles * 2 < grid) grid = (int)(tiles * 2);
-        auto kern = gemm2_kernel<MODE>;
+        auto kern = gemm2_kernel<MODE, I8>;
         { int rc__ = raise_smem_limit(kern); if (rc__ != REBERT_OK) return rc__; }
         kern<<<grid, GEMM_THREADS, G2_SMEM, st>>>(map_q, map_rows, p);
     } else {
         const int64_t tiles = (int64_t)p.num_rt * p.num_qt;
         int grid = num_sms();
         if (tiles < grid) grid = (int)tiles;
-        auto kern = gemm_kernel<MODE>;
+        auto kern = gemm_kernel<MODE, I8>;
         { int rc__ = raise_smem_limit(kern); if (rc__ != REBERT_OK) return rc__; }
         kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_q, map_rows, p);
     }
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
+}
+template <int MODE>
+static int launch_gemm(const rebert_catalog_t* cat, const void* qmat, GemmParams& p, cudaStream_t st) {
+    return cat->dtype == REBERT_I8 ? launch_gemm_t<MODE, true>(cat, qmat, p, st) : launch_gemm_t<MODE, false>(cat, qmat, p, st);
+}
+
+// Queries for the int8 operand path: q8[u, c] = rint(qn32[u, c] / step_u), step_u = max|qn32[u, :]| / 127 (1 for an all-zero
+// query), zero padded to ld8.  eps[u] = the margin a result of query u must clear to count as proven on this path:
+// 6 standard deviations of the score error under the random-direction model — the quantisation error vectors of row
+// and query, of relative norms row_err (the shadow's measured worst) and rho_u (measured here), are not aligned with the
+// vectors they meet, so the dot-product error has standard deviation sqrt(row_err^2 + rho_u^2) / sqrt(d) — plus fp32 noise.
+__global__ void __launch_bounds__(256) query_quantize_i8_kernel(const float* __restrict__ qn32, int d, int ld, int ld8, double row_err,
+                                                                int8_t* __restrict__ q8, float* __restrict__ qscale, double* __restrict__ eps) {
+    __shared__ float s_max[8];
+    __shared__ double s_e2[8], s_n2[8];
+    const int u = blockIdx.x;
+    const float* q = qn32 + (size_t)u * ld;
+    float m = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) m = fmaxf(m, fabsf(q[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m = fmaxf(m, s_max[w]);
+    const float step = m > 0.f ? m / 127.f : 1.f;
+    double e2 = 0.0, n2 = 0.0;
+    for (int c = threadIdx.x; c < ld8; c += blockDim.x) {
+        int v = 0;
+        if (c < d) {
+            const float x = q[c];
+            v = __float2int_rn(x / step);
+            v = max(-127, min(127, v));
+            const double e = (double)x - (double)v * (double)step;
+            e2 = fma(e, e, e2);
+            n2 = fma((double)x, (double)x, n2);
+        }
+        q8[(size_t)u * ld8 + c] = (int8_t)v;
+    }
+    e2 = warp_sum(e2);
+    n2 = warp_sum(n2);
+    if ((threadIdx.x & 31) == 0) { s_e2[threadIdx.x >> 5] = e2; s_n2[threadIdx.x >> 5] = n2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double E = 0.0, N = 0.0;
+        for (int w = 0; w < 8; ++w) { E += s_e2[w]; N += s_n2[w]; }
+        const double rho = N > 0.0 ? sqrt(E / N) : 0.0;                 // relative quantisation error of this query
+        qscale[u] = step;
+        // scores scale with ||q|| (a profile is shorter than a unit vector), and so does their error
+        eps[u] = 6.0 * sqrt(row_err * row_err + rho * rho) / sqrt((double)d) * fmax(sqrt(N), 1e-30) + 64.0 * 5.96e-8;
+    }
+}
+
+__global__ void margin_status_eps_kernel(const double* __restrict__ margin, const double* __restrict__ eps, int b, int* __restrict__ status) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < b && !(margin[q] > eps[q])) status[q] |= 8;
 }
 
 struct GemmWorkspace {
@@ -819,13 +922,17 @@ using namespace rebert;
 
 extern "C" {
 
-REBERT_API int rebert_gemm_plan(int64_t n, int32_t b, int32_t k, rebert_gemm_plan_t* plan) {
+static int gemm_plan_impl(int64_t n, int32_t b, int32_t k, bool shadow, rebert_gemm_plan_t* plan) {
     REBERT_REQUIRE(plan && n > 0 && b > 0 && k > 0, "gemm_plan: bad arguments");
     // Candidates for the exact pass.  The proof margin here must absorb the bf16 rounding of the query (sigma ~ 3e-5 at
     // d = 1536), so the list keeps >= 25 % more than k (the gap between the k-th and the 1.25k-th best of a large catalog
     // is ~1e-3); k itself must stay within what the single-query re-run path can serve.
+    // int8 operands (shadow): the score error is ~10x larger (sigma ~ 0.009 / sqrt(d) per unit of row and query error), and
+    // the margin has to clear 6 sigma plus twice the largest error seen on the candidates — ~0.16 standard deviations of the
+    // score distribution, i.e. ~0.7 k more rows at the densities of a 1M..10M catalog (k z rows per unit z): the list doubles.
     if (rebert_candidates_for_k(k) == 0) { set_error("gemm_plan: k=%d unsupported", k); return REBERT_ERR_UNSUPPORTED; }
     int need = k + 16 > k + (k + 3) / 4 ? k + 16 : k + (k + 3) / 4;
+    if (shadow) need = k + (k > 64 ? k : 64);
     const int kc = (need + 31) / 32 * 32;
     // Expected survivors per query E = rank * n / sample_rows.  Want E >= 8 kc (the kc best are then inside with
     // overwhelming probability: the survivor count is Gamma(rank)-distributed around E) plus headroom for excluded
@@ -854,6 +961,17 @@ REBERT_API int rebert_gemm_plan(int64_t n, int32_t b, int32_t k, rebert_gemm_pla
     return REBERT_OK;
 }
 
+REBERT_API int rebert_gemm_plan(int64_t n, int32_t b, int32_t k, rebert_gemm_plan_t* plan) { return gemm_plan_impl(n, b, k, false, plan); }
+REBERT_API int rebert_gemm_plan_i8(int64_t n, int32_t b, int32_t k, rebert_gemm_plan_t* plan) { return gemm_plan_impl(n, b, k, true, plan); }
+
+REBERT_API int rebert_query_quantize_i8(const float* qn32, int32_t b, int32_t d, int32_t ld, int32_t ld8, double row_err, void* q8,
+                                        float* qscale, double* eps, rebert_stream stream) {
+    REBERT_REQUIRE(qn32 && q8 && qscale && eps && b > 0 && d > 0 && ld >= d && ld8 >= d, "query_quantize_i8: bad arguments");
+    query_quantize_i8_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(qn32, d, ld, ld8, row_err, (int8_t*)q8, qscale, eps);
+    REBERT_CUDA(cudaGetLastError());
+    return REBERT_OK;
+}
+
 REBERT_API size_t rebert_gemm_workspace_bytes(const rebert_catalog_t* cat, const rebert_gemm_plan_t* plan) {
     (void)cat;
     if (!plan) return 0;
@@ -864,7 +982,7 @@ REBERT_API int rebert_gemm_scores(const rebert_catalog_t* cat, const void* qbf16
                                   float* out, rebert_stream stream) {
     int rc = check_gemm_catalog(cat, "gemm_scores");
     if (rc != REBERT_OK) return rc;
-    REBERT_REQUIRE(qbf16 && out && b > 0 && nrows > 0, "gemm_scores: bad arguments");
+    REBERT_REQUIRE(cat->dtype == REBERT_BF16 && qbf16 && out && b > 0 && nrows > 0, "gemm_scores: bad arguments");
     REBERT_REQUIRE(row0 % BN == 0 && nrows % BN == 0 && row0 >= 0, "gemm_scores: row0 and nrows must be multiples of %d", BN);
     REBERT_REQUIRE(((uintptr_t)out & 15) == 0, "gemm_scores: out must be 16-byte aligned");
     GemmParams p;
@@ -879,15 +997,24 @@ REBERT_API int rebert_gemm_scores(const rebert_catalog_t* cat, const void* qbf16
     return launch_gemm<MODE_STORE>(cat, qbf16, p, (cudaStream_t)stream);
 }
 
-REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, const double* q64, const int64_t* excl_row_ptr,
-                                const int32_t* excl_col, const rebert_filter_t* row_filter, const rebert_gemm_plan_t* plan,
-                                void* workspace, size_t workspace_bytes,
-                                int64_t* out_rows, double* out_scores, int32_t* out_count, int32_t* out_status,
-                                rebert_stream stream) {
-    int rc = check_gemm_catalog(cat, "gemm_topk");
+}  // extern "C"
+
+// `op` = the operand catalog the tensor cores stream (cat itself, or its int8 shadow with qmat = int8 queries, qscale / qeps
+// from rebert_query_quantize_i8); the exact pass always reads `cat`.
+static int gemm_topk_impl(const rebert_catalog_t* cat, const rebert_catalog_t* op, const void* qbf16, const float* qscale,
+                          const double* qeps, const double* q64, const int64_t* excl_row_ptr,
+                          const int32_t* excl_col, const rebert_filter_t* row_filter, const rebert_gemm_plan_t* plan,
+                          void* workspace, size_t workspace_bytes,
+                          int64_t* out_rows, double* out_scores, int32_t* out_count, int32_t* out_status,
+                          rebert_stream stream) {
+    int rc = check_gemm_catalog(op, "gemm_topk");
     if (rc != REBERT_OK) return rc;
+    REBERT_REQUIRE(cat && cat->rows && (cat->dtype == REBERT_BF16 || cat->dtype == REBERT_F32), "gemm_topk: the catalog of record must be fp32 or bf16");
     REBERT_REQUIRE(qbf16 && q64 && plan && workspace && out_rows && out_scores && out_count && out_status && cat->norm64,
                    "gemm_topk: null argument");
+    const bool shadow = op->dtype == REBERT_I8;
+    REBERT_REQUIRE(!shadow || (qscale && qeps && op->n == cat->n && op->d == cat->d && op->row_base == cat->row_base),
+                   "gemm_topk: int8 operands need query scales / bounds and a shadow of the same shape as the catalog");
     REBERT_REQUIRE((excl_row_ptr == nullptr) == (excl_col == nullptr), "gemm_topk: exclusion CSR needs both arrays");
     GemmWorkspace w = carve(workspace, plan);
     if (workspace_bytes < w.bytes) { set_error("gemm_topk: workspace %zu < %zu", workspace_bytes, w.bytes); return REBERT_ERR_WORKSPACE; }
@@ -909,8 +1036,9 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     p.tile_stride = stride;
     p.out = w.sample;
     p.out_ld = plan->sample_rows;
+    p.qscale = qscale;
     set_pred(p, cat, nullptr);                   // the sample keeps every row; the predicate is applied by the selector
-    rc = launch_gemm<MODE_STORE>(cat, qbf16, p, st);
+    rc = launch_gemm<MODE_STORE>(op, qbf16, p, st);
     if (rc != REBERT_OK) return rc;
     // 2. thresholds
     const int keys_in_smem = plan->sample_rows <= 48 * 1024;
@@ -933,8 +1061,9 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     p.cand_count = w.cand_count;
     p.cand_cap = plan->cand_cap;
     p.status = out_status;
+    p.qscale = qscale;
     set_pred(p, cat, row_filter);
-    rc = launch_gemm<MODE_FILTER>(cat, qbf16, p, st);
+    rc = launch_gemm<MODE_FILTER>(op, qbf16, p, st);
     if (rc != REBERT_OK) return rc;
     // 4. per-query candidate selection
     int p2 = 2;
@@ -946,8 +1075,15 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     REBERT_CUDA(cudaGetLastError());
     // 5. exact pass
     rc = finalize_launch(cat, q64, w.cand_keys, b, plan->kc, plan->k, out_rows, out_scores, out_count, w.margin, st,
-                         /*exact_order=*/false);   // near-ties come back as margin = -inf and are re-run by the caller
+                         /*exact_order=*/false, shadow ? 2.0 : 4.0);   // near-ties come back as margin = -inf and are re-run by the caller
     if (rc != REBERT_OK) return rc;
+    if (shadow) {
+        // int8 operands: the margin (exact k-th - fast score of the worst kept candidate - 2 x the largest |fast - exact| seen on
+        // the candidates) must clear the query's own 6-sigma model bound (rebert_query_quantize_i8)
+        margin_status_eps_kernel<<<(b + 255) / 256, 256, 0, st>>>(w.margin, qeps, b, out_status);
+        REBERT_CUDA(cudaGetLastError());
+        return REBERT_OK;
+    }
     // The margin already has 4 x (largest observed |fast - exact| over the kc candidates) subtracted (finalize.cu), which
     // calibrates the bf16 rounding of the query; on top require the model bound for that rounding, 3 sigma with
     // sigma = 2^-9 / sqrt(3 d) for a spread-out unit vector, plus the fp32 accumulation term.
@@ -955,6 +1091,49 @@ REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, 
     margin_status_kernel<<<(b + 255) / 256, 256, 0, st>>>(w.margin, eps, b, out_status);
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;
+}
+
+
+extern "C" {
+
+REBERT_API int rebert_gemm_scores_i8(const rebert_catalog_t* shadow, const void* q8, const float* qscale, int32_t b, int64_t row0,
+                                     int64_t nrows, float* out, rebert_stream stream) {
+    int rc = check_gemm_catalog(shadow, "gemm_scores_i8");
+    if (rc != REBERT_OK) return rc;
+    REBERT_REQUIRE(shadow->dtype == REBERT_I8 && q8 && qscale && out && b > 0 && nrows > 0, "gemm_scores_i8: bad arguments");
+    REBERT_REQUIRE(row0 % BN == 0 && nrows % BN == 0 && row0 >= 0, "gemm_scores_i8: row0 and nrows must be multiples of %d", BN);
+    REBERT_REQUIRE(((uintptr_t)out & 15) == 0, "gemm_scores_i8: out must be 16-byte aligned");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.b = b;
+    p.num_rt = (int)(nrows / BN);
+    p.tile0 = row0 / BN;
+    p.tile_stride = 1;
+    p.out = out;
+    p.out_ld = nrows;
+    p.qscale = qscale;
+    set_pred(p, shadow, nullptr);
+    return launch_gemm<MODE_STORE>(shadow, q8, p, (cudaStream_t)stream);
+}
+
+REBERT_API int rebert_gemm_topk(const rebert_catalog_t* cat, const void* qbf16, const double* q64, const int64_t* excl_row_ptr,
+                                const int32_t* excl_col, const rebert_filter_t* row_filter, const rebert_gemm_plan_t* plan,
+                                void* workspace, size_t workspace_bytes,
+                                int64_t* out_rows, double* out_scores, int32_t* out_count, int32_t* out_status,
+                                rebert_stream stream) {
+    REBERT_REQUIRE(cat && cat->dtype == REBERT_BF16, "gemm_topk: the bf16 tensor-core path needs a bf16 catalog");
+    return gemm_topk_impl(cat, cat, qbf16, nullptr, nullptr, q64, excl_row_ptr, excl_col, row_filter, plan, workspace, workspace_bytes,
+                          out_rows, out_scores, out_count, out_status, stream);
+}
+
+REBERT_API int rebert_gemm_topk_i8(const rebert_catalog_t* cat, const rebert_catalog_t* shadow, const void* q8, const float* qscale,
+                                   const double* qeps, const double* q64, const int64_t* excl_row_ptr, const int32_t* excl_col,
+                                   const rebert_filter_t* row_filter, const rebert_gemm_plan_t* plan, void* workspace,
+                                   size_t workspace_bytes, int64_t* out_rows, double* out_scores, int32_t* out_count,
+                                   int32_t* out_status, rebert_stream stream) {
+    REBERT_REQUIRE(shadow && shadow->dtype == REBERT_I8, "gemm_topk_i8: shadow must be an int8 prefilter shadow");
+    return gemm_topk_impl(cat, shadow, q8, qscale, qeps, q64, excl_row_ptr, excl_col, row_filter, plan, workspace, workspace_bytes,
+                          out_rows, out_scores, out_count, out_status, stream);
 }
 
 }  // extern "C"

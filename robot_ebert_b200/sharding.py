@@ -498,14 +498,16 @@ class ShardedCatalog:
         return rr, sc
 
     # ------------------------------------------------------------------ batched (tensor-core) path ----------
-    def batch_context(self, qbf: torch.Tensor, qn64: torch.Tensor, k: int, excl_ptr=None, excl_col=None, row_filter=None):
-        """Allocate everything a batched step needs (device tensors only) for prepared queries [b, ld]."""
+    def batch_context(self, qbf: torch.Tensor, qn64: torch.Tensor, k: int, excl_ptr=None, excl_col=None, row_filter=None, qn32=None):
+        """Allocate everything a batched step needs (device tensors only) for prepared queries [b, ld].  With qn32 given and
+        an int8 shadow the GEMM can use (enable_prefilter), the step runs on int8 operands."""
         import ctypes as C
         store: CatalogStore = self.backend.store
         lib = nat.load()
         dev = store.device
         b = qbf.shape[0]
-        plan = store.gemm_plan(b, k)
+        shadow = store.quantize_queries(qn32) if (qn32 is not None and store.batch_shadow_ok) else None
+        plan = store.gemm_plan(b, k, shadow=shadow is not None)
         ep = ec = None
         if excl_ptr is not None:
             excl_ptr, excl_col = sorted_csr(excl_ptr, excl_col)
@@ -514,6 +516,7 @@ class ShardedCatalog:
         hb = (b + 1) // 2
         words = 2 * b * k + 2 * hb                                       # rows | scores | counts | status
         ctx = {"b": b, "k": k, "plan": plan, "row_filter": row_filter, "qbf": qbf, "qn64": qn64, "ep": ep, "ec": ec, "hb": hb, "words": words,
+               "shadow": shadow,
                "ws": torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan)), dtype=torch.uint8, device=dev),
                "local": torch.empty(words, dtype=torch.int64, device=dev),
                "gathered": torch.empty((self.world, words), dtype=torch.int64, device=dev),
@@ -531,12 +534,29 @@ class ShardedCatalog:
         o_count = local[2 * b * k:2 * b * k + hb].view(torch.int32)
         o_status = local[2 * b * k + hb:].view(torch.int32)
         store.enqueue_batch(ctx["plan"], ctx["qbf"], ctx["qn64"], ctx["ep"], ctx["ec"], ctx["ws"], o_rows, o_scores, o_count, o_status,
-                            ctx.get("row_filter"))
+                            ctx.get("row_filter"), shadow=ctx.get("shadow"))
         dist.all_gather_into_tensor(ctx["gathered"].view(-1), local, group=self.group)
         base = ctx["gathered"].data_ptr()
         nat.check(lib.rebert_merge_topk(base, base + 8 * b * k, base + 16 * b * k, words, words, 2 * words, self.world, b, k,
                                         ctx["m_rows"].data_ptr(), ctx["m_scores"].data_ptr(), ctx["m_count"].data_ptr(),
                                         torch.cuda.current_stream().cuda_stream))
+
+    def batch_collect(self, ctx, queries, excl_ptr=None, excl_col=None):
+        """Second half of a batched step: read the merged results and the per-query status back, and re-run every query some
+        rank could not prove through the sharded single-query route (identical decisions on every rank).
+        Returns (rows [b, k], scores [b, k], counts [b], status [b])."""
+        b, k, hb = ctx["b"], ctx["k"], ctx["hb"]
+        status = ctx["gathered"][:, 2 * b * k + hb:].contiguous().view(torch.int32)[:, :b].max(dim=0).values   # any rank unsure
+        rows, scores = ctx["m_rows"].cpu().numpy(), ctx["m_scores"].cpu().numpy()
+        counts, status = ctx["m_count"].cpu().numpy(), status.cpu().numpy()
+        ecp = None if excl_ptr is None else np.asarray(excl_ptr, dtype=np.int64)
+        eca = None if excl_col is None else np.asarray(excl_col)
+        for u in np.nonzero(status)[0]:
+            ex = None if ecp is None else eca[ecp[u]:ecp[u + 1]]
+            r, sc = self.recommend(query=np.asarray(queries[u]), exclude_rows=ex, k=k, row_filter=ctx.get("row_filter"), prefilter=False)
+            rows[u, :], scores[u, :] = -1, -np.inf
+            rows[u, :len(r)], scores[u, :len(r)], counts[u] = r, sc, len(r)
+        return rows, scores, counts, status
 
     def recommend_batch(self, *, queries=None, liked_ptr=None, liked_col=None, liked_w=None, excl_ptr=None, excl_col=None,
                         k: int = 10, row_filter=None, return_info: bool = False):
@@ -556,7 +576,7 @@ class ShardedCatalog:
                 qn32, qn64, qbf = store.build_profiles(
                     lp, liked_col, liked_w, reduce_fn=lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group))
             try:
-                ctx = self.batch_context(qbf, qn64, k, excl_ptr, excl_col, row_filter)
+                ctx = self.batch_context(qbf, qn64, k, excl_ptr, excl_col, row_filter, qn32=qn32)
             except nat.NativeError as e:
                 if e.code != nat.ERR_UNSUPPORTED:
                     raise

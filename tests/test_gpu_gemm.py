@@ -159,3 +159,87 @@ def test_small_or_fp32_catalogs_are_served_by_the_single_query_kernel():
     _, _, qbf = store.prepare_queries(_queries(4, 64))
     with pytest.raises(Exception):
         store.gemm_scores(qbf, 0, 256)          # the tensor-core building block itself is bf16-only
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# int8 operands (tcgen05 kind::i8 over the prefilter shadow): exact integer arithmetic in the GEMM, same results end to end
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,b", [(4096, 1536, 200), (5000, 256, 128), (2048, 128, 1), (70_000, 512, 300)])
+def test_int8_gemm_scores_are_the_integer_dot_products(n, d, b):
+    import ctypes as C
+    from robot_ebert_b200 import _native as nat
+    lib = nat.load()
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    store.enable_prefilter()
+    assert store.batch_shadow_ok
+    qn32, qn64, qbf = store.prepare_queries(_queries(b, d))
+    q8, qscale, qeps = store.quantize_queries(qn32)
+    nrows = (n + 255) // 256 * 256
+    out = torch.empty((b, nrows), dtype=torch.float32, device=store.device)
+    nat.check(lib.rebert_gemm_scores_i8(C.byref(store._c8), q8.data_ptr(), qscale.data_ptr(), b, 0, nrows, out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    rows8 = store._q8_rows[:n].cpu().numpy().astype(np.int64)
+    factor = store._q8_factor[:n].cpu().numpy().astype(np.float64)
+    acc = q8.cpu().numpy().astype(np.int64) @ rows8.T                               # exact integer dot products
+    want = acc.astype(np.float64) * factor[None, :] * qscale.cpu().numpy().astype(np.float64)[:, None]
+    got = out[:, :n].cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(got, want, rtol=3e-7, atol=1e-9)                     # two fp32 multiplies on an exact integer
+    # the quantised scores approximate the true cosines within the per-query bound the proof uses (6 sigma: generous)
+    m = _stored_f64(store)
+    true = (qn64[:8, :d].cpu().numpy() @ m[:2048].T) / np.linalg.norm(m[:2048], axis=1)
+    assert np.abs(got[:8, :2048] - true).max() < float(qeps[:8].max().item())
+
+
+@pytest.mark.parametrize("n,d,b,k", [(200_000, 1536, 300, 10), (150_000, 256, 257, 100), (300_000, 128, 64, 240)])
+def test_int8_batched_path_equals_bf16_batched_path_and_oracle(n, d, b, k):
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    store.enable_prefilter()
+    m = _stored_f64(store)
+    q = _queries(b, d)
+    rng = np.random.default_rng(5)
+    ptr, cols = [0], []
+    for u in range(b):
+        c = np.sort(rng.choice(n, size=int(rng.integers(0, 200)), replace=False))
+        cols.append(c)
+        ptr.append(ptr[-1] + len(c))
+    ptr, col = np.array(ptr), np.concatenate(cols)
+    r8, s8, c8, i8 = store.recommend_batch(queries=q, excl_ptr=ptr, excl_col=col, k=k, return_info=True, prefilter=True)
+    rb, sb, cb, ib = store.recommend_batch(queries=q, excl_ptr=ptr, excl_col=col, k=k, return_info=True, prefilter=False)
+    assert i8["int8_operands"] and not ib["int8_operands"]
+    assert (i8["status"] != 0).mean() < 0.10, (i8["status"] != 0).mean()            # the int8 filter must carry almost everything
+    np.testing.assert_array_equal(r8, rb)
+    np.testing.assert_array_equal(s8, sb)                                           # same exact pass on the same rows: same bits
+    np.testing.assert_array_equal(c8, cb)
+    unit = m / np.linalg.norm(m, axis=1, keepdims=True)
+    qn = q.astype(np.float64)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    for u in range(0, b, 7):
+        want_rows, want_scores = ora.topk_rows(unit @ qn[u], k, cols[u])
+        np.testing.assert_array_equal(r8[u, :c8[u]], want_rows, err_msg=f"query {u} status {i8['status'][u]}")
+        np.testing.assert_allclose(s8[u, :c8[u]], want_scores, rtol=1e-9, atol=1e-15)
+
+
+def test_int8_batched_profiles_with_predicate_vs_oracle():
+    """CSR profiles (shorter than unit vectors: the error bound scales with their length) + genre/year predicate."""
+    from robot_ebert_b200 import RowFilter
+    n, d, b, k = 160_000, 256, 96, 50
+    store = CatalogStore.synthetic(0, n, d, "bf16", scale_rows=True)
+    store.enable_prefilter()
+    g, y = synth.movie_metadata(3, 0, n)
+    store.set_metadata(g, y)
+    m = _stored_f64(store)
+    lp, lc, ep, ec = [0], [], [0], []
+    users = synth.user_ratings(2, n, b)
+    for rated, rts in users:
+        liked = rated[rts >= 3.5] if (rts >= 3.5).any() else rated[:1]
+        lc.append(liked); lp.append(lp[-1] + len(liked)); ec.append(rated); ep.append(ep[-1] + len(rated))
+    rf = RowFilter(genre_any=0b1011, year_lo=1960, year_hi=2000)
+    keep = ((g & 0b1011) != 0) & (y >= 1960) & (y <= 2000)
+    rows, scores, counts, info = store.recommend_batch(liked_ptr=np.array(lp), liked_col=np.concatenate(lc), excl_ptr=np.array(ep),
+                                                       excl_col=np.concatenate(ec), k=k, row_filter=rf, return_info=True, prefilter=True)
+    assert info["int8_operands"]
+    for u in range(0, b, 5):
+        want_rows, want_scores = ora.recommend_rows(m, lc[u], ec[u], k, keep_mask=keep)
+        np.testing.assert_array_equal(rows[u, :counts[u]], want_rows, err_msg=f"user {u} status {info['status'][u]}")
+        np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
