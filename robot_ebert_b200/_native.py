@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librebert_b200.so")
+# REBERT_DEBUG=1 loads the assertion-carrying twin (build.py --debug): device-side bounds checks at every computed index
+LIB_PATH = os.path.join(_PKG, "librebert_b200_debug.so" if os.environ.get("REBERT_DEBUG") == "1" else "librebert_b200.so")
 
 F32, BF16 = 0, 1
 I8 = 2          # prefilter shadow only (rebert_catalog_quantize_i8)

@@ -15,6 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "librebert_b200.so")
+LIB_DEBUG = os.path.join(PKG, "librebert_b200_debug.so")      # -DREBERT_DEBUG: device-side bounds assertions (common.cuh)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -24,8 +25,8 @@ def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest(paths):
-    h = hashlib.sha256(" ".join(FLAGS).encode())
+def _digest(paths, extra=""):
+    h = hashlib.sha256((" ".join(FLAGS) + extra).encode())
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(p.encode() + b"\0" + f.read())
@@ -38,29 +39,33 @@ def _deps():
     return hdr
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ, exist_ok=True)
+def build_native(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """debug=True builds the assertion-carrying twin librebert_b200_debug.so (same sources, -DREBERT_DEBUG)."""
+    obj_dir = OBJ + ("_debug" if debug else "")
+    lib_path = LIB_DEBUG if debug else LIB
+    flags = FLAGS + (["-DREBERT_DEBUG"] if debug else [])
+    os.makedirs(obj_dir, exist_ok=True)
     srcs, hdrs = _sources(), _deps()
-    stamp = os.path.join(OBJ, "stamp")
-    want = _digest(srcs + hdrs)
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == want:
-        return LIB
+    stamp = os.path.join(obj_dir, "stamp")
+    want = _digest(srcs + hdrs, "debug" if debug else "")
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == want:
+        return lib_path
     if not os.path.exists(NVCC):
-        raise RuntimeError(f"nvcc not found at {NVCC} and {LIB} is missing or stale")
+        raise RuntimeError(f"nvcc not found at {NVCC} and {lib_path} is missing or stale")
 
     def compile_one(src):
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        key = os.path.join(OBJ, os.path.basename(src)[:-3] + ".key")
-        k = _digest([src] + hdrs)
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        key = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".key")
+        k = _digest([src] + hdrs, "debug" if debug else "")
         if not force and os.path.exists(obj) and os.path.exists(key) and open(key).read() == k:
             return obj, ""
-        cmd = [NVCC, *FLAGS, "-Xptxas", "-v", "-c", src, "-o", obj]
+        cmd = [NVCC, *flags, "-Xptxas", "-v", "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         with open(key, "w") as f:
             f.write(k)
-        with open(os.path.join(OBJ, os.path.basename(src)[:-3] + ".ptxas.log"), "w") as f:
+        with open(os.path.join(obj_dir, os.path.basename(src)[:-3] + ".ptxas.log"), "w") as f:
             f.write(r.stderr)
         return obj, r.stderr
 
@@ -70,15 +75,15 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+    cmd = [NVCC, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
            "-Xlinker", "--exclude-libs,ALL"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(want)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build_native(force="--force" in sys.argv, verbose=True))
+    print(build_native(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))

@@ -73,6 +73,23 @@ __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row)
 __host__ __device__ __forceinline__ float key_score(uint64_t k) { return orderable_f32((uint32_t)(k >> 32)); }
 __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
 
+// ---------------------------------------------------------------- debug build ---------------
+// -DREBERT_DEBUG (robot_ebert_b200/build.py --debug -> librebert_b200_debug.so, loaded when REBERT_DEBUG=1) turns on
+// device-side bounds assertions at every computed index the kernels write through; compute-sanitizer is not available on
+// the GPU pool this was developed on, so tools/sanitize_small.py drives the debug library over small and ragged cases.
+#if defined(REBERT_DEBUG) && defined(__CUDACC__)
+#define REBERT_ASSERT(cond)                                                                                              \
+    do {                                                                                                                 \
+        if (!(cond)) {                                                                                                   \
+            printf("REBERT_ASSERT failed: %s  at %s:%d  (block %d, thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                                    \
+            __trap();                                                                                                    \
+        }                                                                                                                \
+    } while (0)
+#else
+#define REBERT_ASSERT(cond) do { } while (0)
+#endif
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device: filter ------------
 struct DevFilter {

@@ -162,6 +162,7 @@ __device__ __forceinline__ void rank_candidates(const double* s_score, const int
             }
         }
         if (NEARTIE && near && rank <= k) s_tmp[1] = 1;    // a divide-after formula cannot be trusted to order these
+        REBERT_ASSERT(rank >= 0 && rank < kc);
         if (rank < k) {
             o_rows[rank] = r;
             o_scores[rank] = sc;

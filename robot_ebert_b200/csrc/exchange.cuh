@@ -69,6 +69,7 @@ __device__ __forceinline__ void xchg_publish_and_wait(const Exchange& x, size_t 
 __device__ __forceinline__ void exchange_results(const Exchange& x, int k, const unsigned long long* local, unsigned long long* out) {
     const int words = 2 * k + 2;
     const int parity = (int)(x.seq & 1u);
+    REBERT_ASSERT(words <= x.words_cap && x.rank < x.world && x.world <= kMaxPeers);
     for (int i = threadIdx.x; i < x.world * words; i += blockDim.x) {
         const int pr = i / words, w = i - pr * words;
         x.peer[pr][xchg_gather_off(x, parity, x.rank) + w] = local[w];
@@ -126,6 +127,7 @@ __device__ __forceinline__ void exchange_results(const Exchange& x, int k, const
 // identical bits.  The weight sum is the same on every rank already (profile_accumulate counts every entry).
 __device__ __forceinline__ void exchange_profile(const Exchange& x, int len, const double* local, double* total) {   // total may alias local
     const int parity = (int)(x.seq & 1u);
+    REBERT_ASSERT(len < x.prof_cap + 1 && x.rank < x.world);
     for (int i = threadIdx.x; i < x.world * len; i += blockDim.x) {
         const int pr = i / len, c = i - pr * len;
         x.peer[pr][xchg_prof_off(x, parity, x.rank) + c] = (unsigned long long)__double_as_longlong(local[c]);

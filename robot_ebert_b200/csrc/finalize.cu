@@ -87,7 +87,7 @@ struct FinalizeParams {
     const double* x_norm64;
     const double* q64;
     int x_ld, x_dtype;
-    int64_t row_base;
+    int64_t row_base, x_n;
     int k, cap;
     unsigned long long* out_packed;
     uint32_t tag;
@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
         int64_t gr = -1;
         if (key != 0) {
             const uint32_t lr = key_row(key);
+            REBERT_ASSERT((int64_t)lr < p.x_n && c < kc);
             sc = exact_score_row_rt(p.x_rows, p.x_dtype, p.x_ld, p.x_norm64, lr, qsrc, lane);
             gr = p.row_base + lr;
             werr = fmax(werr, fabs(sc - (double)key_score(key)));
@@ -219,6 +220,7 @@ int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t 
     p.x_ld = f.exact_cat->ld;
     p.x_dtype = f.exact_cat->dtype;
     p.row_base = row_base;
+    p.x_n = f.exact_cat->n;
     p.k = f.k;
     int need = 2 * pub.keys.kc > pub.keys.kc + pub.keys.lists ? 2 * pub.keys.kc : pub.keys.kc + pub.keys.lists;
     int cap = 1024;

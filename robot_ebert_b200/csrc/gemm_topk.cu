@@ -189,6 +189,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 float val = s[0];
 #pragma unroll
                 for (int j = 1; j < 32; ++j) val = (c == j) ? s[j] : val;       // register select, no local memory
+                REBERT_ASSERT(et >= 0 && et < 128 && (int64_t)(row_chunk0 + (uint32_t)c) < p.n);
                 if (cnt < STAGE_SLOTS) staging[cnt * 128 + et] = make_key(I8 ? val * qs : val, row_chunk0 + (uint32_t)c);
                 ++cnt;
             }

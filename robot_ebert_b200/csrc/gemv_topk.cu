@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
                     ma &= ma - 1;
                     const float sc = __shfl_sync(0xffffffffu, sa, src);
                     const uint32_t lr = (uint32_t)(row0 + base + src / LANES);
+                    REBERT_ASSERT((int64_t)lr < p.n);
                     if (sc > top.thr && row_allowed(p.filter, lr, excl_s)) {
                         top.insert(make_key(sc, lr), lane);
                         publish_hints<kQuantLane>(top.keys[0], top.thr, warp, lane, p.cta_hint, &s_hint, s_wq);
@@ -536,11 +537,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_topk_kernel(const GemvParams
             while (lo < hi) { int mid = (lo + hi) >> 1; if (L[mid] > key) lo = mid + 1; else hi = mid; }
             rank += lo;
         }
+        REBERT_ASSERT(rank >= 0 && w < kConsumerWarps);
         if (rank < kc) merged[rank] = key;
     }
     __syncthreads();
     // publish: the kept keys into the compacted array, the list's head (first pub_P keys) and tail (kc-th key if full)
     {
+        REBERT_ASSERT((int)s_base + nkeep <= p.region_cap && p.pub_P * (int)gridDim.x <= kc + 256);
         uint64_t* dst = p.pub_keys + (size_t)region * p.region_cap + s_base;
         for (int i = threadIdx.x; i < nkeep; i += blockDim.x) dst[i] = merged[i];
         for (int j = threadIdx.x; j < p.pub_P; j += blockDim.x) p.pub_heads[(size_t)blockIdx.x * p.pub_P + j] = j < kc ? merged[j] : 0;

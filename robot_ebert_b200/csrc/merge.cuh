@@ -130,6 +130,7 @@ __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_
                 if (lane_ == 0) wbase = atomicAdd(&s_cnt, __popc(m));
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 const int idx = wbase + __popc(m & ((1u << lane_) - 1u));
+                REBERT_ASSERT(idx >= 0);
                 if (keep && idx < cap) buf[idx] = kk[j];
             }
         }
@@ -169,6 +170,7 @@ __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_
             const uint64_t key = buf[i];
             int rank = 0;
             for (int j = 0; j < cnt; ++j) rank += buf[j] > key;
+            REBERT_ASSERT(key != 0 && rank < cnt);
             if (rank < kc) out[rank] = key;
         }
         __syncthreads();

@@ -130,6 +130,7 @@ __device__ __forceinline__ void profile_accumulate_cta(const T* __restrict__ row
 #pragma unroll
                 for (int j = 0; j < INFLIGHT; ++j) {
                     rr[j] = (i + j < nb) ? s_row[i + j] : -1;
+                    REBERT_ASSERT(rr[j] < n);
                     if (rr[j] >= 0) v[j] = __ldg((const uint4*)(rows + (size_t)rr[j] * ld) + g);
                 }
 #pragma unroll
