@@ -6,8 +6,10 @@
 //
 // One symmetric buffer per rank holds `channels` independent channels (one per concurrent request stream: FastAPI serves
 // from a threadpool, api/users.py:151), each laid out in 64-bit words as
-//     gather [2][world][words_cap]   packed results: rows k | fp64 scores k | count + tag | margin
-//     flags  [2][world]              sequence number of the last result that rank delivered
+//     gather [2][world][2 * words_cap]   packed results (rows k | fp64 scores k | count + tag | margin) in "LL" form: every
+//                                        32-bit half of a word travels in its own 8-byte store together with the call's
+//                                        sequence number, so data and flag arrive atomically — no fence, no separate flag
+//     flags  [2][world]                  (unused by the LL form; kept so the layout has one shape)
 //     prof   [2][world][prof_cap]    fp64 partial profile sums (ld values) + the weight sum
 //     pflags [2][world]
 // The leading [2] is the parity of the channel's call sequence number.  Parity double-buffering suffices because a rank
@@ -32,17 +34,14 @@ struct Exchange {
 };
 
 __host__ __device__ __forceinline__ size_t xchg_channel_words(int world, int words_cap, int prof_cap) {
-    return (size_t)2 * world * words_cap + (size_t)2 * world + (size_t)2 * world * prof_cap + (size_t)2 * world;
+    return (size_t)4 * world * words_cap + (size_t)2 * world + (size_t)2 * world * prof_cap + (size_t)2 * world;
 }
-__device__ __forceinline__ size_t xchg_gather_off(const Exchange& x, int parity, int r) { return ((size_t)parity * x.world + r) * x.words_cap; }
-__device__ __forceinline__ size_t xchg_flag_off(const Exchange& x, int parity, int r) {
-    return (size_t)2 * x.world * x.words_cap + (size_t)parity * x.world + r;
-}
+__device__ __forceinline__ size_t xchg_gather_off(const Exchange& x, int parity, int r) { return ((size_t)parity * x.world + r) * 2 * x.words_cap; }
 __device__ __forceinline__ size_t xchg_prof_off(const Exchange& x, int parity, int r) {
-    return (size_t)2 * x.world * x.words_cap + (size_t)2 * x.world + ((size_t)parity * x.world + r) * x.prof_cap;
+    return (size_t)4 * x.world * x.words_cap + (size_t)2 * x.world + ((size_t)parity * x.world + r) * x.prof_cap;
 }
 __device__ __forceinline__ size_t xchg_pflag_off(const Exchange& x, int parity, int r) {
-    return (size_t)2 * x.world * x.words_cap + (size_t)2 * x.world + (size_t)2 * x.world * x.prof_cap + (size_t)parity * x.world + r;
+    return (size_t)4 * x.world * x.words_cap + (size_t)2 * x.world + (size_t)2 * x.world * x.prof_cap + (size_t)parity * x.world + r;
 }
 
 // publish `seq` in every peer's flag slot for my rank, then wait until every rank's flag in MY buffer shows `seq`.
@@ -64,25 +63,47 @@ __device__ __forceinline__ void xchg_publish_and_wait(const Exchange& x, size_t 
     __syncthreads();
 }
 
-// Result exchange + merge.  `local` = this rank's packed block of 2k+2 words (shared or global memory); `out` receives the
-// merged block (global or pinned host memory).  All threads of the CTA call.
-__device__ __forceinline__ void exchange_results(const Exchange& x, int k, const unsigned long long* local, unsigned long long* out) {
+// Result exchange + merge, LL protocol (as in NCCL's low-latency path): half h (32 bits) of word w of my block goes to
+// every peer as ONE 8-byte store {half, seq}; 8-byte stores are atomic over NVLink, so a reader that sees `seq` in the upper
+// half has the data in the lower half — no system-scope fence and no separate flag round trip, which together cost ~10 us
+// per request in the fenced form.  A stale word (the slot's previous use was call seq - 2) can never carry `seq`.
+// `local` = this rank's packed block of 2k+2 words (shared or global memory); `out` receives the merged block (global or
+// pinned host memory); s_all = world * (2k + 2) words of shared scratch.  All threads of the CTA call.
+__device__ __forceinline__ void exchange_results(const Exchange& x, int k, const unsigned long long* local, unsigned long long* out,
+                                                 unsigned long long* s_all) {
     const int words = 2 * k + 2;
+    const int halves = 2 * words;
     const int parity = (int)(x.seq & 1u);
     REBERT_ASSERT(words <= x.words_cap && x.rank < x.world && x.world <= kMaxPeers);
-    for (int i = threadIdx.x; i < x.world * words; i += blockDim.x) {
-        const int pr = i / words, w = i - pr * words;
-        x.peer[pr][xchg_gather_off(x, parity, x.rank) + w] = local[w];
+    const unsigned long long tagged = (unsigned long long)x.seq << 32;
+    for (int i = threadIdx.x; i < x.world * halves; i += blockDim.x) {
+        const int pr = i / halves, h = i - pr * halves;
+        const unsigned long long wv = local[h >> 1];
+        const unsigned long long half = (h & 1) ? (wv >> 32) : (wv & 0xFFFFFFFFull);
+        unsigned long long* dst = x.peer[pr] + xchg_gather_off(x, parity, x.rank) + h;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(tagged | half) : "memory");
     }
-    __threadfence_system();
-    __syncthreads();
-    xchg_publish_and_wait(x, xchg_flag_off(x, parity, x.rank), xchg_flag_off(x, parity, 0));
+    // collect every rank's block from MY buffer: poll each LL word until it carries this call's sequence number
     const unsigned long long* g = x.peer[x.rank] + xchg_gather_off(x, parity, 0);
+    const long long t0 = clock64();
+    for (int i = threadIdx.x; i < x.world * halves; i += blockDim.x) {
+        const int l = i / halves, h = i - l * halves;
+        const unsigned long long* src = g + (size_t)l * 2 * x.words_cap + h;
+        unsigned long long v;
+        while (true) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if ((unsigned)(v >> 32) == x.seq) break;
+            if (clock64() - t0 > x.timeout_cycles) { *(volatile int*)x.err = 1 + l; v = 0; break; }   // plain store: err may live in pinned host memory
+            __nanosleep(32);
+        }
+        ((unsigned*)s_all)[(size_t)l * halves + h] = (unsigned)v;             // little endian: half h of word h >> 1
+    }
+    __syncthreads();
     int total = 0;
     double margin = INFINITY;
     const unsigned my_tag = (unsigned)(local[2 * k] >> 32);
     for (int l = 0; l < x.world; ++l) {
-        const unsigned long long* L = g + (size_t)l * x.words_cap;
+        const unsigned long long* L = s_all + (size_t)l * words;
         total += min((int)(unsigned)L[2 * k], k);
         margin = fmin(margin, __longlong_as_double((long long)L[2 * k + 1]));
         // every rank must be serving the SAME request on this channel: a differing tag means the callers' request order diverged
@@ -92,14 +113,14 @@ __device__ __forceinline__ void exchange_results(const Exchange& x, int k, const
     const int nout = total < k ? total : k;
     for (int i = threadIdx.x; i < x.world * k; i += blockDim.x) {
         const int l = i / k, e = i - l * k;
-        const unsigned long long* L = g + (size_t)l * x.words_cap;
+        const unsigned long long* L = s_all + (size_t)l * words;
         if (e >= (int)(unsigned)L[2 * k]) continue;
         const int64_t r = (int64_t)L[e];
         const double sc = __longlong_as_double((long long)L[k + e]);
         int rank = e;
         for (int o = 0; o < x.world; ++o) {
             if (o == l) continue;
-            const unsigned long long* O = g + (size_t)o * x.words_cap;
+            const unsigned long long* O = s_all + (size_t)o * words;
             int lo = 0, hi = min((int)(unsigned)O[2 * k], k);
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;

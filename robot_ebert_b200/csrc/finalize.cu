@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     int64_t* s_row = (int64_t*)(s_score + kc);                         // [kc]
     unsigned long long* s_werr = (unsigned long long*)(s_row + kc);    // [cluster warps] largest |fast - exact| per warp
     unsigned long long* s_block = s_werr + kFinalCluster * (kFinalClusterThreads / 32);   // [2 k + 2] local result (row shards)
+    unsigned long long* s_all = s_block + 2 * k + 2;                   // [world][2 k + 2] every rank's result (row shards)
     __shared__ int s_tmp[2];
     __shared__ double s_kth;
     cg::cluster_group cluster = cg::this_cluster();
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     FIN_TRACE(4);
     if (exchange) {
         __syncthreads();
-        exchange_results(p.xchg, k, s_block, p.out_packed);
+        exchange_results(p.xchg, k, s_block, p.out_packed, s_all);
         pdl_trigger();
     }
     if (threadIdx.x < 32) p.pub.ctl[threadIdx.x] = 0u;       // ticket, hint, tile-claim counter, compaction cursors
@@ -232,7 +233,7 @@ int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t 
     p.done_token = f.done_token;
     if (f.xchg) p.xchg = *f.xchg;
     const size_t smem = (size_t)p.x_ld * 8 + (size_t)cap * 8 + (size_t)pub.keys.kc * 24 + (size_t)kFinalCluster * (kFinalClusterThreads / 32) * 8 +
-                        (size_t)(2 * f.k + 2) * 8;
+                        (size_t)(2 * f.k + 2) * 8 * (1 + (f.xchg ? f.xchg->world : 0));
     auto kern = finalize_published_kernel;
     { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
     cudaLaunchConfig_t cfg;
@@ -301,8 +302,9 @@ __global__ void merge_topk_kernel(const int64_t* __restrict__ rows, const double
 // own tail (gemv_topk.cu); these kernels serve callers that hold a packed local result / a partial profile already.
 __global__ void __launch_bounds__(256) exchange_merge_kernel(Exchange x, int k, const unsigned long long* __restrict__ local,
                                                              unsigned long long* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned long long s_xall[];    // [world][2 k + 2]
     pdl_wait();                                      // `local` is written by the kernel launched just before
-    exchange_results(x, k, local, out);
+    exchange_results(x, k, local, out, s_xall);
     pdl_trigger();                                   // only now: see finalize_published_kernel
 }
 
@@ -411,7 +413,7 @@ REBERT_API int rebert_exchange_merge(const rebert_exchange_t* ex, int32_t k, con
     int rc = make_exchange(ex, err_flag, &x);
     if (rc != REBERT_OK) return rc;
     REBERT_REQUIRE(k > 0 && k <= ex->k_max, "exchange_merge: k=%d k_max=%d", k, ex->k_max);
-    REBERT_CUDA(launch_pdl(exchange_merge_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, x, k,
+    REBERT_CUDA(launch_pdl(exchange_merge_kernel, dim3(1), dim3(256), (size_t)ex->world * (2 * k + 2) * 8, (cudaStream_t)stream, x, k,
                            (const unsigned long long*)local_packed, (unsigned long long*)out_packed));
     REBERT_CUDA(cudaGetLastError());
     return REBERT_OK;

@@ -92,9 +92,9 @@ def test_c_abi_argument_validation_without_a_gpu():
     assert lib.rebert_catalog_layout(10, 32, 7, None, None) == nat.ERR_INVALID and b"dtype" in lib.rebert_last_error()
     assert lib.rebert_merge_topk(None, None, None, 1, 1, 1, 2, 1, 10, None, None, None, None) == nat.ERR_INVALID
     assert lib.rebert_exchange_buffer_bytes(0, 10, 0, 1) == 0 and lib.rebert_exchange_buffer_bytes(17, 10, 0, 1) == 0
-    # per channel: results [2][world][2 k_max + 2] + flags [2][world] + profiles [2][world][prof_len + 1] + flags [2][world]
-    assert lib.rebert_exchange_buffer_bytes(8, 240, 0, 1) == (2 * 8 * 482 + 16 + 2 * 8 * 1 + 16) * 8
-    assert lib.rebert_exchange_buffer_bytes(8, 240, 1536, 16) == 16 * (2 * 8 * 482 + 16 + 2 * 8 * 1537 + 16) * 8
+    # per channel: results in LL form [2][world][2 * (2 k_max + 2)] + flags [2][world] + profiles [2][world][prof_len + 1] + flags [2][world]
+    assert lib.rebert_exchange_buffer_bytes(8, 240, 0, 1) == (4 * 8 * 482 + 16 + 2 * 8 * 1 + 16) * 8
+    assert lib.rebert_exchange_buffer_bytes(8, 240, 1536, 16) == 16 * (4 * 8 * 482 + 16 + 2 * 8 * 1537 + 16) * 8
     plan = nat.GemmPlan()
     assert lib.rebert_gemm_plan(1000, 16, 10, C.byref(plan)) == nat.ERR_UNSUPPORTED and b"too small" in lib.rebert_last_error()
     assert lib.rebert_gemm_plan(1_000_000, 4096, 100, C.byref(plan)) == nat.OK
