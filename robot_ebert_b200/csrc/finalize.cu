@@ -12,14 +12,14 @@ namespace rebert {
 
 namespace cg = cooperative_groups;
 
-constexpr int kFinalThreads = 1024;
+constexpr int kFinalThreads = 512;        // two CTAs per SM: one query's ranking overlaps the next one's row gather
 constexpr int kMaxKc = 1024;
 
 // grid = (b); one CTA per query.  cand_keys [b, kc], q64 [b, ld], outputs [b, k].
 // The fp64 query is staged in shared memory once; every warp re-scores candidates with 16-byte row loads
 // (exact_score_row, exact.cuh — the same function the fused single-request kernel uses, so both give the same bits).
 template <typename T, bool DIV>
-__global__ void __launch_bounds__(kFinalThreads, 1)
+__global__ void __launch_bounds__(kFinalThreads, 2)
 finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t row_base, int ld,
                      const double* __restrict__ q64, const uint64_t* __restrict__ cand_keys, int kc, int k,
                      int64_t* __restrict__ out_rows, double* __restrict__ out_scores, int32_t* __restrict__ out_count,

@@ -3,7 +3,7 @@
 // build (lib.py:51-52: mean of the liked rows' unit vectors).  Shared so that every route produces the same bits.
 #pragma once
 
-#include "common.cuh"
+#include "exact.cuh"
 
 namespace rebert {
 
@@ -98,6 +98,7 @@ __device__ __forceinline__ void profile_accumulate_cta(const T* __restrict__ row
     __shared__ int s_row[kProfBlock];
     __shared__ double s_w[kProfBlock];      // weight (DIV) or weight / norm (!DIV)
     __shared__ double s_n[kProfBlock];      // norm (DIV only)
+    __shared__ double s_y[kProfBlock];      // RN(1 / norm) (DIV only): x / norm comes from it by two FMA corrections (exact.cuh)
     __shared__ double s_red[32];
     const int chunks = ld / EPC;
     double acc[kProfMaxIter][EPC];
@@ -117,6 +118,7 @@ __device__ __forceinline__ void profile_accumulate_cta(const T* __restrict__ row
             s_row[i] = mine ? (int)r : -1;
             s_w[i] = DIV ? wt : wt / nrm;
             s_n[i] = nrm;
+            if (DIV) s_y[i] = 1.0 / nrm;
             wloc += wt;
         }
         __syncthreads();
@@ -138,9 +140,10 @@ __device__ __forceinline__ void profile_accumulate_cta(const T* __restrict__ row
                     if (rr[j] < 0) continue;
                     double x[EPC];
                     RowChunk<T>::unpack(v[j], x);
-                    const double wt = s_w[i + j], nrm = s_n[i + j];
+                    const double wt = s_w[i + j], nrm = s_n[i + j], y = DIV ? s_y[i + j] : 0.0;
 #pragma unroll
-                    for (int t = 0; t < EPC; ++t) acc[it][t] = DIV ? fma(wt, x[t] / nrm, acc[it][t]) : fma(x[t], wt, acc[it][t]);
+                    for (int t = 0; t < EPC; ++t)
+                        acc[it][t] = DIV ? fma(wt, div_by_norm(x[t], nrm, y), acc[it][t]) : fma(x[t], wt, acc[it][t]);
                 }
             }
         }
