@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define REBERT_ABI_VERSION 2
+#define REBERT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define REBERT_API __attribute__((visibility("default")))
@@ -123,6 +123,9 @@ typedef struct {
     int32_t proven;      /* 1: margin > bound; 0: not proven — the caller must take an exhaustive route (rebert_collect_above) */
     int32_t used_shadow; /* 1: the result came from the int8 shadow's candidates */
     double  margin;
+    /* where the call's wall time went (host clock, microseconds): packing the request into the pinned block, enqueueing the
+     * kernels, waiting for the completion token (all attempts summed), unpacking the result */
+    double  host_pack_us, host_enqueue_us, host_wait_us, host_unpack_us;
 } rebert_request_info_t;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -209,8 +212,8 @@ REBERT_API int rebert_recommend_device(const rebert_catalog_t* cat, const rebert
 REBERT_API int rebert_recommend_host_scratch(const rebert_catalog_t* cat, int32_t n_liked_cap, int32_t n_exclude_cap, int32_t k,
                                              size_t* pinned_bytes, size_t* device_bytes);
 /* lib.py:43-55 for one request with HOST buffers: pass `query` [d] fp32 (not normalised) OR `liked_rows` (+ optional
- * weights), plus the sorted unique GLOBAL `exclude_rows`; device_filter may add device-resident bitmap / genre / year
- * tests.  The request is packed into the pinned block and read from there by the first kernel (zero-copy, no copy-engine
+ * weights), plus the GLOBAL `exclude_rows` (any order, duplicates allowed: the call sorts and de-duplicates its pinned copy
+ * when the list is not already strictly increasing); device_filter may add device-resident bitmap / genre / year tests.  The request is packed into the pinned block and read from there by the first kernel (zero-copy, no copy-engine
  * operation): a staging kernel normalises the query or builds the profile (mean of the liked rows' unit vectors), then
  * rebert_recommend_device's two chained launches do fused score + mask + top-k and the fp64 exact pass, whose packed
  * result the kernel writes straight into the pinned block; a stream synchronisation ends the call.

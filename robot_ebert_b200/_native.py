@@ -12,7 +12,7 @@ F32, BF16 = 0, 1
 I8 = 2          # prefilter shadow only (rebert_catalog_quantize_i8)
 DTYPES = {"fp32": F32, "bf16": BF16, "i8": I8}
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_DEVICE = 0, -1, -2, -3, -4, -5
 
 
@@ -49,7 +49,8 @@ class Proof(C.Structure):
 
 class RequestInfo(C.Structure):
     _fields_ = [("kc", C.c_int32), ("attempts", C.c_int32), ("proven", C.c_int32), ("used_shadow", C.c_int32),
-                ("margin", C.c_double)]
+                ("margin", C.c_double), ("host_pack_us", C.c_double), ("host_enqueue_us", C.c_double),
+                ("host_wait_us", C.c_double), ("host_unpack_us", C.c_double)]
 
 
 class GemmPlan(C.Structure):

@@ -63,6 +63,9 @@ class _Scratch:
             self.hpin, self.hdev = self._host_scratch(self.nl_cap, self.ne_cap, self.hk_cap)
             self.h_rows = np.empty(self.hk_cap, dtype=np.int64)
             self.h_scores = np.empty(self.hk_cap, dtype=np.float64)
+            # raw addresses / sizes, looked up once: the per-request wrapper is on the latency path of small catalogs
+            self.host_args = (self.hpin.data_ptr(), self.hpin.numel(), self.hdev.data_ptr(), self.hdev.numel())
+            self.out_args = (self.h_rows.ctypes.data, self.h_scores.ctypes.data)
 
     def _host_scratch(self, nl_cap: int, ne_cap: int, k_cap: int):
         lib = nat.load()
@@ -106,8 +109,20 @@ def sorted_unique_i32(rows) -> np.ndarray:
     return ex
 
 
+def _raw_stream(dev_index: int) -> int:
+    """cudaStream_t of torch's current stream on the device (the request path's launches go there)."""
+    return _get_raw_stream(dev_index) if _get_raw_stream is not None else torch.cuda.current_stream(dev_index).cuda_stream
+
+
+# building a torch.cuda.Stream object per request costs ~2 us; torch exposes the raw handle directly (what its own compiled
+# graphs use), with the public API as the fallback
+_get_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 class _on_device:
     """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs ~8 us per request)."""
+
+    __slots__ = ("ctx",)
 
     def __init__(self, dev: torch.device):
         self.ctx = None if torch.cuda.current_device() == (dev.index or 0) else torch.cuda.device(dev)
@@ -203,6 +218,10 @@ class CatalogStore:
         self.fast_eps = float((self.elements_per_lane + 12) * 2.0 ** -24)
         self._c8 = None            # int8 prefilter shadow (enable_prefilter)
         self.q8_eps = float("inf")
+        self._dev_index = self.device.index if self.device.index is not None else 0
+        self._plain_proof = nat.Proof()      # read-only, shared by every request that does not try the shadow
+        self._plain_proof.fast_eps, self._plain_proof.widen = self.fast_eps, 1
+        self._kc_for_k = {}
 
     # ------------------------------------------------------------------ construction -----------
     @staticmethod
@@ -354,7 +373,9 @@ class CatalogStore:
         if query is not None and np.asarray(query).shape != (self.d,):
             raise ValueError(f"query must have shape ({self.d},)")
         lib = nat.load()
-        kc = lib.rebert_candidates_for_k(k)
+        kc = self._kc_for_k.get(k)
+        if kc is None:
+            kc = self._kc_for_k[k] = lib.rebert_candidates_for_k(k)
         if kc == 0:
             # k beyond the register-list kernel (k > 240): threshold bisection + sweep, still exact (rare, slower path)
             rows, scores = self._recommend_large_k(lib, query, liked_rows, weights, exclude_rows, k, row_filter)
@@ -480,15 +501,17 @@ class CatalogStore:
                 if w.shape != lk.shape:
                     raise ValueError("weights must match liked_rows")
         if exclude_rows is not None and len(exclude_rows):
-            ex = sorted_unique_i32(exclude_rows)
+            ex = np.ascontiguousarray(exclude_rows, dtype=np.int32).reshape(-1)     # the C entry sorts / de-duplicates its copy
             ne = int(ex.shape[0])
-        f = self._filter_struct(row_filter)
-        proof = nat.Proof()
-        proof.fast_eps, proof.widen = self.fast_eps, 1
+        f = None if row_filter is None else self._filter_struct(row_filter)
         if shadow_max_k and self._c8 is not None:
+            proof = nat.Proof()
+            proof.fast_eps, proof.widen = self.fast_eps, 1
             proof.shadow = C.pointer(self._c8)
             proof.shadow_eps = self.q8_eps if shadow_eps is None else shadow_eps
             proof.shadow_max_k = shadow_max_k
+        else:
+            proof = self._plain_proof
         cnt, info = C.c_int32(0), nat.RequestInfo()
         # bytes the kernels fetch from / write to the pinned block over PCIe (zero-copy: no copy-engine operation)
         self.last_h2d_bytes = (4 * d if lk is None else 4 * nl * (2 if w is not None else 1)) + 4 * ne
@@ -499,16 +522,17 @@ class CatalogStore:
             rc = lib.rebert_recommend_host(
                 C.byref(self._c), None if q is None else q.ctypes.data, None if lk is None else lk.ctypes.data,
                 None if w is None else w.ctypes.data, nl, None if ex is None else ex.ctypes.data, ne,
-                None if f is None else C.byref(f), k, kc, s.nl_cap, s.ne_cap, s.hpin.data_ptr(), s.hpin.numel(),
-                s.hdev.data_ptr(), s.hdev.numel(), C.byref(proof), None if exchange is None else C.byref(exchange),
-                s.h_rows.ctypes.data, s.h_scores.ctypes.data, C.byref(cnt), C.byref(info),
-                torch.cuda.current_stream().cuda_stream)
+                None if f is None else C.byref(f), k, kc, s.nl_cap, s.ne_cap, *s.host_args,
+                C.byref(proof), None if exchange is None else C.byref(exchange), *s.out_args, C.byref(cnt), C.byref(info),
+                _raw_stream(self._dev_index))
         s.last_attempts = int(info.attempts)         # exchange sequence numbers consumed, also when the call failed (per thread)
         nat.check(rc)
         n = cnt.value
         return s.h_rows[:n].copy(), s.h_scores[:n].copy(), {
             "kc": info.kc, "margin": info.margin, "proven_exact": bool(info.proven), "exact_sweep": False,
-            "prefilter": bool(info.used_shadow), "attempts": info.attempts}
+            "prefilter": bool(info.used_shadow), "attempts": info.attempts,
+            "host_us": {"pack": info.host_pack_us, "enqueue": info.host_enqueue_us, "wait": info.host_wait_us,
+                        "unpack": info.host_unpack_us}}
 
     def _filter_struct(self, row_filter: Optional[RowFilter]):
         """rebert_filter_t for the device-resident predicates of a RowFilter (None when there are none)."""

@@ -145,38 +145,61 @@ __device__ __forceinline__ double exact_score_row_rt(const void* rows, int dtype
     return exact_score_row<__nv_bfloat16, true>((const __nv_bfloat16*)rows, ld, norm64, local_row, qsrc, lane);
 }
 
+// fp64 score -> 64-bit key whose unsigned order is the numeric order (and back).  The two zeros compare equal as numbers, so
+// -0.0 is folded into +0.0 first; key 0 (the image of one NaN pattern no score takes) marks an empty slot.
+__device__ __forceinline__ unsigned long long f64_orderable(double x) {
+    x += 0.0;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_from_orderable(unsigned long long o) {
+    const unsigned long long b = (o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFull) : ~o;
+    return __longlong_as_double((long long)b);
+}
+
 // Rank `kc` re-scored candidates (s_row[c] < 0 = empty slot) by (score desc, row asc): the best k go to o_rows / o_scores
 // (-1 / -inf padded), their number to *o_count.  fast_last = fast score of the worst kept candidate when the fast pass's
 // list was full (list_full): *o_margin = exact k-th - fast_last - err_mult (4) x max|fast - exact| proves the id set when it exceeds the
 // fast pass's error bound; +inf when the list was not full (every allowed row is a candidate), -inf when two distinct
 // scores at or above the k-th place sit within 4 ulp and the caller computed them divide-after (NEARTIE).
 // Every thread of the CTA must call; outputs may be shared, global or device-addressable pinned host memory.
+// s_score is CONSUMED: the scores are replaced in place by their orderable keys, so that the kc x kc comparison pass is integer
+// compares on one shared-memory word per pair.  (Comparing doubles and rows pair by pair made every iteration a chain of two
+// dependent shared loads and fp64 predicates: 22 us for 256 candidates on the request path, as long as the rest of the
+// exact-pass kernel together; profiles/r02_gemv_trace_1p25M.txt.)  Rows are consulted only for exact score ties.
 template <bool NEARTIE>
-__device__ __forceinline__ void rank_candidates(const double* s_score, const int64_t* s_row, int kc, int k, bool list_full, double fast_last,
+__device__ __forceinline__ void rank_candidates(double* s_score, const int64_t* s_row, int kc, int k, bool list_full, double fast_last,
                                                 double maxerr, int64_t* o_rows, double* o_scores, int32_t* o_count,
                                                 double* o_margin, int* s_tmp /* 2 ints of shared scratch, s_tmp[0] = s_tmp[1] = 0 on entry */,
                                                 double* s_kth /* 1 double of shared scratch */, double err_mult = 4.0) {
+    unsigned long long* s_ord = (unsigned long long*)s_score;
+    for (int c = threadIdx.x; c < kc; c += blockDim.x) s_ord[c] = s_row[c] < 0 ? 0ull : f64_orderable(s_score[c]);   // own entries only
+    __syncthreads();
     int valid_mine = 0;
     for (int c = threadIdx.x; c < kc; c += blockDim.x) {
-        const int64_t r = s_row[c];
-        if (r < 0) continue;
+        const unsigned long long oc = s_ord[c];
+        if (oc == 0ull) continue;
         ++valid_mine;
-        const double sc = s_score[c];
-        int rank = 0;
+        int gt = 0, eq = 0;
         bool near = false;
+#pragma unroll 8
         for (int j = 0; j < kc; ++j) {
-            const int64_t rj = s_row[j];
-            if (rj < 0) continue;
-            const double sj = s_score[j];
-            if (better(sj, rj, sc, r)) ++rank;
+            const unsigned long long oj = s_ord[j];
+            gt += oj > oc;
+            eq += oj == oc;
             if (NEARTIE) {
-                const double gap = fabs(sj - sc);
-                near |= gap != 0.0 && gap <= 8.9e-16 * fmax(fabs(sc), 1e-300);   // distinct scores within 4 ulp
+                const unsigned long long dist = oj > oc ? oj - oc : oc - oj;      // distance in representable doubles
+                near |= (dist - 1ull) < 4ull;                                      // distinct scores within 4 ulp
             }
         }
+        const int64_t r = s_row[c];
+        int rank = gt;
+        if (eq > 1)                                                                // exact ties (itself included): ascending row
+            for (int j = 0; j < kc; ++j) rank += (s_ord[j] == oc && s_row[j] < r);
         if (NEARTIE && near && rank <= k) s_tmp[1] = 1;    // a divide-after formula cannot be trusted to order these
         REBERT_ASSERT(rank >= 0 && rank < kc);
         if (rank < k) {
+            const double sc = f64_from_orderable(oc);
             o_rows[rank] = r;
             o_scores[rank] = sc;
             if (rank == k - 1) *s_kth = sc;

@@ -89,6 +89,7 @@ struct FinalizeParams {
     int x_ld, x_dtype;
     int64_t row_base, x_n;
     int k, cap;
+    int split_select;          // 1: winner selection spread over the cluster (long candidate lists), 0: every CTA on its own
     unsigned long long* out_packed;
     uint32_t tag;
     uint32_t* done_flag;       // pinned host word the host polls instead of synchronising the stream (or nullptr)
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     unsigned long long* s_block = s_werr + kFinalCluster * (kFinalClusterThreads / 32);   // [2 k + 2] local result (row shards)
     unsigned long long* s_all = s_block + 2 * k + 2;                   // [world][2 k + 2] every rank's result (row shards)
     __shared__ int s_tmp[2];
+    __shared__ int s_total;                          // survivors pushed into this CTA's buf (select_winners_cluster)
     __shared__ double s_kth;
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     // comes after the exchange.
     const bool exchange = p.xchg.world > 1;
     if (!exchange) pdl_trigger();
-    if (threadIdx.x == 0) { s_tmp[0] = 0; s_tmp[1] = 0; }
+    if (threadIdx.x == 0) { s_tmp[0] = 0; s_tmp[1] = 0; s_total = 0; }
     cluster.sync();                                  // every CTA of the cluster is running: its shared memory may be addressed.
                                                      // Done HERE, while the stream is still running, it costs nothing.
     pdl_wait();                                      // the keys come from the streaming kernel launched just before
@@ -144,7 +146,10 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
         const int i = threadIdx.x + j * kFinalClusterThreads;
         qv[j] = i < p.x_ld ? __ldg(p.q64 + i) : 0.0;
     }
-    select_winners<24>(p.pub.keys, p.cap, buf, fk, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
+    if (p.split_select)      // fk | s_score | s_row = 3 kc words that are free until the winners are known
+        select_winners_cluster<24, kFinalCluster>(cluster, p.pub.keys, p.cap, buf, fk, fk, &s_total, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
+    else
+        select_winners<24>(p.pub.keys, p.cap, buf, fk, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
     {
         const int chunks = p.x_ld / epc;
 #pragma unroll
@@ -227,6 +232,16 @@ int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t 
     int cap = 1024;
     while (cap < need) cap <<= 1;
     p.cap = cap;
+    // Long candidate lists (kc >= 128: k > 16, the int8 shadow, a widened retry) publish tens of thousands of keys: the cluster
+    // shares the scan and the ordering (merge.cuh).  Short lists fit one round of loads per CTA and skip the two extra
+    // cluster barriers.  REBERT_FIN_SPLIT=0/1 forces either way (tools).
+    {
+        static const int forced = [] { const char* e = getenv("REBERT_FIN_SPLIT"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+        int want = forced;
+        if (getenv("REBERT_GEMV_TUNE")) { const char* e = getenv("REBERT_FIN_SPLIT"); want = e ? (e[0] == '0' ? 0 : 1) : -1; }
+        const bool can = 3 * pub.keys.kc >= pub.keys.kc + pub.keys.lists;          // the list heads must fit the 3 kc staging words
+        p.split_select = (want < 0 ? pub.keys.kc >= 128 : want == 1) && can ? 1 : 0;
+    }
     p.out_packed = f.out_packed;
     p.tag = f.tag;
     p.done_flag = f.done_flag;

@@ -833,7 +833,10 @@ int gemv_launch(const rebert_catalog_t* cat, const float* qn32, const rebert_fil
         const int dyn_pct = knobs.dyn_pct;
         const int64_t rounds = (p.num_tiles + g.grid - 1) / g.grid;       // static schedule would need this many
         int64_t sr = rounds - (rounds * dyn_pct + 99) / 100;
-        if (dyn_pct == 0) sr = rounds;
+        // Each CTA keeps four claims in flight from its first instruction on, so a dynamic tail shorter than a few rounds is
+        // swallowed by the CTAs that start first (2264 x 1536: 34 CTAs took all 136 tail tiles and finished 5 us after the
+        // rest).  Short launches are dealt out statically.
+        if (dyn_pct == 0 || rounds - sr < 8) sr = rounds;
         if (sr < 1) sr = 1;                                               // the first tile is always blockIdx.x
         p.static_rounds = sr;
     }

@@ -9,6 +9,7 @@
 // callers only need their own scratch + stream (+ their own exchange channel on a row shard).
 #include <stdlib.h>
 
+#include <algorithm>
 #include <chrono>
 
 #include "exchange.cuh"
@@ -38,6 +39,10 @@ static bool poll_done(const volatile uint32_t* flag, uint32_t token) {
         }
         if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) return false;
     }
+}
+
+static double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -132,6 +137,7 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
                   device_bytes, L.dev_bytes);
         return REBERT_ERR_WORKSPACE;
     }
+    const double t_entry = now_us();
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* h = (unsigned char*)pinned;
     unsigned char* dv = (unsigned char*)device_scratch;
@@ -154,7 +160,18 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
     *err_word = 0;
 
     // ---- the request goes into the pinned block; the kernels read it from there
-    if (n_exclude) memcpy(h + L.off_excl, exclude_rows, (size_t)n_exclude * 4);
+    if (n_exclude) {
+        // the kernels binary-search the exclusions: the pinned copy is made strictly increasing here if it is not already
+        int32_t* e = (int32_t*)(h + L.off_excl);
+        memcpy(e, exclude_rows, (size_t)n_exclude * 4);
+        bool increasing = true;
+        for (int32_t i = 1; i < n_exclude; ++i)
+            if (e[i] <= e[i - 1]) { increasing = false; break; }
+        if (!increasing) {
+            std::sort(e, e + n_exclude);
+            n_exclude = (int32_t)(std::unique(e, e + n_exclude) - e);
+        }
+    }
     if (query) {
         memcpy(h + L.off_q, query, (size_t)cat->d * 4);
     } else {
@@ -169,15 +186,19 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
     rebert_request_info_t inf;
     memset(&inf, 0, sizeof(inf));
     auto finish = [&]() {
+        const double t_u = now_us();
         const int32_t cnt = (int32_t)(uint32_t)res[2 * (size_t)k];
         memcpy(out_rows, res, (size_t)k * 8);
         memcpy(out_scores, res + k, (size_t)k * 8);
         *out_count = cnt;
         memcpy(&inf.margin, res + 2 * (size_t)k + 1, 8);
-        if (info) *info = inf;
         *in_flight = 0;
+        inf.host_unpack_us = now_us() - t_u;
+        if (info) *info = inf;
     };
 
+    double t_mark = now_us();
+    inf.host_pack_us = t_mark - t_entry;
     // ---- staging kernel: normalised query, or the profile (with the partial-profile exchange on a row shard)
     uint32_t seq = sharded ? exchange->seq : 0;
     Exchange x;
@@ -201,7 +222,7 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
     f.exclude_rows = n_exclude ? excl_dev : nullptr;
     f.n_exclude = n_exclude;
     const uint32_t tag = sharded ? request_tag(query ? (const void*)query : (const void*)liked_rows,
-                                               query ? (size_t)cat->d * 4 : (size_t)n_liked * 4, exclude_rows, (size_t)n_exclude * 4,
+                                               query ? (size_t)cat->d * 4 : (size_t)n_liked * 4, excl_host, (size_t)n_exclude * 4,
                                                liked_w, liked_w ? (size_t)n_liked * 4 : 0, ((uint64_t)k << 32) | (uint32_t)n_liked)
                                  : 0u;
 
@@ -235,7 +256,11 @@ REBERT_API int rebert_recommend_host(const rebert_catalog_t* cat, const float* q
         const int use_kc = shadow_turn ? 256 : cur_kc;
         rc = gemv_launch(shadow_turn ? proof->shadow : cat, qn32, &f, use_kc, dv + L.off_ws, L.ws_bytes, nullptr, &gf, st);
         if (rc != REBERT_OK) return rc;
+        const double t_enq = now_us();
+        inf.host_enqueue_us += t_enq - t_mark;
         if (!poll || !poll_done(done_flag, gf.done_token)) REBERT_CUDA(cudaStreamSynchronize(st));
+        t_mark = now_us();
+        inf.host_wait_us += t_mark - t_enq;
         ++inf.attempts;
         ++seq;
         if (*err_word != 0) {

@@ -55,6 +55,34 @@ __device__ __forceinline__ unsigned long long merge_timer_ns() {
 }
 #define MERGE_TRACE(slot) do { if (tr && threadIdx.x == 0) tr[(slot)] = merge_timer_ns(); } while (0)
 
+// Mass ties (more keys within the threshold than any buffer holds): merge everything that was published, region by region,
+// into the running best kc.  Correct for any input, slow.  rtot: keys per region (shared memory); all threads call.
+__device__ inline void merge_all_regions(const PublishedKeys& pub, const unsigned* rtot, int cap, uint64_t* buf, uint64_t* out) {
+    const int kc = pub.kc;
+    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = 0;
+    __syncthreads();
+    for (int r = 0; r < kPubRegions; ++r) {
+        int tot = (int)rtot[r];
+        if (tot > pub.region_cap) tot = pub.region_cap;
+        // merge region r into the running best kc: buf = [out (kc) | region chunk]
+        int done = 0;
+        while (done < tot) {
+            int take = tot - done;
+            if (take > cap - kc) take = cap - kc;
+            for (int i = threadIdx.x; i < kc; i += blockDim.x) buf[i] = out[i];
+            for (int i = threadIdx.x; i < take; i += blockDim.x) buf[kc + i] = ldcg_u64(pub.keys + (size_t)r * pub.region_cap + done + i);
+            int p2 = 2;
+            while (p2 < kc + take) p2 <<= 1;
+            for (int i = kc + take + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
+            __syncthreads();
+            block_bitonic_sort_desc(buf, p2);
+            for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
+            __syncthreads();
+            done += take;
+        }
+    }
+}
+
 template <int INFLIGHT>
 __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_t* buf, uint64_t* out, unsigned long long* tr = nullptr) {
     __shared__ unsigned long long s_t0, s_t1;
@@ -139,28 +167,7 @@ __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_
     MERGE_TRACE(2);                                 // survivors gathered
     const int cnt = s_cnt;
     if (cnt > cap) {                               // mass ties: correct but slow path over everything that was published
-        for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = 0;
-        __syncthreads();
-        for (int r = 0; r < kPubRegions; ++r) {
-            int tot = (int)s_rtot[r];
-            if (tot > pub.region_cap) tot = pub.region_cap;
-            // merge region r into the running best kc: buf = [out (kc) | region chunk]
-            int done = 0;
-            while (done < tot) {
-                int take = tot - done;
-                if (take > cap - kc) take = cap - kc;
-                for (int i = threadIdx.x; i < kc; i += blockDim.x) buf[i] = out[i];
-                for (int i = threadIdx.x; i < take; i += blockDim.x) buf[kc + i] = ldcg_u64(pub.keys + (size_t)r * pub.region_cap + done + i);
-                int p2 = 2;
-                while (p2 < kc + take) p2 <<= 1;
-                for (int i = kc + take + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
-                __syncthreads();
-                block_bitonic_sort_desc(buf, p2);
-                for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
-                __syncthreads();
-                done += take;
-            }
-        }
+        merge_all_regions(pub, s_rtot, cap, buf, out);
         return;
     }
     if (cnt <= 512) {
@@ -183,6 +190,143 @@ __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_
     block_bitonic_sort_desc(buf, p2);
     for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
     __syncthreads();
+}
+
+// The same selection spread over the CTAs of a thread-block cluster (the request path's exact-pass kernel, long candidate
+// lists).  With kc = 128 / 256 the streaming kernel publishes 19k / 38k keys; every CTA scanning all of them took 7 rounds of
+// L2 loads (25 us at kc = 256) and the survivors (> 512) a block-wide bitonic sort (9 us).  Here
+//   (1) every CTA finds the threshold T from the list heads and tails (redundant: ~300 keys),
+//   (2) CTA c scans only its kPubRegions / CSIZE regions — one round of loads — and keeps the keys >= T,
+//   (3) pushes its survivors into EVERY CTA's `buf` through distributed shared memory (one remote atomic per target reserves
+//       the range), cluster barrier,
+//   (4) ranks its 1/CSIZE slice of the survivors against all of them (4 threads per survivor) and stores each winner at its
+//       rank into every CTA's `out`, cluster barrier.
+// stage: 3 kc keys of scratch that nothing else uses until the winners are known (heads first, then the local survivors);
+// `out` may be its first kc entries.  s_total: one int per CTA, zero before a cluster barrier that precedes this call.
+// Falls back to merge_all_regions (every CTA, redundantly) when the survivors overflow `buf` or a CTA's stage.
+template <int INFLIGHT, int CSIZE, typename Cluster>
+__device__ inline void select_winners_cluster(Cluster& cluster, const PublishedKeys& pub, int cap, uint64_t* buf, uint64_t* stage, uint64_t* out,
+                                              int* s_total, unsigned long long* tr = nullptr) {
+    static_assert(kPubRegions % CSIZE == 0, "regions must divide over the cluster");
+    constexpr int RPC = kPubRegions / CSIZE;        // regions scanned by one CTA
+    __shared__ unsigned long long s_t0, s_t1;
+    __shared__ int s_cnt;
+    __shared__ unsigned s_rtot[kPubRegions];
+    __shared__ int s_base[CSIZE];
+    const int crank = (int)cluster.block_rank();
+    const int kc = pub.kc, lists = pub.lists;
+    const int S = pub.P * lists;                    // kc <= S < kc + lists <= 3 kc (the caller checks)
+    const int stage_cap = 3 * kc;
+    if (threadIdx.x == 0) { s_t0 = 0; s_t1 = 0; s_cnt = 0; }
+    if (threadIdx.x < kPubRegions) s_rtot[threadIdx.x] = __ldcg(pub.cursors + threadIdx.x);
+    unsigned long long t0 = 0;
+    for (int l = threadIdx.x; l < lists; l += blockDim.x) {
+        const unsigned long long v = ldcg_u64(pub.tails + l);
+        t0 = v > t0 ? v : t0;
+    }
+    for (int e = threadIdx.x; e < S; e += blockDim.x) stage[e] = ldcg_u64(pub.heads + e);
+    // optimistic batch over this CTA's regions, flattened like select_winners: slot s = entry (s / (32 RPC)) * 32 + s % 32 of
+    // region crank * RPC + (s / 32) % RPC
+    uint64_t kk[INFLIGHT];
+    const int per_round = INFLIGHT * (int)blockDim.x;
+#pragma unroll
+    for (int j = 0; j < INFLIGHT; ++j) {
+        const int sidx = threadIdx.x + j * blockDim.x;
+        const int r = crank * RPC + (sidx >> 5) % RPC, e = (sidx / (32 * RPC)) * 32 + (sidx & 31);
+        kk[j] = e < pub.region_cap ? ldcg_u64(pub.keys + (size_t)r * pub.region_cap + e) : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, t0, o);
+        t0 = v > t0 ? v : t0;
+    }
+    if ((threadIdx.x & 31) == 0 && t0) atomicMax(&s_t0, t0);
+    __syncthreads();
+    MERGE_TRACE(0);                                 // heads / tails landed
+    for (int e = threadIdx.x; e < S; e += blockDim.x) {
+        const uint64_t key = stage[e];
+        if (key == 0) continue;
+        int rank = 0;
+        for (int j = 0; j < S; ++j) rank += stage[j] > key;
+        if (rank == kc - 1) s_t1 = key;
+    }
+    __syncthreads();
+    const uint64_t T = s_t0 > s_t1 ? s_t0 : s_t1;
+    unsigned max_tot = 0;
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) max_tot = max(max_tot, s_rtot[crank * RPC + r]);
+    if ((int)max_tot > pub.region_cap) max_tot = (unsigned)pub.region_cap;
+    const int slots = (((int)max_tot + 31) / 32) * 32 * RPC;
+    __syncthreads();                                // the heads are dead: `stage` now collects this CTA's survivors
+    MERGE_TRACE(1);                                 // threshold known
+    for (int base = 0; base < slots; base += per_round) {
+        if (base > 0) {
+#pragma unroll
+            for (int j = 0; j < INFLIGHT; ++j) {
+                const int sidx = base + threadIdx.x + j * blockDim.x;
+                const int r = crank * RPC + (sidx >> 5) % RPC, e = (sidx / (32 * RPC)) * 32 + (sidx & 31);
+                kk[j] = (sidx < slots && e < (int)s_rtot[r]) ? ldcg_u64(pub.keys + (size_t)r * pub.region_cap + e) : 0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < INFLIGHT; ++j) {
+            const int sidx = base + threadIdx.x + j * blockDim.x;
+            const int r = crank * RPC + (sidx >> 5) % RPC, e = (sidx / (32 * RPC)) * 32 + (sidx & 31);
+            const bool keep = e < (int)s_rtot[r] && e < pub.region_cap && kk[j] >= T && kk[j] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                const int lane_ = threadIdx.x & 31;
+                int wbase = 0;
+                if (lane_ == 0) wbase = atomicAdd(&s_cnt, __popc(m));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                const int idx = wbase + __popc(m & ((1u << lane_) - 1u));
+                if (keep && idx < stage_cap) stage[idx] = kk[j];
+            }
+        }
+    }
+    __syncthreads();
+    const int mine = s_cnt;
+    const bool overflow = mine > stage_cap;
+    // reserve this CTA's range in every CTA's buf (an overflowing CTA poisons the totals: everybody takes the slow path)
+    if (threadIdx.x < CSIZE) s_base[threadIdx.x] = atomicAdd(cluster.map_shared_rank(s_total, threadIdx.x), overflow ? cap + 1 : mine);
+    __syncthreads();
+    if (!overflow) {
+        for (int t = 0; t < CSIZE; ++t) {
+            uint64_t* rbuf = cluster.map_shared_rank(buf, t);
+            const int b0 = s_base[t];
+            for (int i = threadIdx.x; i < mine; i += blockDim.x)
+                if (b0 + i < cap) rbuf[b0 + i] = stage[i];
+        }
+    }
+    cluster.sync();                                 // every CTA's survivors are in every CTA's buf (and every stage is dead)
+    MERGE_TRACE(2);                                 // survivors gathered
+    const int total = *s_total;
+    if (total > cap) {
+        merge_all_regions(pub, s_rtot, cap, buf, out);
+        return;
+    }
+    for (int i = total + threadIdx.x; i < kc; i += blockDim.x) out[i] = 0;
+    // rank counting, 4 threads per survivor (keys are distinct: ranks are a permutation).  Each CTA ranks the survivors it
+    // gathered itself — the range it reserved in its OWN buf.  (The arrival order of the pushes differs from CTA to CTA, so a
+    // position-based split of buf would not partition the survivors.)
+    const int lo = s_base[crank];
+    const int len = mine;
+    const int g = threadIdx.x >> 2, sub = threadIdx.x & 3, groups = (int)blockDim.x >> 2;
+    for (int b0 = 0; b0 < len; b0 += groups) {      // trip count uniform over the CTA: the shuffles below need whole warps
+        const int ii = b0 + g;
+        const bool live = ii < len;
+        const uint64_t key = live ? buf[lo + ii] : ~0ull;
+        int rank = 0;
+        for (int j = sub; j < total; j += 4) rank += buf[j] > key;
+        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+        rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+        if (live && sub == 0 && rank < kc) {
+            REBERT_ASSERT(key != 0);
+#pragma unroll
+            for (int t = 0; t < CSIZE; ++t) cluster.map_shared_rank(out, t)[rank] = key;
+        }
+    }
+    cluster.sync();                                 // the winners are in every CTA's out
 }
 
 }  // namespace rebert

@@ -243,3 +243,35 @@ def test_int8_batched_profiles_with_predicate_vs_oracle():
         want_rows, want_scores = ora.recommend_rows(m, lc[u], ec[u], k, keep_mask=keep)
         np.testing.assert_array_equal(rows[u, :counts[u]], want_rows, err_msg=f"user {u} status {info['status'][u]}")
         np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
+
+
+def test_int8_filter_with_accumulators_beyond_the_fast_conversion_range():
+    """Rows and queries of +-1 entries quantise to +-127 everywhere, so the int32 accumulators reach 1536 * 127^2 = 24.8M: far outside
+    the +-2^22 range in which the filter's pipe-friendly int->float conversion is exact.  Outside it the conversion only ever
+    over-estimates, and staged winners are re-converted exactly — the results must still equal the bf16 path's and the oracle's."""
+    n, d, b, k = 70_000, 1536, 140, 10
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 2, size=(b, d)).astype(np.float32) * 2 - 1
+    m = rng.integers(0, 2, size=(n, d)).astype(np.float32) * 2 - 1
+    for u in range(b):                                         # plant near-copies of every query: high positive accumulators
+        for j in range(12):
+            r = (u * 12 + j) * 37 % n
+            flips = rng.choice(d, size=8 * (j + 1), replace=False)
+            m[r] = base[u]
+            m[r, flips] *= -1
+    m[5] = -base[0]                                            # and a strongly negative one
+    store = CatalogStore.from_host(None, m, dtype="bf16")
+    store.enable_prefilter()
+    assert store.batch_shadow_ok
+    r8, s8, c8, i8 = store.recommend_batch(queries=base, k=k, return_info=True, prefilter=True)
+    rb, sb, cb, ib = store.recommend_batch(queries=base, k=k, return_info=True, prefilter=False)
+    assert i8["int8_operands"]
+    np.testing.assert_array_equal(r8, rb)
+    np.testing.assert_array_equal(s8, sb)
+    m64 = m.astype(np.float64)
+    unit = m64 / np.linalg.norm(m64, axis=1, keepdims=True)
+    for u in range(0, b, 9):
+        qn = base[u].astype(np.float64) / np.linalg.norm(base[u].astype(np.float64))
+        want_rows, want_scores = ora.topk_rows(unit @ qn, k, np.zeros(0, dtype=np.int64))
+        np.testing.assert_array_equal(r8[u, :c8[u]], want_rows, err_msg=f"query {u} status {i8['status'][u]}")
+        np.testing.assert_allclose(s8[u, :c8[u]], want_scores, rtol=1e-9, atol=1e-15)

@@ -210,7 +210,7 @@ def test_concurrent_requests_from_threads():
     assert not errors, errors
 
 
-@pytest.mark.parametrize("n,d,k", [(624, 1, 1), (3000, 1, 10), (5000, 2, 25)])
+@pytest.mark.parametrize("n,d,k", [(624, 1, 1), (3000, 1, 10), (5000, 2, 25), (40_000, 2, 100)])
 def test_mass_ties_are_resolved_by_the_exact_sweep(n, d, k):
     """Hundreds of rows tie EXACTLY in float64 (d = 1: every cosine is +-1; d = 2: rows on a few rays) but not in fp32.
     No candidate list can prove that; the exact sweep must, and the row-ascending tie-break must hold."""
@@ -318,16 +318,17 @@ for n, d, dtype, k in [(70_001, 1536, "bf16", 10), (70_001, 1536, "bf16", 100), 
     keys, fused = {}, {}
     for hint in ("0", "1"):
         for dyn in ("0", "12", "50", "100"):
-            for stages, prune, early in (("2", "1", "1"), ("4", "1", "1"), ("4", "0", "1"), ("4", "1", "0"), ("3", "0", "0")):
+            for stages, prune, early, split in (("2", "1", "1", "1"), ("4", "1", "1", "0"), ("4", "0", "1", "1"), ("4", "1", "0", "0"),
+                                                ("3", "0", "0", "1")):
                 os.environ.update(REBERT_GEMV_CTA_HINT=hint, REBERT_GEMV_DYN_PCT=dyn, REBERT_GEMV_STAGES=stages,
-                                  REBERT_GEMV_MERGE_PRUNE=prune, REBERT_GEMV_EARLY_TMA=early)
+                                  REBERT_GEMV_MERGE_PRUNE=prune, REBERT_GEMV_EARLY_TMA=early, REBERT_FIN_SPLIT=split)
                 for _ in range(3):                              # repeated launches: the counters must be left at zero
                     nat.check(lib.rebert_gemv_topk(C.byref(store._c), s.qn32.data_ptr(), C.byref(f), kc, s.ws.data_ptr(),
                                                    s.ws.numel(), s.cand.data_ptr(), torch.cuda.current_stream().cuda_stream))
-                keys[(hint, dyn, stages, prune, early)] = s.cand.cpu().numpy().copy()
+                keys[(hint, dyn, stages, prune, early, split)] = s.cand.cpu().numpy().copy()
                 for _ in range(2):                              # the one-launch request path (exact pass in the kernel's tail)
                     store.enqueue_fused(k, kc, ptr, ne)
-                fused[(hint, dyn, stages, prune, early)] = s.d_out.cpu().numpy().copy()
+                fused[(hint, dyn, stages, prune, early, split)] = s.d_out.cpu().numpy().copy()
     first = next(iter(keys.values()))
     ffirst = next(iter(fused.values()))
     store.enqueue_topk(k, kc, ptr, ne)                           # two-kernel form: gemv_topk -> finalize_topk
@@ -347,7 +348,7 @@ _KNOB_DIGESTS = {}
 @pytest.mark.parametrize("pdl", ["1", "0"])
 def test_scheduling_knobs_change_speed_never_results(pdl):
     """Threshold hints, the static / dynamically claimed tile schedule, the pipeline depth, hint pruning in the CTA merge,
-    early TMA issue and programmatic dependent launch are speed knobs: the candidate keys — and the packed result of the
+    early TMA issue, the cluster-wide winner selection of long candidate lists and programmatic dependent launch are speed knobs: the candidate keys — and the packed result of the
     one-launch request path, which must also equal the two-kernel form bit for bit — are identical under every combination
     (own process: the library reads its knobs at the first launch)."""
     import json

@@ -5,7 +5,7 @@
 traced instead (rebert_recommend_device) and the cluster kernel behind the streaming kernel adds its own stamps
 (REBERT_FIN_TRACE): 0 entry, 1 streaming kernel complete, 2 winners selected, 3 exact scores in CTA 0, 4 ranked, 5 end.
 Prints the spread of every stamp relative to the earliest kernel entry, for a few launches back to back, beside the
-CUDA-event time of the same launches.   trace_gemv.py <rows> <k> [i8] [fused]"""
+CUDA-event time of the same launches.   trace_gemv.py <rows> <k> [i8] [fused] [dim=D] [fp32]"""
 import ctypes as C, json, os, sys
 os.environ["REBERT_GEMV_TUNE"] = "1"          # make the library re-read its knobs at every launch
 import numpy as np
@@ -18,8 +18,10 @@ K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 I8 = "i8" in sys.argv[3:]                                  # trace the int8 prefilter shadow's fast pass (kc = 256)
 FUSED = "fused" in sys.argv[3:]                            # the one-launch request path (exact pass in the kernel's tail)
 lib = nat.load(); dev = torch.device("cuda:0")
-store = CatalogStore.synthetic(0, n, 1536, "bf16", device=dev)
-q = synth.query_f32(1, 1536); excl = np.random.default_rng(1).choice(n, size=133, replace=False)
+D = next((int(a[4:]) for a in sys.argv[3:] if a.startswith("dim=")), 1536)
+DT = "fp32" if "fp32" in sys.argv[3:] else "bf16"
+store = CatalogStore.synthetic(0, n, D, DT, device=dev)
+q = synth.query_f32(1, D); excl = np.random.default_rng(1).choice(n, size=min(133, n // 4), replace=False)
 kc = 256 if I8 else lib.rebert_candidates_for_k(K)
 if I8:
     store.enable_prefilter()
@@ -61,13 +63,16 @@ fnames = ["entry", "stream_complete", "winners_selected", "exact_in_cta0", "rank
 prev_end = None
 for i in range(L):
     t = bufs[i].cpu().numpy().reshape(sms + 1, 8)
-    t0 = t[:sms, 0].min()
-    row = {"launch": i}
+    live = np.nonzero(t[:sms, 0])[0]                      # a small catalog launches fewer CTAs than SMs
+    t0 = t[live, 0].min()
+    row = {"launch": i, "ctas": int(len(live))}
     if prev_end is not None:
         row["gap_from_prev_end_us"] = round((t0 - prev_end) / 1e3, 2)
     for j, nm in enumerate(names):
-        v = (t[:sms, j] - t0) / 1e3
+        v = (t[live, j] - t0) / 1e3
         row[nm] = [round(float(v.min()), 2), round(float(np.median(v)), 2), round(float(v.max()), 2)]
+    slow = live[np.argmax(t[live, 5])]
+    row["slowest_cta"] = {"block": int(slow), "stamps": [round(float(x - t0) / 1e3, 2) for x in t[slow, :6]]}
     if FUSED:
         ft = fbufs[i].cpu().numpy()
         row["cluster_kernel"] = {nm: round(float(ft[j] - t0) / 1e3, 2) for j, nm in enumerate(fnames)}
