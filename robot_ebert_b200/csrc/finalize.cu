@@ -89,6 +89,7 @@ struct FinalizeParams {
     int x_ld, x_dtype;
     int64_t row_base, x_n;
     int k, cap;
+    int stage_words;           // words from fk on that are free until the winners are known: max(3 kc, heads of every list)
     int split_select;          // 1: winner selection spread over the cluster (long candidate lists), 0: every CTA on its own
     unsigned long long* out_packed;
     uint32_t tag;
@@ -104,6 +105,10 @@ __device__ __forceinline__ unsigned long long ftimer_ns() {
 }
 #define FIN_TRACE(slot) do { if (p.pub.trace && threadIdx.x == 0 && crank == 0) p.pub.trace[(slot)] = ftimer_ns(); } while (0)
 
+// SPLIT: winner selection spread over the cluster (long candidate lists); XCHG: row shard, NVLink exchange + merge at the end.
+// Four instantiations instead of run-time branches: this kernel runs once per request with a cold instruction cache, and
+// every variant it does not need (each one thousands of unrolled instructions) would sit between the ones it does.
+template <bool SPLIT, bool XCHG>
 __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_kernel(const FinalizeParams p) {
     extern __shared__ __align__(16) unsigned char fsm[];
     const int kc = p.pub.keys.kc, k = p.k;
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     uint64_t* fk = buf + p.cap;                                        // [kc] winners, best fast score first
     double* s_score = (double*)(fk + kc);                              // [kc]   (filled remotely in CTA 0)
     int64_t* s_row = (int64_t*)(s_score + kc);                         // [kc]
-    unsigned long long* s_werr = (unsigned long long*)(s_row + kc);    // [cluster warps] largest |fast - exact| per warp
+    unsigned long long* s_werr = (unsigned long long*)(fk + p.stage_words);   // [cluster warps] largest |fast - exact| per warp
     unsigned long long* s_block = s_werr + kFinalCluster * (kFinalClusterThreads / 32);   // [2 k + 2] local result (row shards)
     unsigned long long* s_all = s_block + 2 * k + 2;                   // [world][2 k + 2] every rank's result (row shards)
     __shared__ int s_tmp[2];
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     // blocked behind this kernel, while the peer — in the mirrored state on another channel — needs exactly those SMs to
     // produce what this kernel waits for (deadlock across ranks with concurrent channels).  So on a row shard the trigger
     // comes after the exchange.
-    const bool exchange = p.xchg.world > 1;
+    constexpr bool exchange = XCHG;
     if (!exchange) pdl_trigger();
     if (threadIdx.x == 0) { s_tmp[0] = 0; s_tmp[1] = 0; s_total = 0; }
     cluster.sync();                                  // every CTA of the cluster is running: its shared memory may be addressed.
@@ -146,10 +151,10 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
         const int i = threadIdx.x + j * kFinalClusterThreads;
         qv[j] = i < p.x_ld ? __ldg(p.q64 + i) : 0.0;
     }
-    if (p.split_select)      // fk | s_score | s_row = 3 kc words that are free until the winners are known
-        select_winners_cluster<24, kFinalCluster>(cluster, p.pub.keys, p.cap, buf, fk, fk, &s_total, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
+    if (SPLIT)               // fk | s_score | s_row = 3 kc words that are free until the winners are known
+        select_winners_cluster<24, kFinalCluster, kFinalClusterThreads>(cluster, p.pub.keys, p.cap, buf, fk, p.stage_words, fk, &s_total, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
     else
-        select_winners<24>(p.pub.keys, p.cap, buf, fk, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
+        select_winners<24, kFinalClusterThreads>(p.pub.keys, p.cap, buf, fk, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
     {
         const int chunks = p.x_ld / epc;
 #pragma unroll
@@ -239,17 +244,19 @@ int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t 
         static const int forced = [] { const char* e = getenv("REBERT_FIN_SPLIT"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
         int want = forced;
         if (getenv("REBERT_GEMV_TUNE")) { const char* e = getenv("REBERT_FIN_SPLIT"); want = e ? (e[0] == '0' ? 0 : 1) : -1; }
-        const bool can = 3 * pub.keys.kc >= pub.keys.kc + pub.keys.lists;          // the list heads must fit the 3 kc staging words
-        p.split_select = (want < 0 ? pub.keys.kc >= 128 : want == 1) && can ? 1 : 0;
+        p.split_select = (want < 0 ? pub.keys.kc >= 128 : want == 1) ? 1 : 0;
     }
+    p.stage_words = 3 * pub.keys.kc > pub.keys.kc + pub.keys.lists ? 3 * pub.keys.kc : pub.keys.kc + pub.keys.lists;
     p.out_packed = f.out_packed;
     p.tag = f.tag;
     p.done_flag = f.done_flag;
     p.done_token = f.done_token;
     if (f.xchg) p.xchg = *f.xchg;
-    const size_t smem = (size_t)p.x_ld * 8 + (size_t)cap * 8 + (size_t)pub.keys.kc * 24 + (size_t)kFinalCluster * (kFinalClusterThreads / 32) * 8 +
+    const size_t smem = (size_t)p.x_ld * 8 + (size_t)cap * 8 + (size_t)p.stage_words * 8 + (size_t)kFinalCluster * (kFinalClusterThreads / 32) * 8 +
                         (size_t)(2 * f.k + 2) * 8 * (1 + (f.xchg ? f.xchg->world : 0));
-    auto kern = finalize_published_kernel;
+    const bool xchg = p.xchg.world > 1;
+    auto kern = p.split_select ? (xchg ? finalize_published_kernel<true, true> : finalize_published_kernel<true, false>)
+                               : (xchg ? finalize_published_kernel<false, true> : finalize_published_kernel<false, false>);
     { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

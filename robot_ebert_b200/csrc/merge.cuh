@@ -57,7 +57,7 @@ __device__ __forceinline__ unsigned long long merge_timer_ns() {
 
 // Mass ties (more keys within the threshold than any buffer holds): merge everything that was published, region by region,
 // into the running best kc.  Correct for any input, slow.  rtot: keys per region (shared memory); all threads call.
-__device__ inline void merge_all_regions(const PublishedKeys& pub, const unsigned* rtot, int cap, uint64_t* buf, uint64_t* out) {
+static __device__ void merge_all_regions(const PublishedKeys& pub, const unsigned* rtot, int cap, uint64_t* buf, uint64_t* out) {
     const int kc = pub.kc;
     for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = 0;
     __syncthreads();
@@ -83,11 +83,25 @@ __device__ inline void merge_all_regions(const PublishedKeys& pub, const unsigne
     }
 }
 
-template <int INFLIGHT>
+// More than 512 survivors (rare): pad to a power of two, bitonic sort, keep the best kc.  Out of line: cold code.
+static __device__ void sort_survivors(uint64_t* buf, int cnt, int kc, uint64_t* out) {
+    int p2 = 2;
+    while (p2 < cnt || p2 < kc) p2 <<= 1;
+    for (int i = cnt + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
+    __syncthreads();
+    block_bitonic_sort_desc(buf, p2);
+    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
+    __syncthreads();
+}
+
+// THREADS: the block size when the caller knows it at compile time (the slot arithmetic below then folds into shifts and masks —
+// a third of this function's instructions otherwise), 0 = read blockDim.x.
+template <int INFLIGHT, int THREADS = 0>
 __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_t* buf, uint64_t* out, unsigned long long* tr = nullptr) {
     __shared__ unsigned long long s_t0, s_t1;
     __shared__ int s_cnt;
     __shared__ unsigned s_rtot[kPubRegions];
+    const int nthr = THREADS ? THREADS : (int)blockDim.x;
     const int kc = pub.kc, lists = pub.lists;
     const int S = pub.P * lists;                    // kc <= S < kc + lists <= cap
     if (threadIdx.x == 0) { s_t0 = 0; s_t1 = 0; s_cnt = 0; }
@@ -104,10 +118,10 @@ __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_
     // consecutive keys of ONE region (coalesced), the warps rotate through the regions, and every region's first entries
     // (the only ones that exist when lists are short) come first.
     uint64_t kk[INFLIGHT];
-    const int per_round = INFLIGHT * (int)blockDim.x;
+    const int per_round = INFLIGHT * nthr;
 #pragma unroll
     for (int j = 0; j < INFLIGHT; ++j) {
-        const int sidx = threadIdx.x + j * blockDim.x;
+        const int sidx = (int)threadIdx.x + j * nthr;
         const int r = (sidx >> 5) % kPubRegions, e = (sidx / (32 * kPubRegions)) * 32 + (sidx & 31);
         kk[j] = e < pub.region_cap ? ldcg_u64(pub.keys + (size_t)r * pub.region_cap + e) : 0;
     }
@@ -139,14 +153,14 @@ __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_
         if (base > 0) {
 #pragma unroll
             for (int j = 0; j < INFLIGHT; ++j) {
-                const int sidx = base + threadIdx.x + j * blockDim.x;
+                const int sidx = base + (int)threadIdx.x + j * nthr;
                 const int r = (sidx >> 5) % kPubRegions, e = (sidx / (32 * kPubRegions)) * 32 + (sidx & 31);
                 kk[j] = (sidx < slots && e < (int)s_rtot[r]) ? ldcg_u64(pub.keys + (size_t)r * pub.region_cap + e) : 0;
             }
         }
 #pragma unroll
         for (int j = 0; j < INFLIGHT; ++j) {
-            const int sidx = base + threadIdx.x + j * blockDim.x;
+            const int sidx = base + (int)threadIdx.x + j * nthr;
             const int r = (sidx >> 5) % kPubRegions, e = (sidx / (32 * kPubRegions)) * 32 + (sidx & 31);
             // first batch: stale slots beyond the region size are dropped here.  One shared-memory atomic per WARP (ballot +
             // prefix count): a hundred survivors appending one by one would queue on the counter for microseconds.
@@ -183,13 +197,7 @@ __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_
         __syncthreads();
         return;
     }
-    int p2 = 2;
-    while (p2 < cnt || p2 < kc) p2 <<= 1;
-    for (int i = cnt + threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0;
-    __syncthreads();
-    block_bitonic_sort_desc(buf, p2);
-    for (int i = threadIdx.x; i < kc; i += blockDim.x) out[i] = buf[i];
-    __syncthreads();
+    sort_survivors(buf, cnt, kc, out);
 }
 
 // The same selection spread over the CTAs of a thread-block cluster (the request path's exact-pass kernel, long candidate
@@ -201,12 +209,12 @@ __device__ inline void select_winners(const PublishedKeys& pub, int cap, uint64_
 //       the range), cluster barrier,
 //   (4) ranks its 1/CSIZE slice of the survivors against all of them (4 threads per survivor) and stores each winner at its
 //       rank into every CTA's `out`, cluster barrier.
-// stage: 3 kc keys of scratch that nothing else uses until the winners are known (heads first, then the local survivors);
-// `out` may be its first kc entries.  s_total: one int per CTA, zero before a cluster barrier that precedes this call.
+// stage: stage_cap >= max(3 kc, kc + lists) keys of scratch that nothing else uses until the winners are known (heads first, then
+// the local survivors); `out` may be its first kc entries.  s_total: one int per CTA, zero before a cluster barrier that precedes this call.
 // Falls back to merge_all_regions (every CTA, redundantly) when the survivors overflow `buf` or a CTA's stage.
-template <int INFLIGHT, int CSIZE, typename Cluster>
-__device__ inline void select_winners_cluster(Cluster& cluster, const PublishedKeys& pub, int cap, uint64_t* buf, uint64_t* stage, uint64_t* out,
-                                              int* s_total, unsigned long long* tr = nullptr) {
+template <int INFLIGHT, int CSIZE, int THREADS, typename Cluster>
+__device__ inline void select_winners_cluster(Cluster& cluster, const PublishedKeys& pub, int cap, uint64_t* buf, uint64_t* stage, int stage_cap,
+                                              uint64_t* out, int* s_total, unsigned long long* tr = nullptr) {
     static_assert(kPubRegions % CSIZE == 0, "regions must divide over the cluster");
     constexpr int RPC = kPubRegions / CSIZE;        // regions scanned by one CTA
     __shared__ unsigned long long s_t0, s_t1;
@@ -215,8 +223,7 @@ __device__ inline void select_winners_cluster(Cluster& cluster, const PublishedK
     __shared__ int s_base[CSIZE];
     const int crank = (int)cluster.block_rank();
     const int kc = pub.kc, lists = pub.lists;
-    const int S = pub.P * lists;                    // kc <= S < kc + lists <= 3 kc (the caller checks)
-    const int stage_cap = 3 * kc;
+    const int S = pub.P * lists;                    // kc <= S < kc + lists <= stage_cap (the caller sizes the stage for it)
     if (threadIdx.x == 0) { s_t0 = 0; s_t1 = 0; s_cnt = 0; }
     if (threadIdx.x < kPubRegions) s_rtot[threadIdx.x] = __ldcg(pub.cursors + threadIdx.x);
     unsigned long long t0 = 0;
@@ -228,10 +235,11 @@ __device__ inline void select_winners_cluster(Cluster& cluster, const PublishedK
     // optimistic batch over this CTA's regions, flattened like select_winners: slot s = entry (s / (32 RPC)) * 32 + s % 32 of
     // region crank * RPC + (s / 32) % RPC
     uint64_t kk[INFLIGHT];
-    const int per_round = INFLIGHT * (int)blockDim.x;
+    constexpr int nthr = THREADS;
+    const int per_round = INFLIGHT * nthr;
 #pragma unroll
     for (int j = 0; j < INFLIGHT; ++j) {
-        const int sidx = threadIdx.x + j * blockDim.x;
+        const int sidx = (int)threadIdx.x + j * nthr;
         const int r = crank * RPC + (sidx >> 5) % RPC, e = (sidx / (32 * RPC)) * 32 + (sidx & 31);
         kk[j] = e < pub.region_cap ? ldcg_u64(pub.keys + (size_t)r * pub.region_cap + e) : 0;
     }
@@ -263,14 +271,14 @@ __device__ inline void select_winners_cluster(Cluster& cluster, const PublishedK
         if (base > 0) {
 #pragma unroll
             for (int j = 0; j < INFLIGHT; ++j) {
-                const int sidx = base + threadIdx.x + j * blockDim.x;
+                const int sidx = base + (int)threadIdx.x + j * nthr;
                 const int r = crank * RPC + (sidx >> 5) % RPC, e = (sidx / (32 * RPC)) * 32 + (sidx & 31);
                 kk[j] = (sidx < slots && e < (int)s_rtot[r]) ? ldcg_u64(pub.keys + (size_t)r * pub.region_cap + e) : 0;
             }
         }
 #pragma unroll
         for (int j = 0; j < INFLIGHT; ++j) {
-            const int sidx = base + threadIdx.x + j * blockDim.x;
+            const int sidx = base + (int)threadIdx.x + j * nthr;
             const int r = crank * RPC + (sidx >> 5) % RPC, e = (sidx / (32 * RPC)) * 32 + (sidx & 31);
             const bool keep = e < (int)s_rtot[r] && e < pub.region_cap && kk[j] >= T && kk[j] != 0;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
