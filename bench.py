@@ -575,11 +575,6 @@ def run_b200(args):
             want = expected_digest(f"batched-ids:{rows}x{DIM}:B4096:k100")
             if want is not None and isinstance(configs.get(name), dict) and "ids_digest" in configs[name]:
                 assert configs[name]["ids_digest"] == want, f"{name}: ids digest {configs[name]['ids_digest']} != committed {want}"
-    store._c8 = None                                     # free the shadow
-    store._q8_rows = store._q8_factor = None
-    if sharded is not None:
-        sharded.q8_eps = None
-    torch.cuda.empty_cache()
 
     # ---- C5 (N > 1): ragged-CSR profile build + genre/year-filtered top-50 over the sharded catalog
     def c5_leg():
@@ -619,12 +614,37 @@ def run_b200(args):
             t_step = time_device(lambda: store.enqueue_batch(plan, qbf, qn64, ept, ect, ws, *o, rf), 3, 1, barrier, world, dist, dev)
             nrerun = int((o[3] != 0).sum().item())
         flops = 2.0 * B * rows * DIM
-        return {"workload": f"C5: {world} x B200, {B} users (CSR, nnz_liked={len(lc)}), profile build + genre/year-filtered top-{K5} over {rows} x {DIM} bf16",
-                "profile_build_ms": t_prof, "score_filter_topk_ms": t_step, "users_per_s": B / ((t_prof + t_step) * 1e-3),
-                "tflops_scoring": flops / (t_step * 1e-3) / 1e12, "frac_of_measured_bf16_peak": flops / (t_step * 1e-3) / 1e12 / (pk["bf16"] * world),
-                "queries_flagged_for_rerun": nrerun, "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
+        out = {"workload": f"C5: {world} x B200, {B} users (CSR, nnz_liked={len(lc)}), profile build + genre/year-filtered top-{K5} over {rows} x {DIM} bf16",
+               "profile_build_ms": t_prof, "score_filter_topk_ms": t_step, "users_per_s": B / ((t_prof + t_step) * 1e-3),
+               "tflops_scoring": flops / (t_step * 1e-3) / 1e12, "frac_of_measured_bf16_peak": flops / (t_step * 1e-3) / 1e12 / (pk["bf16"] * world),
+               "queries_flagged_for_rerun": nrerun, "plan": {f: getattr(plan, f) for f, _ in plan._fields_}}
+        if store.batch_shadow_ok:
+            # the same step on int8 operands (the prefilter shadow, tcgen05 kind::i8): the ids of every user both passes prove must agree
+            if sharded is not None:
+                bf_rows, bf_status = ctx["m_rows"].clone(), status.clone()
+                ctx8 = sharded.batch_context(qbf, qn64, K5, ep, ec, rf, qn32=qn32)
+                t8 = time_device(lambda: sharded.batch_step(ctx8), 3, 1, barrier, world, dist, dev)
+                st8 = ctx8["gathered"][:, 2 * B * K5 + ctx8["hb"]:].contiguous().view(torch.int32)[:, :B].max(dim=0).values
+                rows8 = ctx8["m_rows"]
+            else:
+                bf_rows, bf_status = o[0].clone(), o[3].clone()
+                plan8 = store.gemm_plan(B, K5, shadow=True)
+                sh = store.quantize_queries(qn32)
+                ws8 = torch.empty(lib.rebert_gemm_workspace_bytes(C.byref(store._c), C.byref(plan8)), dtype=torch.uint8, device=dev)
+                t8 = time_device(lambda: store.enqueue_batch(plan8, qbf, qn64, ept, ect, ws8, *o, rf, shadow=sh), 3, 1, barrier, world, dist, dev)
+                st8, rows8 = o[3], o[0]
+            both = (bf_status == 0) & (st8 == 0)
+            assert bool((rows8[both] == bf_rows[both]).all().item()), "C5: int8 and bf16 operands disagree on a proven user"
+            out["int8_operands"] = {"score_filter_topk_ms": t8, "users_per_s": B / ((t_prof + t8) * 1e-3), "tflops_scoring": flops / (t8 * 1e-3) / 1e12,
+                                    "queries_flagged_for_rerun": int((st8 != 0).sum().item()), "users_proven_by_both_with_equal_ids": int(both.sum().item())}
+        return out
     if not args.no_batched:
         guarded("C5_csr_profiles_genre_year_top50", c5_leg)
+    store._c8 = None                                     # free the shadow
+    store._q8_rows = store._q8_factor = None
+    if sharded is not None:
+        sharded.q8_eps = None
+    torch.cuda.empty_cache()
 
     # ---- single-GPU configs measured on rank 0's GPU only at N = 1 (they do not shard: C1-C3 are one-GPU configs)
     if world == 1 and not args.no_configs:

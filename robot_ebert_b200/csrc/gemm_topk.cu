@@ -62,7 +62,6 @@ struct GemmParams {
     const float* inv_norm;
     DevFilter pred;         // per-row predicate (bitmap / genre / year); n_exclude is always 0 here
     int has_pred;
-    int l2_prefetch;        // 2-CTA kernel: prefetch the next wave's row tiles into L2 (REBERT_GEMM_L2_PREFETCH=0 turns it off)
     // MODE_STORE
     float* out;             // [b, out_ld], column = launch tile index * 256 + c
     int64_t out_ld;
@@ -152,33 +151,21 @@ constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_
 // filter compares acc * factor[row] against tau / qs (the caller passes that as `tau`), so the hot loop gains one I2F per
 // element and nothing else; only stored samples and staged winners are multiplied by qs.
 template <bool I8> __device__ __forceinline__ float acc_f32(uint32_t v) { return I8 ? __int2float_rn((int)v) : __uint_as_float(v); }
-// The filter's hot loop must not convert through I2FP: that instruction issues on the XU pipe, and ncu showed the int8 kernel
-// bound by it (XU 88 % busy, tensor pipe 77 %; profiles/r02_gemm2_filter_10M_int8_ncu_summary.md).  Adding the integer to the bit
-// pattern of 1.5 * 2^23 and subtracting that constant is one IADD + one FADD on the full-rate pipes, exact for |x| < 2^22 and NEVER
-// BELOW the exact value outside that range (x >= 2^22 lands in a binade with a coarser step and comes out as 2^22 + 2(x - 2^22) or
-// more; x < -2^22 comes out as -2^22 - (|x| - 2^22) / 2).  So "max of the fast values <= tau" still proves that no element of
-// the chunk passes, and the rare chunk that may hold a winner re-converts the elements it stages exactly.
-__device__ __forceinline__ float i32_to_f32_upper(uint32_t v) { return __uint_as_float(v + 0x4B400000u) - 12582912.0f; }
+// (Tried and measured slower, same box: replacing the I2FP — it issues on the XU pipe, which ncu showed 88 % busy — by an integer add
+// onto the bit pattern of 1.5 * 2^23 plus an FADD, which run on the main pipes: 7.44 vs 7.21 ms at 4096 x 1M.  The kernel sits at the
+// board's power limit, where two instructions on the main pipes cost more than one on an idle pipe saves.  DESIGN.md 4.3.)
 
 template <int MODE, bool I8>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, const float* inv_chunk, float tau, float qs, int q,
                                                float* out_row, uint32_t row_chunk0, uint64_t* staging, int et, int& cnt) {
-    constexpr bool FASTCVT = I8 && MODE == MODE_FILTER;
     float s[32];
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
         const float4 iv = ((const float4*)inv_chunk)[c4];
-        if (FASTCVT) {
-            s[c4 * 4 + 0] = i32_to_f32_upper(v[c4 * 4 + 0]) * iv.x;
-            s[c4 * 4 + 1] = i32_to_f32_upper(v[c4 * 4 + 1]) * iv.y;
-            s[c4 * 4 + 2] = i32_to_f32_upper(v[c4 * 4 + 2]) * iv.z;
-            s[c4 * 4 + 3] = i32_to_f32_upper(v[c4 * 4 + 3]) * iv.w;
-        } else {
-            s[c4 * 4 + 0] = acc_f32<I8>(v[c4 * 4 + 0]) * iv.x;
-            s[c4 * 4 + 1] = acc_f32<I8>(v[c4 * 4 + 1]) * iv.y;
-            s[c4 * 4 + 2] = acc_f32<I8>(v[c4 * 4 + 2]) * iv.z;
-            s[c4 * 4 + 3] = acc_f32<I8>(v[c4 * 4 + 3]) * iv.w;
-        }
+        s[c4 * 4 + 0] = acc_f32<I8>(v[c4 * 4 + 0]) * iv.x;
+        s[c4 * 4 + 1] = acc_f32<I8>(v[c4 * 4 + 1]) * iv.y;
+        s[c4 * 4 + 2] = acc_f32<I8>(v[c4 * 4 + 2]) * iv.z;
+        s[c4 * 4 + 3] = acc_f32<I8>(v[c4 * 4 + 3]) * iv.w;
     }
     if (MODE == MODE_STORE) {
         if (q < p.b) {
@@ -202,18 +189,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             while (mask) {
                 const int c = __ffs(mask) - 1;
                 mask &= mask - 1;
-                float val;
-                if (FASTCVT) {                                                  // exact conversion of the element that is staged
-                    uint32_t raw = v[0];
+                float val = s[0];
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) raw = (c == j) ? v[j] : raw;   // register select, no local memory
-                    val = __int2float_rn((int)raw) * inv_chunk[c];
-                    if (!(val > tau)) continue;                                 // only an out-of-range accumulator gets here
-                } else {
-                    val = s[0];
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) val = (c == j) ? s[j] : val;
-                }
+                for (int j = 1; j < 32; ++j) val = (c == j) ? s[j] : val;       // register select, no local memory
                 REBERT_ASSERT(et >= 0 && et < 128 && (int64_t)(row_chunk0 + (uint32_t)c) < p.n);
                 if (cnt < STAGE_SLOTS) staging[cnt * 128 + et] = make_key(I8 ? val * qs : val, row_chunk0 + (uint32_t)c);
                 ++cnt;
@@ -404,10 +382,6 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar), "l"(policy)
         : "memory");
 }
-// Pull the box a later TMA load will fetch into L2 (no shared memory, no barrier).
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"((uint16_t)3)
@@ -480,20 +454,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             const uint64_t pol_rows = l2_policy_evict_normal();
             const uint64_t pol_q = l2_policy_evict_last();
             uint32_t it = 0;
-            // All query tiles of a row tile run in the same wave, so every cluster meets its catalog rows at DRAM latency and the
-            // int8 path (a k-block is consumed in 0.33 us, six stages hold 2 us) was exposed to it.  The cluster working on query
-            // tile 0 therefore pulls the row tile that the NEXT wave will read into L2 while it streams its own.
-            const int64_t pf_dist = num_clusters / num_qt2 + 1;
             for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
                 const int64_t rt = t / num_qt2;
                 const int qt = (int)(t - rt * num_qt2);
                 const int row0 = (int)((p.tile0 + rt * p.tile_stride) * BN) + (int)cta_rank * 128;
                 const int q0 = qt * 256 + (int)cta_rank * 128;
-                const bool pf = p.l2_prefetch && qt == 0 && rt + pf_dist < p.num_rt;
-                const int pf_row0 = (int)((p.tile0 + (rt + pf_dist) * p.tile_stride) * BN) + (int)cta_rank * 128;
                 for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
                     const int s = it % G2_STAGES;
-                    if (pf) tma_prefetch_2d(&map_rows, kb * BKE, pf_row0);
                     mbar_wait(&empty_bar[s], ((it / G2_STAGES) & 1u) ^ 1u);
                     unsigned char* sa = stages + s * G2_STAGE_BYTES;
                     const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);        // the leader's full barrier
@@ -850,8 +817,6 @@ static int launch_gemm_t(const rebert_catalog_t* cat, const void* qmat, GemmPara
     p.n = cat->n;
     p.inv_norm = cat->inv_norm;
     p.num_qt = (p.b + BM - 1) / BM;
-    static const int l2_prefetch = [] { const char* e = getenv("REBERT_GEMM_L2_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
-    p.l2_prefetch = l2_prefetch;
     if (pair) {
         const int64_t tiles = (int64_t)p.num_rt * ((p.b + 255) / 256);
         int grid = num_sms() & ~1;

@@ -245,10 +245,10 @@ def test_int8_batched_profiles_with_predicate_vs_oracle():
         np.testing.assert_allclose(scores[u, :counts[u]], want_scores, rtol=1e-9, atol=1e-15)
 
 
-def test_int8_filter_with_accumulators_beyond_the_fast_conversion_range():
-    """Rows and queries of +-1 entries quantise to +-127 everywhere, so the int32 accumulators reach 1536 * 127^2 = 24.8M: far outside
-    the +-2^22 range in which the filter's pipe-friendly int->float conversion is exact.  Outside it the conversion only ever
-    over-estimates, and staged winners are re-converted exactly — the results must still equal the bf16 path's and the oracle's."""
+def test_int8_filter_with_saturated_accumulators():
+    """Rows and queries of +-1 entries quantise to +-127 everywhere, so the int32 accumulators reach 1536 * 127^2 = 24.8M (beyond
+    fp32's 24-bit integers: the int->float conversion of the epilogue rounds there) and the shadow is exact — the proof's error
+    bound collapses to its floor.  The results must still equal the bf16 path's and the oracle's."""
     n, d, b, k = 70_000, 1536, 140, 10
     rng = np.random.default_rng(11)
     base = rng.integers(0, 2, size=(b, d)).astype(np.float32) * 2 - 1
