@@ -300,8 +300,13 @@ __global__ void __launch_bounds__(256) stage_profile_kernel(const T* __restrict_
     // a kernel that waits for a peer lets its dependents in only after that wait (see finalize_published_kernel)
     if (x.world <= 1) pdl_trigger();
     pdl_wait();
-    copy_list_zero_copy(excl_host, n_excl, excl_dev);
-    profile_accumulate_cta<T, true, 16>(rows, norm64, n, row_base, ld, liked_host, w_host, n_liked, sum64, wsum);
+    // One GPU: the grid splits the row's 16-byte column chunks (one SM's fp64 unit made an 82-row profile a 20 us step); every
+    // CTA owns its columns from the accumulation to the division.  Row shard: one CTA, the exchange needs the whole vector.
+    constexpr int EPC = RowChunk<T>::EPC;
+    const int chunks = ld / EPC;
+    const int lo = (int)((int64_t)chunks * blockIdx.x / gridDim.x), hi = (int)((int64_t)chunks * (blockIdx.x + 1) / gridDim.x);
+    if (blockIdx.x == 0) copy_list_zero_copy(excl_host, n_excl, excl_dev);
+    profile_accumulate_cta<T, true, 16>(rows, norm64, n, row_base, ld, liked_host, w_host, n_liked, sum64, wsum, lo, hi);
     __syncthreads();
     if (x.world > 1) {
         exchange_profile(x, ld, sum64, sum64);
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(256) stage_profile_kernel(const T* __restrict_
         __syncthreads();
     }
     const double ws = wsum[0];
-    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    for (int c = lo * EPC + threadIdx.x; c < hi * EPC; c += blockDim.x) {
         const double v = ws != 0.0 ? sum64[c] / ws : 0.0;
         qn64[c] = v;
         qn32[c] = (float)v;
@@ -322,11 +327,15 @@ int stage_profile_launch(const rebert_catalog_t* cat, const int32_t* liked_host,
     Exchange xe;
     memset(&xe, 0, sizeof(xe));
     if (x) xe = *x;
+    const int chunks = cat->ld * (cat->dtype == REBERT_F32 ? 4 : 2) / 16;
+    int grid = (x && x->world > 1) ? 1 : (chunks + 31) / 32;                 // a warp's worth of column chunks per CTA
+    if (grid > 16) grid = 16;
+    if (grid < 1) grid = 1;
     if (cat->dtype == REBERT_F32)
-        REBERT_CUDA(launch_pdl(stage_profile_kernel<float>, dim3(1), dim3(256), 0, st, (const float*)cat->rows, cat->norm64, cat->n,
+        REBERT_CUDA(launch_pdl(stage_profile_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)cat->rows, cat->norm64, cat->n,
                                cat->row_base, cat->ld, liked_host, w_host, n_liked, excl_host, n_excl, excl_dev, sum64, wsum, qn32, qn64, xe));
     else
-        REBERT_CUDA(launch_pdl(stage_profile_kernel<__nv_bfloat16>, dim3(1), dim3(256), 0, st, (const __nv_bfloat16*)cat->rows, cat->norm64,
+        REBERT_CUDA(launch_pdl(stage_profile_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)cat->rows, cat->norm64,
                                cat->n, cat->row_base, cat->ld, liked_host, w_host, n_liked, excl_host, n_excl, excl_dev, sum64, wsum, qn32,
                                qn64, xe));
     return REBERT_OK;

@@ -93,7 +93,10 @@ template <typename T, bool DIV, int INFLIGHT = 4>
 __device__ __forceinline__ void profile_accumulate_cta(const T* __restrict__ rows, const double* __restrict__ norm64, int64_t n,
                                                        int64_t row_base, int ld, const int32_t* __restrict__ col,
                                                        const float* __restrict__ w, int count, double* __restrict__ sum64,
-                                                       double* __restrict__ wsum) {
+                                                       double* __restrict__ wsum, int chunk_lo = 0, int chunk_hi = 0x7fffffff) {
+    // [chunk_lo, chunk_hi): the 16-byte column chunks this CTA accumulates and writes.  Columns are independent and every column
+    // walks the rows in list order, so splitting them over several CTAs (single request: one SM's fp64 unit is the bottleneck)
+    // changes no bit; the weight sum is computed by every CTA in full, with the same thread layout.
     constexpr int EPC = RowChunk<T>::EPC;
     __shared__ int s_row[kProfBlock];
     __shared__ double s_w[kProfBlock];      // weight (DIV) or weight / norm (!DIV)
@@ -125,7 +128,7 @@ __device__ __forceinline__ void profile_accumulate_cta(const T* __restrict__ row
 #pragma unroll
         for (int it = 0; it < kProfMaxIter; ++it) {
             const int g = it * (int)blockDim.x + (int)threadIdx.x;
-            if (g >= chunks) continue;
+            if (g >= chunks || g < chunk_lo || g >= chunk_hi) continue;
             for (int i = 0; i < nb; i += INFLIGHT) {
                 uint4 v[INFLIGHT];
                 int rr[INFLIGHT];
@@ -151,7 +154,7 @@ __device__ __forceinline__ void profile_accumulate_cta(const T* __restrict__ row
 #pragma unroll
     for (int it = 0; it < kProfMaxIter; ++it) {
         const int g = it * (int)blockDim.x + (int)threadIdx.x;
-        if (g >= chunks) continue;
+        if (g >= chunks || g < chunk_lo || g >= chunk_hi) continue;
 #pragma unroll
         for (int t = 0; t < EPC; ++t) sum64[(int64_t)g * EPC + t] = acc[it][t];
     }
