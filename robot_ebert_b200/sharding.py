@@ -71,6 +71,7 @@ class CudaShardBackend:
         self._seq = [0]
         self._nccl_lock = threading.Lock()      # the NCCL fallback keeps per-process buffers: one request at a time
         self._err = {}
+        self._xstructs = {}                     # channel -> its reusable rebert_exchange_t
 
     def setup_p2p(self, group=None, channels: Optional[int] = None) -> bool:
         """Map one symmetric buffer per rank (torch symmetric memory = CUDA VMM + fabric handles) holding `channels`
@@ -92,6 +93,7 @@ class CudaShardBackend:
             self._symm_buf, self._symm_hdl = buf, hdl
             self._peer_ptrs = (C.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
             self._p2p_out = {}
+            self._xstructs = {}
             self._p2p_world, self._p2p_rank = world, rank
             ok.fill_(1)
         except Exception as e:  # noqa: BLE001 - any failure of the plumbing means: keep NCCL
@@ -119,10 +121,15 @@ class CudaShardBackend:
         return self.exchange == "p2p"
 
     def exchange_struct(self, channel: int, seq: int) -> "nat.Exchange":
-        x = nat.Exchange()
-        x.peer_buffers = C.cast(self._peer_ptrs, C.c_void_p)
-        x.world, x.rank, x.k_max, x.prof_len = self._p2p_world, self._p2p_rank, self.K_MAX, self.store.ld
-        x.channels, x.channel, x.seq = self.channels, channel, (seq & 0xFFFFFFFF) or 1
+        """This rank's rebert_exchange_t for one call on `channel` (the caller holds the channel's lock, so the channel's
+        struct is reused: only the sequence number changes from call to call)."""
+        x = self._xstructs.get(channel)
+        if x is None:
+            x = self._xstructs[channel] = nat.Exchange()
+            x.peer_buffers = C.cast(self._peer_ptrs, C.c_void_p)
+            x.world, x.rank, x.k_max, x.prof_len = self._p2p_world, self._p2p_rank, self.K_MAX, self.store.ld
+            x.channels, x.channel = self.channels, channel
+        x.seq = (seq & 0xFFFFFFFF) or 1
         return x
 
     def next_seq(self, channel: int, n: int = 1) -> int:
@@ -250,6 +257,7 @@ class ShardedCatalog:
         self.ids = list(ids) if ids is not None else None
         self._row_of = None
         self._locks = [threading.Lock() for _ in range(max(1, getattr(backend, "channels", 1)))]
+        self._kc_for_k = {}
         self.q8_eps = None
 
     @classmethod
@@ -386,8 +394,9 @@ class ShardedCatalog:
                                           channel, p2p)
 
     def _recommend_locked(self, query, liked_rows, weights, exclude_rows, k, row_filter, return_info, prefilter, channel, p2p):
-        lib = nat.load()
-        kc = lib.rebert_candidates_for_k(k)
+        kc = self._kc_for_k.get(k)
+        if kc is None:
+            kc = self._kc_for_k[k] = nat.load().rebert_candidates_for_k(k)
         eps = getattr(getattr(self.backend, "store", None), "fast_eps", 0.0)
         if kc == 0:
             # k beyond the register-list kernel (k > 240): sharded threshold bisection + sweep, still exact (slower route)
