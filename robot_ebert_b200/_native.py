@@ -122,6 +122,26 @@ def load() -> C.CDLL:
     return lib
 
 
+_fast_call = False      # False = not looked up yet, None = unavailable
+
+
+def fast_recommend_host():
+    """robot_ebert_b200._pycall.recommend_host bound to the loaded library's rebert_recommend_host (csrc/pycall.c), or None
+    when that optional module has not been built — the caller then makes the same call through ctypes.
+    REBERT_PYCALL=0 forces the ctypes route."""
+    global _fast_call
+    if _fast_call is False:
+        _fast_call = None
+        if os.environ.get("REBERT_PYCALL", "1") != "0":
+            try:
+                from . import _pycall
+                _pycall.set_entry(C.cast(load().rebert_recommend_host, C.c_void_p).value)
+                _fast_call = _pycall.recommend_host
+            except ImportError:
+                pass
+    return _fast_call
+
+
 def exported_symbols():
     return list(_SIGS)
 

@@ -85,5 +85,28 @@ def build_native(force: bool = False, verbose: bool = False, debug: bool = False
     return lib_path
 
 
+def build_pycall(force: bool = False) -> str:
+    """Compile csrc/pycall.c (CPython side door into rebert_recommend_host: saves the ctypes call overhead on the request
+    path) with the host C compiler into robot_ebert_b200/_pycall<EXT_SUFFIX>.  Optional: without it the same call goes
+    through ctypes."""
+    import sysconfig
+    src = os.path.join(CSRC, "pycall.c")
+    out = os.path.join(PKG, "_pycall" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+    stamp = os.path.join(OBJ, "pycall.stamp")
+    os.makedirs(OBJ, exist_ok=True)
+    want = _digest([src], sysconfig.get_paths()["include"])
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == want:
+        return out
+    cc = os.environ.get("CC", "gcc")
+    cmd = [cc, "-O2", "-std=c11", "-Wall", "-Wextra", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], src, "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"{cc} failed for {src}:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(want)
+    return out
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))
+    print(build_pycall(force="--force" in sys.argv))

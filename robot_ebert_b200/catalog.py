@@ -50,6 +50,9 @@ class _Scratch:
         self.qn64 = torch.zeros(ld, dtype=torch.float64, device=dev)
         self.sum64 = torch.zeros(ld, dtype=torch.float64, device=dev)
         self.wsum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.info = nat.RequestInfo()                 # reused: one request at a time per scratch (thread / channel)
+        self.info_addr = C.addressof(self.info)
+        self.last_attempts = 0
 
     def ensure_host(self, n_liked: int, n_excl: int, k: int):
         """Pinned + device scratch of rebert_recommend_host.  Sized once for any k of the single-request path (256) and lists
@@ -219,6 +222,7 @@ class CatalogStore:
         self._c8 = None            # int8 prefilter shadow (enable_prefilter)
         self.q8_eps = float("inf")
         self._dev_index = self.device.index if self.device.index is not None else 0
+        self._c_addr = C.addressof(self._c)
         self._plain_proof = nat.Proof()      # read-only, shared by every request that does not try the shadow
         self._plain_proof.fast_eps, self._plain_proof.widen = self.fast_eps, 1
         self._kc_for_k = {}
@@ -370,8 +374,6 @@ class CatalogStore:
             raise ValueError("pass exactly one of query / liked_rows")
         if k <= 0:
             raise ValueError("k must be positive")
-        if query is not None and np.asarray(query).shape != (self.d,):
-            raise ValueError(f"query must have shape ({self.d},)")
         lib = nat.load()
         kc = self._kc_for_k.get(k)
         if kc is None:
@@ -512,22 +514,31 @@ class CatalogStore:
             proof.shadow_max_k = shadow_max_k
         else:
             proof = self._plain_proof
-        cnt, info = C.c_int32(0), nat.RequestInfo()
         # bytes the kernels fetch from / write to the pinned block over PCIe (zero-copy: no copy-engine operation)
         self.last_h2d_bytes = (4 * d if lk is None else 4 * nl * (2 if w is not None else 1)) + 4 * ne
         self.last_d2h_bytes = 8 * (2 * k + 2)
         with _on_device(self.device):                 # a serving thread's current device is 0 until it says otherwise
             s = scratch if scratch is not None else self._scratch()
             s.ensure_host(nl, ne, k)
-            rc = lib.rebert_recommend_host(
-                C.byref(self._c), None if q is None else q.ctypes.data, None if lk is None else lk.ctypes.data,
-                None if w is None else w.ctypes.data, nl, None if ex is None else ex.ctypes.data, ne,
-                None if f is None else C.byref(f), k, kc, s.nl_cap, s.ne_cap, *s.host_args,
-                C.byref(proof), None if exchange is None else C.byref(exchange), *s.out_args, C.byref(cnt), C.byref(info),
-                _raw_stream(self._dev_index))
+            info = s.info
+            info.attempts = 0                         # an argument error returns before the C entry writes it
+            fast = nat.fast_recommend_host()
+            if fast is not None:
+                # same C entry point, called through the CPython module instead of ctypes (csrc/pycall.c)
+                rc, n = fast(self._c_addr, q, lk, w, ex, 0 if f is None else C.addressof(f), k, kc, s.nl_cap, s.ne_cap, *s.host_args,
+                             C.addressof(proof), 0 if exchange is None else C.addressof(exchange), *s.out_args, s.info_addr,
+                             _raw_stream(self._dev_index))
+            else:
+                cnt = C.c_int32(0)
+                rc = lib.rebert_recommend_host(
+                    C.byref(self._c), None if q is None else q.ctypes.data, None if lk is None else lk.ctypes.data,
+                    None if w is None else w.ctypes.data, nl, None if ex is None else ex.ctypes.data, ne,
+                    None if f is None else C.byref(f), k, kc, s.nl_cap, s.ne_cap, *s.host_args,
+                    C.byref(proof), None if exchange is None else C.byref(exchange), *s.out_args, C.byref(cnt), C.byref(info),
+                    _raw_stream(self._dev_index))
+                n = cnt.value
         s.last_attempts = int(info.attempts)         # exchange sequence numbers consumed, also when the call failed (per thread)
         nat.check(rc)
-        n = cnt.value
         return s.h_rows[:n].copy(), s.h_scores[:n].copy(), {
             "kc": info.kc, "margin": info.margin, "proven_exact": bool(info.proven), "exact_sweep": False,
             "prefilter": bool(info.used_shadow), "attempts": info.attempts,

@@ -161,3 +161,33 @@ def test_header_is_plain_c_and_library_links_from_c(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "c_embed ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_pycall_module_validates_its_arguments_without_a_gpu():
+    """csrc/pycall.c is the CPython side door into rebert_recommend_host (saves the ctypes call overhead per request).  Without a
+    GPU the C entry refuses a NULL catalog before touching anything, which is enough to drive the module's own argument handling:
+    buffers of the wrong item size, mismatched weights, negative addresses, wrong arity."""
+    import ctypes as C
+    fast = nat.fast_recommend_host()
+    assert fast is not None, "robot_ebert_b200/_pycall*.so missing: run __graft_entry__.build()"
+    proof, info = nat.Proof(), nat.RequestInfo()
+    q = np.zeros(32, dtype=np.float32)
+    ex = np.arange(45, dtype=np.int32)
+    lk = np.arange(5, dtype=np.int32)
+    rows, scores = np.empty(16, dtype=np.int64), np.empty(16, dtype=np.float64)
+    tail = (0, 10, 32, 64, 64, 1, 1, 1, 1, C.addressof(proof), 0, rows.ctypes.data, scores.ctypes.data, C.addressof(info), 0)
+    rc, n = fast(0, q, None, None, ex, *tail)                       # cat = NULL: refused by the library, not by the module
+    assert rc == nat.ERR_INVALID and n == 0 and b"null argument" in nat.load().rebert_last_error()
+    assert fast(0, None, lk, np.ones(5, dtype=np.float32), None, *tail)[0] == nat.ERR_INVALID
+    with pytest.raises(TypeError):
+        fast(0, np.zeros(4, dtype=np.float64), None, None, None, *tail)      # 8-byte items
+    with pytest.raises(ValueError):
+        fast(0, None, lk, np.ones(3, dtype=np.float32), None, *tail)         # weights do not match liked rows
+    with pytest.raises(TypeError):
+        fast(0, "abc", None, None, None, *tail)
+    with pytest.raises(OverflowError):
+        fast(-1, q, None, None, None, *tail)
+    with pytest.raises(TypeError):
+        fast(0, q)
+    with pytest.raises(ValueError):
+        fast(0, q[::2], None, None, None, *tail)                              # not contiguous
