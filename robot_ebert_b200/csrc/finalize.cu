@@ -242,8 +242,9 @@ int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t 
     // cluster barriers.  REBERT_FIN_SPLIT=0/1 forces either way (tools).
     {
         static const int forced = [] { const char* e = getenv("REBERT_FIN_SPLIT"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+        static const bool tuning = getenv("REBERT_GEMV_TUNE") != nullptr;      // read once: getenv is a linear scan, this is the request path
         int want = forced;
-        if (getenv("REBERT_GEMV_TUNE")) { const char* e = getenv("REBERT_FIN_SPLIT"); want = e ? (e[0] == '0' ? 0 : 1) : -1; }
+        if (tuning) { const char* e = getenv("REBERT_FIN_SPLIT"); want = e ? (e[0] == '0' ? 0 : 1) : -1; }
         p.split_select = (want < 0 ? pub.keys.kc >= 128 : want == 1) ? 1 : 0;
     }
     p.stage_words = 3 * pub.keys.kc > pub.keys.kc + pub.keys.lists ? 3 * pub.keys.kc : pub.keys.kc + pub.keys.lists;
