@@ -69,7 +69,8 @@ finalize_topk_kernel(const T* __restrict__ rows, const double* __restrict__ norm
 // ---------------------------------------------------------------------------------------------------------
 // Request path, second (and last) launch: a CLUSTER of 8 CTAs placed behind the streaming kernel by programmatic dependent
 // launch.  The streaming kernel's CTAs have published their pruned candidate keys (gemv_topk.cu); here
-//   (1) every CTA selects the kc winners from them (redundantly — 30 KB of keys, cheaper than any cross-CTA step),
+//   (1) the kc winners are selected from them: short lists (kc < 128) by every CTA redundantly — <= 38 KB of keys, one round of
+//       loads, cheaper than any cross-CTA step —, long lists by the cluster together (select_winners_cluster, merge.cuh),
 //   (2) the winners are dealt out over the 8 x 8 warps of the cluster for the fp64 exact pass — one row per warp, on 8 SMs,
 //       instead of a queue of rows behind one SM's fp64 unit — and each warp stores its score straight into CTA 0's shared
 //       memory (distributed shared memory),
