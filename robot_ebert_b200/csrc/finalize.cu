@@ -91,7 +91,7 @@ struct FinalizeParams {
     int64_t row_base, x_n;
     int k, cap;
     int stage_words;           // words from fk on that are free until the winners are known: max(3 kc, heads of every list)
-    int split_select;          // 1: winner selection spread over the cluster (long candidate lists), 0: every CTA on its own
+    int split_select;          // 0: every CTA selects on its own; 1 / 2: selection spread over the cluster (24 / 4 key loads in flight)
     unsigned long long* out_packed;
     uint32_t tag;
     uint32_t* done_flag;       // pinned host word the host polls instead of synchronising the stream (or nullptr)
@@ -107,9 +107,12 @@ __device__ __forceinline__ unsigned long long ftimer_ns() {
 #define FIN_TRACE(slot) do { if (p.pub.trace && threadIdx.x == 0 && crank == 0) p.pub.trace[(slot)] = ftimer_ns(); } while (0)
 
 // SPLIT: winner selection spread over the cluster (long candidate lists); XCHG: row shard, NVLink exchange + merge at the end.
-// Four instantiations instead of run-time branches: this kernel runs once per request with a cold instruction cache, and
+// Eight instantiations (with the element type) instead of run-time branches: this kernel runs once per request with a cold instruction cache, and
 // every variant it does not need (each one thousands of unrolled instructions) would sit between the ones it does.
-template <bool SPLIT, bool XCHG>
+// T: element type of the catalog of record — the exact pass carries one row function instead of both.
+// SPLIT: 0 = every CTA selects on its own, 1 = cluster-wide with 24 key loads in flight per thread (kc >= 128), 2 = cluster-wide
+// with 4 in flight (kc <= 64: a CTA's two regions hold <= 5 keys per thread; a sixth of the unrolled code).
+template <int SPLIT, bool XCHG, typename T>
 __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_kernel(const FinalizeParams p) {
     extern __shared__ __align__(16) unsigned char fsm[];
     const int kc = p.pub.keys.kc, k = p.k;
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
     // (Waiting on the CTAs' publish counter instead would start 1-3 us earlier, but a cluster placed early by programmatic
     // launch could then mistake the PREVIOUS request's count for its own; stream order is the simple, safe hand-off.)
     FIN_TRACE(1);
-    const int epc = p.x_dtype == REBERT_F32 ? 4 : 8;
+    constexpr int epc = ChunkDot<T>::EPC;
     // the fp64 query: its loads are issued here, ahead of the ones select_winners issues, and consumed only afterwards —
     // one L2 round trip for everything this kernel reads before the candidate rows
     constexpr int kQPre = 8;
@@ -152,7 +155,10 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
         const int i = threadIdx.x + j * kFinalClusterThreads;
         qv[j] = i < p.x_ld ? __ldg(p.q64 + i) : 0.0;
     }
-    if (SPLIT)               // fk | s_score | s_row = 3 kc words that are free until the winners are known
+    if (SPLIT == 2)
+        select_winners_cluster<4, kFinalCluster, kFinalClusterThreads>(cluster, p.pub.keys, p.cap, buf, fk, p.stage_words, fk, &s_total,
+                                                                       (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
+    else if (SPLIT == 1)     // fk | s_score | s_row = 3 kc words that are free until the winners are known
         select_winners_cluster<24, kFinalCluster, kFinalClusterThreads>(cluster, p.pub.keys, p.cap, buf, fk, p.stage_words, fk, &s_total, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
     else
         select_winners<24, kFinalClusterThreads>(p.pub.keys, p.cap, buf, fk, (p.pub.trace && crank == 0) ? p.pub.trace + 8 : nullptr);
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(kFinalClusterThreads, 2) finalize_published_ke
         if (key != 0) {
             const uint32_t lr = key_row(key);
             REBERT_ASSERT((int64_t)lr < p.x_n && c < kc);
-            sc = exact_score_row_rt(p.x_rows, p.x_dtype, p.x_ld, p.x_norm64, lr, qsrc, lane);
+            sc = exact_score_row<T, true>((const T*)p.x_rows, p.x_ld, p.x_norm64, lr, qsrc, lane);
             gr = p.row_base + lr;
             werr = fmax(werr, fabs(sc - (double)key_score(key)));
         }
@@ -246,7 +252,7 @@ int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t 
         static const bool tuning = getenv("REBERT_GEMV_TUNE") != nullptr;      // read once: getenv is a linear scan, this is the request path
         int want = forced;
         if (tuning) { const char* e = getenv("REBERT_FIN_SPLIT"); want = e ? (e[0] == '0' ? 0 : 1) : -1; }
-        p.split_select = (want < 0 ? pub.keys.kc >= 128 : want == 1) ? 1 : 0;
+        p.split_select = (want < 0 ? pub.keys.kc >= 128 : want == 1) ? (pub.keys.kc >= 128 ? 1 : 2) : 0;
     }
     p.stage_words = 3 * pub.keys.kc > pub.keys.kc + pub.keys.lists ? 3 * pub.keys.kc : pub.keys.kc + pub.keys.lists;
     p.out_packed = f.out_packed;
@@ -257,8 +263,14 @@ int finalize_published_launch(const Published& pub, const GemvFused& f, int64_t 
     const size_t smem = (size_t)p.x_ld * 8 + (size_t)cap * 8 + (size_t)p.stage_words * 8 + (size_t)kFinalCluster * (kFinalClusterThreads / 32) * 8 +
                         (size_t)(2 * f.k + 2) * 8 * (1 + (f.xchg ? f.xchg->world : 0));
     const bool xchg = p.xchg.world > 1;
-    auto kern = p.split_select ? (xchg ? finalize_published_kernel<true, true> : finalize_published_kernel<true, false>)
-                               : (xchg ? finalize_published_kernel<false, true> : finalize_published_kernel<false, false>);
+    void (*kern)(const FinalizeParams) = nullptr;
+#define REBERT_FIN_PICK(TT)                                                                                                         \
+    kern = p.split_select == 2 ? (xchg ? finalize_published_kernel<2, true, TT> : finalize_published_kernel<2, false, TT>)           \
+         : p.split_select == 1 ? (xchg ? finalize_published_kernel<1, true, TT> : finalize_published_kernel<1, false, TT>)           \
+                               : (xchg ? finalize_published_kernel<0, true, TT> : finalize_published_kernel<0, false, TT>)
+    if (p.x_dtype == REBERT_F32) REBERT_FIN_PICK(float);
+    else REBERT_FIN_PICK(__nv_bfloat16);
+#undef REBERT_FIN_PICK
     { int rc = raise_smem_limit(kern); if (rc != REBERT_OK) return rc; }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

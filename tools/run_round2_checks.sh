@@ -1,6 +1,8 @@
-# one GPU box: the full GPU suite (request path through the CPython side door), a slice of it through ctypes, the latency breakdown, the bench line
-timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -30 > gpurun_out/r2_gpu_tests9.log; tail -3 gpurun_out/r2_gpu_tests9.log
-REBERT_PYCALL=0 timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "vs_oracle or ties or concurrent" 2>&1 | tail -3
-python tools/latency_breakdown.py > gpurun_out/r2_latency5.log 2>&1; cat gpurun_out/r2_latency5.log | cut -c1-700
-python -c "import __graft_entry__ as g; g.smoke()"
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench7.json 2> gpurun_out/r2_bench7.err; tail -c 400 gpurun_out/r2_bench7.err; head -c 300 gpurun_out/r2_bench7.json
+# one GPU box: the full GPU suite, then the exact-pass kernel's selection variants side by side (traces + end-to-end latency)
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -30 > gpurun_out/r2_gpu_tests10.log; tail -3 gpurun_out/r2_gpu_tests10.log
+run() { if [ "$1" = default ]; then shift; env -u REBERT_FIN_SPLIT "$@"; else shift; env REBERT_FIN_SPLIT=1 "$@"; fi; }
+{
+for v in default split; do for a in "1250000 10 fused" "2264 10 fused" "2269 10 fused dim=32 fp32"; do echo "## $v: trace_gemv.py $a"; run $v python tools/trace_gemv.py $a 2>&1 | cut -c1-1500 | sed -n 2,6p; done; done
+} > gpurun_out/r2_trace8.log 2>&1
+grep -A3 "^##" gpurun_out/r2_trace8.log | grep -o '^##.*\|"event_us_per_launch[^}]*\|"cluster_kernel.*' | cut -c1-330
+for v in default split; do echo "== $v"; run $v python tools/latency_breakdown.py 2269 32 fp32 | cut -c1-420; run $v python tools/latency_breakdown.py 1250000 1536 bf16 | cut -c1-420; done 2>&1 | tee gpurun_out/r2_latency6.log
